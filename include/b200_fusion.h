@@ -1,0 +1,201 @@
+/* b200_fusion.h -- C ABI of libb200fusion.so: hand-written sm_100a kernels for the fusion hot
+ * path of nl1xx/simple-multimodal (models/fusion_layers.py + models/encoders.py:280-321).
+ *
+ * The reference has no FFI, plugin registry or operator API: its boundary is the
+ * Python nn.Module contract consumed by models/multimodal_model.py:29-46,110-144.  This header is
+ * the build-defined C boundary underneath that contract; each entry point names the reference
+ * arithmetic it replaces.  The Python host (simple-multimodal_b200/) binds it with ctypes.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every pointer is DEVICE memory owned by the caller (PyTorch's
+ *     caching allocator in practice) unless stated otherwise; the library allocates nothing
+ *     persistent and keeps no pointer after return.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no internal sync.
+ *   - return 0 (B200F_OK) or a b200f_status; never throws, never exits; b200f_last_error() gives
+ *     a thread-local message for the last non-zero return.
+ *   - dtype: B200F_F32 = fp32 storage and CUDA-core FFMA arithmetic (parity mode, rtol 1e-5);
+ *            B200F_BF16 = bf16 storage, tcgen05 tensor-core contractions with fp32 accumulation,
+ *            fp32 statistics (LayerNorm mean/rstd, softmax LSE, losses) and fp32 parameter grads.
+ *   - matrices are row-major with an explicit leading dimension (elements).
+ */
+#ifndef B200_FUSION_H
+#define B200_FUSION_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  B200F_OK = 0,
+  B200F_ERR_SHAPE = 1,
+  B200F_ERR_DTYPE = 2,
+  B200F_ERR_ALIGN = 3,
+  B200F_ERR_CUDA = 4,
+  B200F_ERR_UNSUPPORTED = 5
+} b200f_status;
+
+typedef enum { B200F_F32 = 0, B200F_BF16 = 1 } b200f_dtype;
+
+/* GEMM epilogue flags */
+enum {
+  B200F_EPI_RELU = 1,       /* C = max(C, 0) after bias / residual                                  */
+  B200F_EPI_OUT_F32 = 2,    /* C is fp32 regardless of dtype                                         */
+  B200F_EPI_ACCUM = 4,      /* C (fp32) += result (atomic; used for parameter gradients, split-K)    */
+  B200F_EPI_GELU_RSVD = 8   /* reserved                                                              */
+};
+
+int b200f_version(void);
+const char* b200f_last_error(void);
+/* 0 if `device` is an sm_100 part that can run the bf16/tcgen05 kernels. */
+int b200f_device_supported(int device);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM with fused epilogue:  C[m,n] = epi( alpha * sum_k A(m,k) * B(n,k) )
+ *   a_layout 0: A stored [M,K] (K contiguous)   1: A stored [K,M] (M contiguous)
+ *   b_layout 0: B stored [N,K] (K contiguous)   1: B stored [K,N] (N contiguous)
+ *   epi(x) = [relu]( x + bias[n] + residual[m,n] ) * (relu_mask[m,n] > 0 ? 1 : 0)
+ * Replaces every nn.Linear on the path (fusion_layers.py:21-28,55-57,124-128,195-200,238,
+ * 304-327,395-412,471-476 and the packed in/out projections of nn.MultiheadAttention,
+ * torch/nn/functional.py:5833-5860,6653) in forward (layouts 0/0), input-gradient (0/1) and
+ * weight-gradient (1/1, B200F_EPI_ACCUM) form.  bf16: tcgen05.mma, TMA-fed, accumulators in TMEM.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t M, N, K;
+  int32_t a_layout, b_layout;
+  const void* A; int64_t lda;
+  const void* B; int64_t ldb;
+  void* C; int64_t ldc;
+  const float* bias;                    /* [N] fp32 or NULL                                      */
+  const void* residual; int64_t ldr;    /* [M,N] in `dtype`, or NULL                             */
+  const void* relu_mask; int64_t ldm;   /* [M,N] in `dtype`: zero the output where mask <= 0     */
+  float alpha;
+  int32_t flags;                        /* B200F_EPI_*                                           */
+  int32_t dtype;                        /* b200f_dtype of A, B, residual, relu_mask (and C)      */
+  int32_t split_k;                      /* >1 only with B200F_EPI_ACCUM; 0/1 = none              */
+} b200f_gemm_args;
+int b200f_gemm(const b200f_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-head attention core (torch/nn/functional.py:6630-6647, need_weights path with the
+ * weights discarded: fusion_layers.py:161-163,204):  O = softmax(scale * Q K^T) V  per (b, head).
+ * Q/K/V/O are token-major: element (b, l, h, d) at  base + (b*L + l)*ld + h*D + d, so they can
+ * alias column slices of packed projection outputs.  LSE[b,h,l] (fp32, natural log of the
+ * scaled-score row sum) is saved for backward.  D (head dim) must be 64 for bf16.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, H, Lq, Lk, D;
+  const void* Q; int64_t ldq;
+  const void* K; int64_t ldk;
+  const void* V; int64_t ldv;
+  void* O; int64_t ldo;
+  float* LSE;                           /* [B,H,Lq]                                              */
+  float scale;
+  int32_t dtype;
+  /* backward only */
+  const void* dO; int64_t lddo;
+  void* dQ; int64_t lddq;
+  void* dK; int64_t lddk;
+  void* dV; int64_t lddv;
+  float* delta;                         /* [B,H,Lq] workspace: rowsum(dO * O)                    */
+} b200f_attn_args;
+int b200f_attn_fwd(const b200f_attn_args* args, void* stream);
+int b200f_attn_bwd(const b200f_attn_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row-wise kernels over [rows, H] activations (128-bit vectorised, warp-shuffle reductions).
+ * ------------------------------------------------------------------------------------------- */
+/* y = LayerNorm(x) * gamma + beta (+ post1 + post2)  (fusion_layers.py:205,209; the optional
+ * post-adds implement the 3-way residual of :156-158 in the same pass).  mean/rstd saved. */
+int b200f_layernorm_fwd(const void* x, const float* gamma, const float* beta, const void* post1,
+                        const void* post2, void* y, float* mean, float* rstd, int64_t rows, int32_t H,
+                        float eps, int32_t dtype, void* stream);
+/* dx = LN'(dy) (+ dres);  dgamma += sum dy*xhat;  dbeta += sum dy   (fp32 atomics). */
+int b200f_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
+                        const float* gamma, const void* dres, void* dx, float* dgamma, float* dbeta,
+                        int64_t rows, int32_t H, int32_t dtype, void* stream);
+/* out[n] += sum_m x[m,n]   (bias gradients). */
+int b200f_colsum_accum(const void* x, int64_t ldx, float* out, int64_t M, int64_t N, int32_t dtype, void* stream);
+/* y = a + b (+ c), elementwise over n elements (c may be NULL). */
+int b200f_add(const void* a, const void* b, const void* c, void* y, int64_t n, int32_t dtype, void* stream);
+/* y = x * (ref > 0)   (ReLU backward given the forward output). */
+int b200f_relu_bwd(const void* dy, const void* ref, void* dx, int64_t n, int32_t dtype, void* stream);
+/* fp32 -> bf16 cast with optional scale (weights -> tensor-core operands). */
+int b200f_cast_f32_to_bf16(const float* src, void* dst, int64_t n, float scale, void* stream);
+int b200f_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
+/* mean over L: x[B,L,H] -> y[B, H] written with row stride ldy (fusion_layers.py:166-168);
+ * backward: dx[b,l,:] = dy[b,:] / L. */
+int b200f_meanpool_fwd(const void* x, void* y, int64_t ldy, int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream);
+int b200f_meanpool_bwd(const void* dy, int64_t lddy, void* dx, int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream);
+/* cat = [t*m0 | a*m1 | v*m2]  rows of 3H (fusion_layers.py:38,350,437 + encoders.py:317-319);
+ * mask is [B,3] fp32 keep-mask or NULL.  Backward splits and re-applies the mask, accumulating
+ * into dt/da/dv when `accumulate`. */
+int b200f_concat3_fwd(const void* t, const void* a, const void* v, const float* mask, void* cat,
+                      int64_t B, int32_t H, int32_t dtype, void* stream);
+int b200f_concat3_bwd(const void* dcat, const float* mask, void* dt, void* da, void* dv, int32_t accumulate,
+                      int64_t B, int32_t H, int32_t dtype, void* stream);
+/* x[b, l, :] *= mask[b, col]   in place (modality dropout on [B,L,H] sequences). */
+int b200f_rowmask_apply(void* x, const float* mask, int32_t col, int64_t B, int64_t L, int32_t H, int32_t dtype, void* stream);
+/* z = y / max(||y||_2, eps) per row (F.normalize, fusion_layers.py:338-340); norm saved. */
+int b200f_l2norm_fwd(const void* y, void* z, float* norm, int64_t rows, int32_t D, float eps, int32_t dtype, void* stream);
+int b200f_l2norm_bwd(const void* dz, const void* z, const float* norm, void* dy, int64_t rows, int32_t D, float eps,
+                     int32_t dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * InfoNCE (ContrastiveFusion.contrastive_loss, fusion_layers.py:361-375) without materialising
+ * the similarity matrix.  x: [Bl, D] local rows, y: [Bg, D] gathered rows (Bg = Bl when single
+ * GPU), s_ij = inv_tau * <x_i, y_j>.
+ *   lse:   lse[i]  = log sum_j exp(s_ij);  diag[i] = s_{i, diag_off + i}
+ *   grad:  dx[i,:] (+)= coef * sum_j ( exp(s_ij - lse_x[i]) + exp(s_ij - lse_y[j]) - 2*[j == diag_off+i] ) * y[j,:]
+ * Called twice per modality pair with the roles swapped (rows, then columns of S): the only
+ * collective the path needs is the all-gather that produced y (and lse_y).
+ * ------------------------------------------------------------------------------------------- */
+int b200f_infonce_lse(const void* x, const void* y, float* lse, float* diag, int64_t Bl, int64_t Bg, int32_t D,
+                      int64_t diag_off, float inv_tau, int32_t dtype, void* stream);
+int b200f_infonce_grad(const void* x, const void* y, const float* lse_x, const float* lse_y, const float* coef_dev,
+                       float* dx, int32_t accumulate, int64_t Bl, int64_t Bg, int32_t D, int64_t diag_off,
+                       float inv_tau, int32_t dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small per-sample heads (one warp per sample).
+ * ------------------------------------------------------------------------------------------- */
+/* GATConv core on dense 3-node graphs (fusion_layers.py:267-282 + PyG GATConv semantics,
+ * SURVEY 8c): xp [B,3,heads*C] (the `lin` projection), att_src/att_dst [heads*C], bias [C]
+ *   out[b,i,:] = relu( mean_h sum_j softmax_j(leaky_relu(a_src[j,h]+a_dst[i,h])) xp[b,j,h,:] + bias )
+ * alpha [B,3(i),heads,3(j)] fp32 is saved for backward. */
+int b200f_gat_fwd(const void* xp, const float* att_src, const float* att_dst, const float* bias, void* out,
+                  float* alpha, int64_t B, int32_t heads, int32_t C, float slope, int32_t dtype, void* stream);
+int b200f_gat_bwd(const void* dout, const void* out, const void* xp, const float* alpha, const float* att_src,
+                  const float* att_dst, void* dxp, float* datt_src, float* datt_dst, float* dbias, int64_t B,
+                  int32_t heads, int32_t C, float slope, int32_t dtype, void* stream);
+/* Attention over the 3 modality tokens (AdaptiveFusion, fusion_layers.py:432-434): qkv [B,3,3H]
+ * packed projections -> ctx [B,3,H], probs [B,heads,3,3] fp32 (saved), head-averaged weights
+ * avgw [B,3,3] fp32 (returned to the caller, torch/nn/functional.py:6657-6659). */
+int b200f_tok3_attn_fwd(const void* qkv, void* ctx, float* probs, float* avgw, int64_t B, int32_t heads, int32_t H,
+                        float scale, int32_t dtype, void* stream);
+int b200f_tok3_attn_bwd(const void* dctx, const float* davgw, const void* qkv, const float* probs, void* dqkv,
+                        int64_t B, int32_t heads, int32_t H, float scale, int32_t dtype, void* stream);
+/* Gated mix (fusion_layers.py:437-443): gate = softmax(logits[B,3]); mixed = sum_m att[b,m,:]*gate[b,m]. */
+int b200f_gate_mix_fwd(const void* att, const void* logits, float* gate, void* mixed, int64_t B, int32_t H,
+                       int32_t dtype, void* stream);
+int b200f_gate_mix_bwd(const void* dmixed, const float* dgate_ext, const void* att, const float* gate, void* datt,
+                       void* dlogits, int64_t B, int32_t H, int32_t dtype, void* stream);
+/* LateFusion combine (fusion_layers.py:75-82): fused = sum_m softmax(w)[m] * logits_m. */
+int b200f_late_combine_fwd(const void* lt, const void* la, const void* lv, const float* w3, float* wsoft, void* fused,
+                           int64_t B, int32_t E, int32_t dtype, void* stream);
+int b200f_late_combine_bwd(const void* dfused, const void* lt, const void* la, const void* lv, const float* wsoft,
+                           const float* dwsoft_ext, void* dlt, void* dla, void* dlv, float* dw3, int64_t B, int32_t E,
+                           int32_t dtype, void* stream);
+/* Modality-dropout keep mask (encoders.py:303-314): mask[B,3] fp32 from a counter-based RNG,
+ * keep iff u > rate, with the keep-one repair, no host sync. */
+int b200f_modality_mask(float* mask, int64_t B, float rate, uint64_t seed, uint64_t offset, void* stream);
+/* Inverted dropout with a counter-based RNG (nn.Dropout on the path): y = x * keep / (1-p);
+ * the same (seed, offset) regenerates the mask in backward. */
+int b200f_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset, int32_t dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_FUSION_H */

@@ -1,0 +1,71 @@
+// C-ABI entry points that need no kernel of their own: version, error buffer, device check,
+// GEMM dtype dispatch, debug knobs.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace b200f {
+
+static thread_local char g_err[512] = "";
+char* err_buf() { return g_err; }
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st);
+int gemm_f32_simt(const b200f_gemm_args& a, cudaStream_t st);
+extern uint32_t g_dbg_mn_lbo, g_dbg_mn_sbo, g_dbg_mn_kadv;
+
+}  // namespace b200f
+
+extern "C" {
+
+int b200f_version(void) { return 100; }
+
+const char* b200f_last_error(void) { return b200f::err_buf(); }
+
+int b200f_device_supported(int device) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return b200f::fail(B200F_ERR_CUDA, "cudaGetDeviceProperties(%d): %s", device, cudaGetErrorString(e));
+  if (prop.major != 10) return b200f::fail(B200F_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor);
+  return B200F_OK;
+}
+
+int b200f_gemm(const b200f_gemm_args* a, void* stream) {
+  if (!a) return b200f::fail(B200F_ERR_SHAPE, "gemm: null args");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->dtype == B200F_BF16) return b200f::gemm_bf16_tc(*a, st);
+  if (a->dtype == B200F_F32) return b200f::gemm_f32_simt(*a, st);
+  return b200f::fail(B200F_ERR_DTYPE, "gemm: unknown dtype %d", a->dtype);
+}
+
+// debug: override MN-major UMMA descriptor geometry (0 restores the default). Not part of the product API.
+int b200f_debug_set(int key, unsigned value) {
+  switch (key) {
+    case 0: b200f::g_dbg_mn_lbo = value; break;
+    case 1: b200f::g_dbg_mn_sbo = value; break;
+    case 2: b200f::g_dbg_mn_kadv = value; break;
+    default: return b200f::fail(B200F_ERR_UNSUPPORTED, "unknown debug key %d", key);
+  }
+  return B200F_OK;
+}
+
+}  // extern "C"

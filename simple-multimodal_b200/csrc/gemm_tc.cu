@@ -1,0 +1,354 @@
+// bf16 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands by TMA).
+//
+//   C[m,n] = epi( alpha * sum_k A(m,k) * B(n,k) ),  fp32 accumulation
+//
+// One persistent CTA per SM, 6 warps, warp-specialised:
+//   warp 0    TMA producer   : cp.async.bulk.tensor -> STAGES-deep ring of {A,B} smem tiles (SWIZZLE_128B)
+//   warp 1    MMA issuer     : one lane issues tcgen05.mma (128 x BN x 16) into one of two TMEM accumulators
+//   warps 2-5 epilogue       : tcgen05.ld -> bias / residual / ReLU / mask -> global, while the MMA warp
+//                              already fills the other accumulator (mainloop/epilogue overlap)
+// Both operands may be K-major (reduction dim contiguous) or MN-major, so forward (X W^T), input-gradient
+// (dY W) and weight-gradient (dY^T X, fp32 atomics with split-K over tokens) all run without a transpose.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200f {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int GEMM_THREADS = 192;
+
+struct GemmTcParams {
+  int M, N, K;
+  int num_m, num_n, split_k, kb_total, kb_per_split;
+  void* C;
+  long long ldc;
+  const float* bias;
+  const bf16* residual;
+  long long ldr;
+  const bf16* mask;
+  long long ldm;
+  float alpha;
+  int flags;
+  // UMMA descriptor geometry (bytes), filled by the host so it can be probed without recompiling
+  uint32_t a_lbo, a_sbo, a_kadv, b_lbo, b_sbo, b_kadv;
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // +1024 alignment slack
+};
+
+template <int BN, int STAGES, int A_MN, int B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmTcParams p) {
+  using S = GemmSmem<BN, STAGES>;
+  constexpr int TMEM_COLS = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int units = p.num_m * p.num_n * p.split_k;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int n_blk = u % p.num_n;
+        const int m_blk = (u / p.num_n) % p.num_m;
+        const int ks = u / (p.num_n * p.num_m);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          uint8_t* sb = sa + S::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (BK * 128), &tma_a, &full_bar[stage], m_blk * BM + c * 64, kb * BK);
+          } else {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (BK * 128), &tma_b, &full_bar[stage], n_blk * BN + c * 64, kb * BK);
+          } else {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+        const int ks = u / (p.num_n * p.num_m);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = umma_desc(sa + k * p.a_kadv, p.a_lbo, p.a_sbo);
+            const uint64_t db = umma_desc(sb + k * p.b_kadv, p.b_lbo, p.b_sbo);
+            umma_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are the ones this warp may touch
+    const bool out_f32 = (p.flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) != 0;
+    const bool accum = (p.flags & B200F_EPI_ACCUM) != 0;
+    const bool relu = (p.flags & B200F_EPI_RELU) != 0;
+    int it = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+      const int n_blk = u % p.num_n;
+      const int m_blk = (u / p.num_n) % p.num_m;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const long long row = (long long)m_blk * BM + lane_grp * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + (uint32_t(lane_grp * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c0, r);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c0;
+        if (row_ok && col0 < p.N) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col >= p.N) break;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * p.alpha;
+            const bool full8 = (col + 8 <= p.N);
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (full8 || col + j < p.N) v[j] += __ldg(p.bias + col + j);
+            }
+            if (p.residual) {
+              const bf16* rp = p.residual + row * p.ldr + col;
+              if (full8) {
+                Vec16<bf16> rv; rv.load(rp);
+                float f[8]; rv.unpack(f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += f[j];
+              } else {
+                for (int j = 0; j < 8 && col + j < p.N; ++j) v[j] += to_f32(rp[j]);
+              }
+            }
+            if (relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (p.mask) {
+              const bf16* mp = p.mask + row * p.ldm + col;
+              if (full8) {
+                Vec16<bf16> mv; mv.load(mp);
+                float f[8]; mv.unpack(f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = f[j] > 0.f ? v[j] : 0.f;
+              } else {
+                for (int j = 0; j < 8 && col + j < p.N; ++j) v[j] = to_f32(mp[j]) > 0.f ? v[j] : 0.f;
+              }
+            }
+            if (out_f32) {
+              float* cp = reinterpret_cast<float*>(p.C) + row * p.ldc + col;
+              if (accum) {
+                for (int j = 0; j < 8 && (full8 || col + j < p.N); ++j) atomicAdd(cp + j, v[j]);
+              } else if (full8) {
+                *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(cp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              } else {
+                for (int j = 0; j < 8 && col + j < p.N; ++j) cp[j] = v[j];
+              }
+            } else {
+              bf16* cp = reinterpret_cast<bf16*>(p.C) + row * p.ldc + col;
+              if (full8) {
+                Vec16<bf16> ov; ov.pack(v); ov.store(cp);
+              } else {
+                for (int j = 0; j < 8 && col + j < p.N; ++j) cp[j] = __float2bfloat16_rn(v[j]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// bf16 tensor map of rank 2..4 with SWIZZLE_128B; dims[0] is the contiguous dimension.
+int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(B200F_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t d[4]; cuuint64_t s[3]; cuuint32_t b[4]; cuuint32_t e[4] = {1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(B200F_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu] stride %llu box [%u,%u] base %p", int(r), rank,
+                (unsigned long long)d[0], (unsigned long long)d[1], (unsigned long long)s[0], b[0], b[1], base);
+  return B200F_OK;
+}
+
+// debug overrides for the MN-major descriptor geometry (b200f_debug_set); 0 = use the default
+uint32_t g_dbg_mn_lbo = 0, g_dbg_mn_sbo = 0, g_dbg_mn_kadv = 0;
+
+template <int BN, int STAGES, int A_MN, int B_MN>
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcParams& p, int grid, cudaStream_t st) {
+  using S = GemmSmem<BN, STAGES>;
+  auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    B200F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, p);
+  return check_launch("gemm_tc_kernel");
+}
+
+int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
+  B200F_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, B200F_ERR_SHAPE, "gemm: empty shape M=%lld N=%lld K=%lld", (long long)a.M, (long long)a.N, (long long)a.K);
+  B200F_REQUIRE(a.lda % 8 == 0 && a.ldb % 8 == 0, B200F_ERR_ALIGN, "gemm(bf16): lda/ldb must be multiples of 8 elements (TMA 16-byte strides)");
+  B200F_REQUIRE(aligned16(a.A) && aligned16(a.B) && aligned16(a.C), B200F_ERR_ALIGN, "gemm(bf16): A/B/C must be 16-byte aligned");
+  const bool out_f32 = (a.flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) != 0;
+  B200F_REQUIRE(a.ldc % (out_f32 ? 4 : 8) == 0, B200F_ERR_ALIGN, "gemm(bf16): ldc alignment");
+  B200F_REQUIRE(!a.residual || (a.ldr % 8 == 0 && aligned16(a.residual)), B200F_ERR_ALIGN, "gemm(bf16): residual alignment");
+  B200F_REQUIRE(!a.relu_mask || (a.ldm % 8 == 0 && aligned16(a.relu_mask)), B200F_ERR_ALIGN, "gemm(bf16): mask alignment");
+  const int split = a.split_k > 1 ? a.split_k : 1;
+  B200F_REQUIRE(split == 1 || (a.flags & B200F_EPI_ACCUM), B200F_ERR_UNSUPPORTED, "gemm: split_k needs B200F_EPI_ACCUM");
+
+  const int BN = (a.N > 128) ? 256 : 128;
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2], strides[1]; uint32_t box[2];
+    if (a.a_layout == 0) { dims[0] = a.K; dims[1] = a.M; box[0] = 64; box[1] = BM; }
+    else                 { dims[0] = a.M; dims[1] = a.K; box[0] = 64; box[1] = BK; }
+    strides[0] = uint64_t(a.lda) * 2;
+    int rc = make_tmap_bf16(&ta, a.A, 2, dims, strides, box);
+    if (rc) return rc;
+    if (a.b_layout == 0) { dims[0] = a.K; dims[1] = a.N; box[0] = 64; box[1] = BN; }
+    else                 { dims[0] = a.N; dims[1] = a.K; box[0] = 64; box[1] = BK; }
+    strides[0] = uint64_t(a.ldb) * 2;
+    rc = make_tmap_bf16(&tb, a.B, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  GemmTcParams p;
+  p.M = int(a.M); p.N = int(a.N); p.K = int(a.K);
+  p.num_m = int((a.M + BM - 1) / BM);
+  p.num_n = int((a.N + BN - 1) / BN);
+  p.kb_total = int((a.K + BK - 1) / BK);
+  p.split_k = split > p.kb_total ? p.kb_total : split;
+  p.kb_per_split = (p.kb_total + p.split_k - 1) / p.split_k;
+  p.split_k = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+  p.C = a.C; p.ldc = a.ldc;
+  p.bias = a.bias;
+  p.residual = static_cast<const bf16*>(a.residual); p.ldr = a.ldr;
+  p.mask = static_cast<const bf16*>(a.relu_mask); p.ldm = a.ldm;
+  p.alpha = a.alpha; p.flags = a.flags;
+  // K-major SW128: rows of 128 B, 8-row groups 1024 B apart, +32 B per K=16 step inside the swizzle row.
+  // MN-major SW128: 64-element (128 B) MN chunks, k rows 128 B apart, 8-k-row groups 1024 B apart (SBO),
+  //                 MN chunks BK*128 B apart (LBO), +16 k rows = 2048 B per K=16 step.
+  const uint32_t mn_lbo = g_dbg_mn_lbo ? g_dbg_mn_lbo : BK * 128, mn_sbo = g_dbg_mn_sbo ? g_dbg_mn_sbo : 1024,
+                 mn_kadv = g_dbg_mn_kadv ? g_dbg_mn_kadv : 2048;
+  if (a.a_layout == 0) { p.a_lbo = 16; p.a_sbo = 1024; p.a_kadv = 32; } else { p.a_lbo = mn_lbo; p.a_sbo = mn_sbo; p.a_kadv = mn_kadv; }
+  if (a.b_layout == 0) { p.b_lbo = 16; p.b_sbo = 1024; p.b_kadv = 32; } else { p.b_lbo = mn_lbo; p.b_sbo = mn_sbo; p.b_kadv = mn_kadv; }
+
+  const int units = p.num_m * p.num_n * p.split_k;
+  const int grid = units < num_sms() ? units : num_sms();
+  const int key = (BN == 256 ? 4 : 0) | (a.a_layout ? 2 : 0) | (a.b_layout ? 1 : 0);
+  switch (key) {
+    case 0: return launch_cfg<128, 6, 0, 0>(ta, tb, p, grid, st);
+    case 1: return launch_cfg<128, 6, 0, 1>(ta, tb, p, grid, st);
+    case 2: return launch_cfg<128, 6, 1, 0>(ta, tb, p, grid, st);
+    case 3: return launch_cfg<128, 6, 1, 1>(ta, tb, p, grid, st);
+    case 4: return launch_cfg<256, 4, 0, 0>(ta, tb, p, grid, st);
+    case 5: return launch_cfg<256, 4, 0, 1>(ta, tb, p, grid, st);
+    case 6: return launch_cfg<256, 4, 1, 0>(ta, tb, p, grid, st);
+    default: return launch_cfg<256, 4, 1, 1>(ta, tb, p, grid, st);
+  }
+}
+
+}  // namespace b200f

@@ -1,0 +1,78 @@
+"""GPU diagnostic (not a pytest): per-layout tcgen05 GEMM error table, with an MN-major descriptor
+sweep if the default geometry is wrong.  Writes gpurun_out/probe_gemm.json."""
+import importlib
+import itertools
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tests.test_gemm_gpu import L, make_operands, rel_err, run_gemm  # noqa: E402
+
+out = {"default": {}, "sweep": []}
+for (a_l, b_l) in [(0, 0), (0, 1), (1, 0), (1, 1)]:
+    for shape in [(128, 128, 64), (128, 256, 64), (256, 256, 256), (4096, 1536, 512)]:
+        A, B, ref = make_operands(*shape, a_l, b_l, torch.bfloat16)
+        try:
+            got = run_gemm(A, B, *shape, a_l, b_l, torch.bfloat16, out_f32=True)
+            e = rel_err(got, ref)
+        except Exception as ex:  # noqa: BLE001
+            e = repr(ex)
+        out["default"][f"{a_l}{b_l}_{shape}"] = e
+        print(a_l, b_l, shape, e, flush=True)
+bad_mn = any(not isinstance(v, float) or not (v < 1e-4) for k, v in out["default"].items() if not k.startswith("00"))
+kmajor_ok = all(isinstance(v, float) and v < 1e-4 for k, v in out["default"].items() if k.startswith("00"))
+if bad_mn and kmajor_ok:
+    for lbo, sbo, kadv in itertools.product([8192, 1024, 128, 16, 2048], [1024, 8192, 128, 2048], [2048, 32, 256, 1024]):
+        for i, v in enumerate((lbo, sbo, kadv)):
+            L.lib().b200f_debug_set(i, v)
+        res = {}
+        for (a_l, b_l) in [(0, 1), (1, 0)]:
+            shape = (128, 128, 64)
+            A, B, ref = make_operands(*shape, a_l, b_l, torch.bfloat16)
+            try:
+                res[f"{a_l}{b_l}"] = rel_err(run_gemm(A, B, *shape, a_l, b_l, torch.bfloat16, out_f32=True), ref)
+            except Exception as ex:  # noqa: BLE001
+                res[f"{a_l}{b_l}"] = repr(ex)
+                break
+        out["sweep"].append({"lbo": lbo, "sbo": sbo, "kadv": kadv, **res})
+        print(lbo, sbo, kadv, res, flush=True)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/probe_gemm.json", "w"), indent=1)
+
+# ---- timing vs cuBLAS (torch.matmul) on MulT-shaped problems
+for i in range(3):
+    L.lib().b200f_debug_set(i, 0)
+perf = {}
+for (M, N, K, a_l, b_l, tag) in [(65536, 3072, 512, 0, 0, "proj_fwd"), (65536, 2048, 512, 0, 0, "ffn1_fwd"),
+                                 (65536, 512, 2048, 0, 0, "ffn2_fwd"), (65536, 512, 2048, 0, 1, "ffn1_dgrad"),
+                                 (2048, 512, 65536, 1, 1, "ffn1_wgrad")]:
+    A, B, ref = make_operands(M, N, K, a_l, b_l, torch.bfloat16)
+    acc = torch.zeros(M, N, device="cuda", dtype=torch.float32) if tag.endswith("wgrad") else None
+    kw = dict(accum_into=acc, split_k=16) if acc is not None else {}
+    try:
+        for _ in range(3):
+            run_gemm(A, B, M, N, K, a_l, b_l, torch.bfloat16, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            run_gemm(A, B, M, N, K, a_l, b_l, torch.bfloat16, **kw)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        Am = A if a_l == 0 else A.t()
+        Bm = B.t() if b_l == 0 else B
+        for _ in range(3):
+            torch.matmul(Am, Bm)
+        e0.record()
+        for _ in range(10):
+            torch.matmul(Am, Bm)
+        e1.record(); torch.cuda.synchronize()
+        ms_ref = e0.elapsed_time(e1) / 10
+        perf[tag] = {"ms": ms, "tflops": 2 * M * N * K / ms / 1e9, "cublas_ms": ms_ref, "cublas_tflops": 2 * M * N * K / ms_ref / 1e9}
+    except Exception as ex:  # noqa: BLE001
+        perf[tag] = repr(ex)
+    print(tag, perf[tag], flush=True)
+out["perf"] = perf
+json.dump(out, open("gpurun_out/probe_gemm.json", "w"), indent=1)

@@ -1,0 +1,107 @@
+"""tcgen05 / SIMT GEMM against torch.matmul in fp32 (through the C ABI)."""
+import ctypes as C
+import importlib
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+L = importlib.import_module("simple-multimodal_b200._lib")
+
+
+def run_gemm(A, B, M, N, K, a_layout, b_layout, dtype, bias=None, residual=None, mask=None, relu=False,
+             accum_into=None, split_k=1, alpha=1.0, out_f32=False):
+    dev = A.device
+    flags = 0
+    if relu:
+        flags |= L.EPI_RELU
+    if accum_into is not None:
+        Cbuf = accum_into
+        flags |= L.EPI_ACCUM
+    elif out_f32 or dtype == torch.float32:
+        Cbuf = torch.full((M, N), float("nan"), device=dev, dtype=torch.float32)
+        flags |= L.EPI_OUT_F32 if dtype != torch.float32 else 0
+    else:
+        Cbuf = torch.full((M, N), float("nan"), device=dev, dtype=dtype)
+    args = L.GemmArgs(M=M, N=N, K=K, a_layout=a_layout, b_layout=b_layout,
+                      A=A.data_ptr(), lda=A.stride(0), B=B.data_ptr(), ldb=B.stride(0),
+                      C=Cbuf.data_ptr(), ldc=Cbuf.stride(0),
+                      bias=None if bias is None else bias.data_ptr(),
+                      residual=None if residual is None else residual.data_ptr(),
+                      ldr=0 if residual is None else residual.stride(0),
+                      relu_mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
+                      alpha=alpha, flags=flags, dtype=L.dtype_code(dtype), split_k=split_k)
+    L.check(L.lib().b200f_gemm(C.byref(args), L.stream_ptr()), "b200f_gemm")
+    torch.cuda.synchronize()
+    return Cbuf
+
+
+def make_operands(M, N, K, a_layout, b_layout, dtype, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    A = torch.randn((M, K) if a_layout == 0 else (K, M), device="cuda", generator=g).to(dtype)
+    B = torch.randn((N, K) if b_layout == 0 else (K, N), device="cuda", generator=g).to(dtype)
+    Am = A.float() if a_layout == 0 else A.float().t()
+    Bm = B.float() if b_layout == 0 else B.float().t()
+    return A, B, Am @ Bm.t()
+
+
+def rel_err(x, ref):
+    return float((x.float() - ref).norm() / ref.norm().clamp_min(1e-30))
+
+
+SHAPES = [(128, 128, 64), (128, 256, 64), (256, 256, 128), (384, 512, 512), (1000, 520, 200), (4096, 1536, 512),
+          (130, 24, 72), (64, 2048, 512)]
+
+
+@pytest.mark.parametrize("layouts", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_gemm_bf16_tc(shape, layouts):
+    M, N, K = shape
+    a_l, b_l = layouts
+    if (a_l == 1 and M % 8) or (b_l == 1 and N % 8) or (a_l == 0 and K % 8) or (b_l == 0 and K % 8):
+        pytest.skip("leading dimension not a multiple of 8")
+    A, B, ref = make_operands(M, N, K, a_l, b_l, torch.bfloat16)
+    out = run_gemm(A, B, M, N, K, a_l, b_l, torch.bfloat16, out_f32=True)
+    assert rel_err(out, ref) < 1e-5, f"fp32-out rel err {rel_err(out, ref)}"
+    out16 = run_gemm(A, B, M, N, K, a_l, b_l, torch.bfloat16)
+    assert rel_err(out16, ref) < 5e-3
+
+
+@pytest.mark.parametrize("layouts", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (200, 136, 100), (513, 70, 33)])
+def test_gemm_f32_simt(shape, layouts):
+    M, N, K = shape
+    A, B, ref = make_operands(M, N, K, *layouts, torch.float32)
+    out = run_gemm(A, B, M, N, K, *layouts, torch.float32)
+    assert rel_err(out, ref) < 2e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gemm_epilogue(dtype):
+    M, N, K = 300, 264, 192
+    A, B, ref = make_operands(M, N, K, 0, 0, dtype, seed=1)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).to(dtype)
+    mask = torch.randn(M, N, device="cuda", generator=g).to(dtype)
+    want = torch.relu(0.5 * ref + bias + res.float()) * (mask.float() > 0)
+    got = run_gemm(A, B, M, N, K, 0, 0, dtype, bias=bias, residual=res, mask=mask, relu=True, alpha=0.5)
+    assert rel_err(got, want) < (2e-6 if dtype == torch.float32 else 5e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gemm_weight_grad_accumulate_split_k(dtype):
+    M, N, K = 512, 136, 4096          # dW[N_out=512, K_in=136] over 4096 tokens, both operands MN-major
+    A, B, ref = make_operands(M, N, K, 1, 1, dtype, seed=2)
+    acc = torch.ones(M, N, device="cuda", dtype=torch.float32)
+    run_gemm(A, B, M, N, K, 1, 1, dtype, accum_into=acc, split_k=8)
+    assert rel_err(acc - 1.0, ref) < 1e-5
+
+
+def test_gemm_bad_args_report_errors():
+    A = torch.zeros(128, 60, device="cuda", dtype=torch.bfloat16)
+    B = torch.zeros(128, 60, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(L.B200FusionError, match="multiples of 8"):
+        run_gemm(A, B, 128, 128, 60, 0, 0, torch.bfloat16)

@@ -148,15 +148,21 @@ int b200f_l2norm_bwd(const void* dz, const void* z, const float* norm, void* dy,
  * the similarity matrix.  x: [Bl, D] local rows, y: [Bg, D] gathered rows (Bg = Bl when single
  * GPU), s_ij = inv_tau * <x_i, y_j>.
  *   lse:   lse[i]  = log sum_j exp(s_ij);  diag[i] = s_{i, diag_off + i}
- *   grad:  dx[i,:] (+)= coef * sum_j ( exp(s_ij - lse_x[i]) + exp(s_ij - lse_y[j]) - 2*[j == diag_off+i] ) * y[j,:]
+ *   grad:  dx[i,:] (+)= coef * g * sum_j ( exp(s_ij - lse_x[i]) + exp(s_ij - lse_y[j]) - 2*[j == diag_off+i] ) * y[j,:]
  * Called twice per modality pair with the roles swapped (rows, then columns of S): the only
- * collective the path needs is the all-gather that produced y (and lse_y).
+ * collective the path needs is the all-gather that produced y (and lse_y).  dx is fp32.  The caller
+ * provides the workspace that holds the fp32 similarity block between the GEMM and the row kernels
+ * (b200f_infonce_workspace_bytes).
  * ------------------------------------------------------------------------------------------- */
+size_t b200f_infonce_workspace_bytes(int64_t Bl, int64_t Bg, int32_t dtype, int32_t for_grad);
 int b200f_infonce_lse(const void* x, const void* y, float* lse, float* diag, int64_t Bl, int64_t Bg, int32_t D,
-                      int64_t diag_off, float inv_tau, int32_t dtype, void* stream);
-int b200f_infonce_grad(const void* x, const void* y, const float* lse_x, const float* lse_y, const float* coef_dev,
-                       float* dx, int32_t accumulate, int64_t Bl, int64_t Bg, int32_t D, int64_t diag_off,
-                       float inv_tau, int32_t dtype, void* stream);
+                      int64_t diag_off, float inv_tau, int32_t dtype, void* workspace, size_t workspace_bytes,
+                      void* stream);
+/* coef is a host scalar, gscale_dev an optional device scalar (the upstream loss gradient) multiplied in. */
+int b200f_infonce_grad(const void* x, const void* y, const float* lse_x, const float* lse_y, float coef,
+                       const float* gscale_dev, float* dx, int32_t accumulate, int64_t Bl, int64_t Bg, int32_t D,
+                       int64_t diag_off, float inv_tau, int32_t dtype, void* workspace, size_t workspace_bytes,
+                       void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Small per-sample heads (one warp per sample).

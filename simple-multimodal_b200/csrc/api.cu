@@ -69,3 +69,42 @@ int b200f_debug_set(int key, unsigned value) {
 }
 
 }  // extern "C"
+
+namespace b200f {
+int attn_fwd_simt_dispatch(const b200f_attn_args& a, cudaStream_t st);
+int attn_bwd_simt_dispatch(const b200f_attn_args& a, cudaStream_t st);
+int attn_fwd_tc(const b200f_attn_args& a, cudaStream_t st);
+int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st);
+bool g_force_simt_attention = false;
+
+static int attn_check(const b200f_attn_args* a) {
+  if (!a) return fail(B200F_ERR_SHAPE, "attention: null args");
+  B200F_REQUIRE(a->B >= 0 && a->H > 0 && a->Lq > 0 && a->Lk > 0 && a->D > 0, B200F_ERR_SHAPE, "attention: bad shape B=%d H=%d Lq=%d Lk=%d D=%d", a->B,
+                a->H, a->Lq, a->Lk, a->D);
+  B200F_REQUIRE(a->dtype == B200F_F32 || a->dtype == B200F_BF16, B200F_ERR_DTYPE, "attention: unknown dtype %d", a->dtype);
+  return B200F_OK;
+}
+}  // namespace b200f
+
+extern "C" {
+
+int b200f_attn_fwd(const b200f_attn_args* a, void* stream) {
+  int rc = b200f::attn_check(a);
+  if (rc || a->B == 0) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->dtype == B200F_BF16 && a->D == 64 && !b200f::g_force_simt_attention) return b200f::attn_fwd_tc(*a, st);
+  return b200f::attn_fwd_simt_dispatch(*a, st);
+}
+
+int b200f_attn_bwd(const b200f_attn_args* a, void* stream) {
+  int rc = b200f::attn_check(a);
+  if (rc || a->B == 0) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->dtype == B200F_BF16 && a->D == 64 && !b200f::g_force_simt_attention) return b200f::attn_bwd_tc(*a, st);
+  return b200f::attn_bwd_simt_dispatch(*a, st);
+}
+
+// debug: route bf16 attention through the CUDA-core kernels (for A/B comparison against the tcgen05 path)
+int b200f_debug_force_simt_attention(int on) { b200f::g_force_simt_attention = on != 0; return B200F_OK; }
+
+}  // extern "C"

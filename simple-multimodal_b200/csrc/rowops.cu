@@ -1,0 +1,594 @@
+// Row-wise, HBM-bound kernels of the fusion path: LayerNorm (+ residual post-adds), bias-gradient column
+// sums, elementwise adds / ReLU backward / casts, mean-pool over the sequence, the masked 3-way concat,
+// and the L2 row normalisation of the contrastive projections.  All use 128-bit vector loads/stores
+// (4 x fp32 or 8 x bf16 per thread access), fp32 arithmetic and warp-shuffle reductions.
+#include "common.cuh"
+
+namespace b200f {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward: one warp per row; the row lives in registers between the two statistics passes.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, const T* __restrict__ post1,
+                                                            const T* __restrict__ post2, T* __restrict__ y,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            long long rows, int H, float eps) {
+  constexpr int VN = Vec16<T>::N;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int nvec = H / VN;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const T* xr = x + row * H;
+    float v[NV][VN];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        Vec16<T> t; t.load(xr + vi * VN); t.unpack(v[i]);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) s += v[i][j];
+      }
+    }
+    const float mean = warp_sum(s) / H;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (lane + i * 32 < nvec) {
+#pragma unroll
+        for (int j = 0; j < VN; ++j) { const float d = v[i][j] - mean; q += d * d; }
+      }
+    const float rstd = rsqrtf(warp_sum(q) / H + eps);
+    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float o[VN];
+#pragma unroll
+        for (int j = 0; j < VN; ++j) o[j] = (v[i][j] - mean) * rstd * gamma[vi * VN + j] + beta[vi * VN + j];
+        if (post1) {
+          Vec16<T> t; t.load(post1 + row * H + vi * VN); float f[VN]; t.unpack(f);
+#pragma unroll
+          for (int j = 0; j < VN; ++j) o[j] += f[j];
+        }
+        if (post2) {
+          Vec16<T> t; t.load(post2 + row * H + vi * VN); float f[VN]; t.unpack(f);
+#pragma unroll
+          for (int j = 0; j < VN; ++j) o[j] += f[j];
+        }
+        Vec16<T> t; t.pack(o); t.store(y + row * H + vi * VN);
+      }
+    }
+  }
+}
+
+// LayerNorm backward: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma  (+ dres);
+// dgamma/dbeta: per-lane register partials over the warp's rows -> shared atomics -> global atomics.
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                            const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                            const float* __restrict__ gamma, const T* __restrict__ dres,
+                                                            T* __restrict__ dx, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, long long rows, int H) {
+  constexpr int VN = Vec16<T>::N;
+  extern __shared__ float sred[];  // [2][H]
+  for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int nvec = H / VN;
+  float pg[NV][VN], pb[NV][VN], gm[NV][VN];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) { pg[i][j] = 0.f; pb[i][j] = 0.f; gm[i][j] = vi < nvec ? gamma[vi * VN + j] : 0.f; }
+  }
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float xh[NV][VN], g[NV][VN];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        Vec16<T> a, b; a.load(dy + row * H + vi * VN); b.load(x + row * H + vi * VN);
+        float d[VN], xv[VN]; a.unpack(d); b.unpack(xv);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) {
+          xh[i][j] = (xv[j] - mean) * rstd;
+          g[i][j] = d[j] * gm[i][j];
+          s1 += g[i][j];
+          s2 += g[i][j] * xh[i][j];
+          pg[i][j] += d[j] * xh[i][j];
+          pb[i][j] += d[j];
+        }
+      }
+    }
+    const float c1 = warp_sum(s1) / H, c2 = warp_sum(s2) / H;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float o[VN];
+#pragma unroll
+        for (int j = 0; j < VN; ++j) o[j] = rstd * (g[i][j] - c1 - xh[i][j] * c2);
+        if (dres) {
+          Vec16<T> t; t.load(dres + row * H + vi * VN); float f[VN]; t.unpack(f);
+#pragma unroll
+          for (int j = 0; j < VN; ++j) o[j] += f[j];
+        }
+        Vec16<T> t; t.pack(o); t.store(dx + row * H + vi * VN);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        atomicAdd(&sred[vi * VN + j], pg[i][j]);
+        atomicAdd(&sred[H + vi * VN + j], pb[i][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    atomicAdd(dgamma + i, sred[i]);
+    atomicAdd(dbeta + i, sred[H + i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) colsum_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ out,
+                                                     long long M, long long N, int rows_per_block) {
+  constexpr int VN = Vec16<T>::N;
+  const long long c0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VN;
+  if (c0 >= N) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  float acc[VN];
+#pragma unroll
+  for (int j = 0; j < VN; ++j) acc[j] = 0.f;
+  if (c0 + VN <= N) {
+#pragma unroll 4
+    for (long long r = r0; r < r1; ++r) {
+      Vec16<T> t; t.load(x + r * ldx + c0); float f[VN]; t.unpack(f);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) acc[j] += f[j];
+    }
+  } else {
+    for (long long r = r0; r < r1; ++r)
+      for (int j = 0; j < VN && c0 + j < N; ++j) acc[j] += to_f32(x[r * ldx + c0 + j]);
+  }
+  for (int j = 0; j < VN && c0 + j < N; ++j) atomicAdd(out + c0 + j, acc[j]);
+}
+
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c, T* __restrict__ y, long long nvec) {
+  constexpr int VN = Vec16<T>::N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    Vec16<T> va, vb; va.load(a + i * VN); vb.load(b + i * VN);
+    float fa[VN], fb[VN]; va.unpack(fa); vb.unpack(fb);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) fa[j] += fb[j];
+    if (c) {
+      Vec16<T> vc; vc.load(c + i * VN); vc.unpack(fb);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) fa[j] += fb[j];
+    }
+    Vec16<T> o; o.pack(fa); o.store(y + i * VN);
+  }
+}
+
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ ref, T* __restrict__ dx, long long nvec) {
+  constexpr int VN = Vec16<T>::N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    Vec16<T> va, vb; va.load(dy + i * VN); vb.load(ref + i * VN);
+    float fa[VN], fb[VN]; va.unpack(fa); vb.unpack(fb);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) fa[j] = fb[j] > 0.f ? fa[j] : 0.f;
+    Vec16<T> o; o.pack(fa); o.store(dx + i * VN);
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n, float scale) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long nvec = n / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const float4 a = *reinterpret_cast<const float4*>(src + i * 8);
+    const float4 b = *reinterpret_cast<const float4*>(src + i * 8 + 4);
+    const float f[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
+    Vec16<bf16> o; o.pack(f); o.store(dst + i * 8);
+  }
+  for (long long i = nvec * 8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i] * scale);
+}
+
+__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __bfloat162float(src[i]);
+}
+
+// x[B,L,H] -> y[b,:] = mean_l x[b,l,:]; one thread per 16-byte column group, loop over L.
+template <typename T>
+__global__ void __launch_bounds__(128) meanpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long ldy, int L, int H) {
+  constexpr int VN = Vec16<T>::N;
+  const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * VN;
+  if (c0 >= H) return;
+  const long long b = blockIdx.x;
+  const T* xb = x + b * (long long)L * H + c0;
+  float acc[VN];
+#pragma unroll
+  for (int j = 0; j < VN; ++j) acc[j] = 0.f;
+#pragma unroll 4
+  for (int l = 0; l < L; ++l) {
+    Vec16<T> t; t.load(xb + (long long)l * H); float f[VN]; t.unpack(f);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) acc[j] += f[j];
+  }
+  const float inv = 1.f / L;
+#pragma unroll
+  for (int j = 0; j < VN; ++j) acc[j] *= inv;
+  Vec16<T> o; o.pack(acc); o.store(y + b * ldy + c0);
+}
+
+template <typename T>
+__global__ void meanpool_bwd_kernel(const T* __restrict__ dy, long long lddy, T* __restrict__ dx, long long B, int L, int H) {
+  constexpr int VN = Vec16<T>::N;
+  const int hv = H / VN;
+  const long long total = B * L * hv;
+  const float inv = 1.f / L;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % hv);
+    const long long b = i / ((long long)hv * L);
+    Vec16<T> t; t.load(dy + b * lddy + c * VN); float f[VN]; t.unpack(f);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) f[j] *= inv;
+    Vec16<T> o; o.pack(f); o.store(dx + i * VN);
+  }
+}
+
+template <typename T>
+__global__ void concat3_fwd_kernel(const T* __restrict__ t, const T* __restrict__ a, const T* __restrict__ v,
+                                   const float* __restrict__ mask, T* __restrict__ cat, long long B, int H) {
+  constexpr int VN = Vec16<T>::N;
+  const int hv = H / VN;
+  const long long total = B * 3 * hv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % hv);
+    const int m = int((i / hv) % 3);
+    const long long b = i / (3LL * hv);
+    const T* src = (m == 0 ? t : (m == 1 ? a : v)) + b * H + c * VN;
+    Vec16<T> x; x.load(src);
+    if (mask) {
+      const float k = mask[b * 3 + m];
+      float f[VN]; x.unpack(f);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) f[j] *= k;
+      x.pack(f);
+    }
+    x.store(cat + b * 3LL * H + (long long)m * H + c * VN);
+  }
+}
+
+template <typename T>
+__global__ void concat3_bwd_kernel(const T* __restrict__ dcat, const float* __restrict__ mask, T* __restrict__ dt,
+                                   T* __restrict__ da, T* __restrict__ dv, int accumulate, long long B, int H) {
+  constexpr int VN = Vec16<T>::N;
+  const int hv = H / VN;
+  const long long total = B * 3 * hv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % hv);
+    const int m = int((i / hv) % 3);
+    const long long b = i / (3LL * hv);
+    T* dst = (m == 0 ? dt : (m == 1 ? da : dv)) + b * H + c * VN;
+    Vec16<T> x; x.load(dcat + b * 3LL * H + (long long)m * H + c * VN);
+    float f[VN]; x.unpack(f);
+    const float k = mask ? mask[b * 3 + m] : 1.f;
+    if (accumulate) {
+      Vec16<T> o; o.load(dst); float g[VN]; o.unpack(g);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) f[j] = g[j] + f[j] * k;
+    } else {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) f[j] *= k;
+    }
+    x.pack(f); x.store(dst);
+  }
+}
+
+template <typename T>
+__global__ void rowmask_kernel(T* __restrict__ x, const float* __restrict__ mask, int col, long long B, long long L, int H) {
+  constexpr int VN = Vec16<T>::N;
+  const long long per_b = L * (H / VN);
+  const long long total = B * per_b;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float k = mask[(i / per_b) * 3 + col];
+    if (k == 1.f) continue;
+    Vec16<T> t; t.load(x + i * VN); float f[VN]; t.unpack(f);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) f[j] *= k;
+    t.pack(f); t.store(x + i * VN);
+  }
+}
+
+// L2 row normalisation: one warp per row.
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) l2norm_fwd_kernel(const T* __restrict__ y, T* __restrict__ z, float* __restrict__ norm_out,
+                                                         long long rows, int D, float eps) {
+  constexpr int VN = Vec16<T>::N;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = D / VN;
+  float v[NV][VN];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (lane + i * 32 < nvec) {
+      Vec16<T> t; t.load(y + row * D + (lane + i * 32) * VN); t.unpack(v[i]);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) s += v[i][j] * v[i][j];
+    }
+  const float nrm = sqrtf(warp_sum(s));
+  const float inv = 1.f / fmaxf(nrm, eps);
+  if (lane == 0) norm_out[row] = nrm;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (lane + i * 32 < nvec) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) v[i][j] *= inv;
+      Vec16<T> t; t.pack(v[i]); t.store(z + row * D + (lane + i * 32) * VN);
+    }
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const T* __restrict__ dz, const T* __restrict__ z, const float* __restrict__ norm_in,
+                                                         T* __restrict__ dy, long long rows, int D, float eps) {
+  constexpr int VN = Vec16<T>::N;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = D / VN;
+  float g[NV][VN], zz[NV][VN];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (lane + i * 32 < nvec) {
+      Vec16<T> a, b; a.load(dz + row * D + (lane + i * 32) * VN); b.load(z + row * D + (lane + i * 32) * VN);
+      a.unpack(g[i]); b.unpack(zz[i]);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) dot += g[i][j] * zz[i][j];
+    }
+  dot = warp_sum(dot);
+  const float nrm = norm_in[row];
+  const bool clamped = nrm < eps;            // y / eps: plain scaling, no projection term
+  const float inv = 1.f / fmaxf(nrm, eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (lane + i * 32 < nvec) {
+      float o[VN];
+#pragma unroll
+      for (int j = 0; j < VN; ++j) o[j] = clamped ? g[i][j] * inv : (g[i][j] - zz[i][j] * dot) * inv;
+      Vec16<T> t; t.pack(o); t.store(dy + row * D + (lane + i * 32) * VN);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch helpers
+// ------------------------------------------------------------------------------------------------
+static inline int ew_grid(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  const long long cap = (long long)num_sms() * 16;
+  return int(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+#define DISPATCH_DTYPE(dtype, T, ...)                                              \
+  if ((dtype) == B200F_F32) { using T = float; __VA_ARGS__ }                       \
+  else if ((dtype) == B200F_BF16) { using T = bf16; __VA_ARGS__ }                  \
+  else return fail(B200F_ERR_DTYPE, "unknown dtype %d", int(dtype));
+
+#define DISPATCH_NV(nv_needed, NV, ...)                                            \
+  if ((nv_needed) <= 1) { constexpr int NV = 1; __VA_ARGS__ }                      \
+  else if ((nv_needed) <= 2) { constexpr int NV = 2; __VA_ARGS__ }                 \
+  else if ((nv_needed) <= 4) { constexpr int NV = 4; __VA_ARGS__ }                 \
+  else if ((nv_needed) <= 8) { constexpr int NV = 8; __VA_ARGS__ }                 \
+  else return fail(B200F_ERR_SHAPE, "row too long for the row-wise kernels");
+
+}  // namespace b200f
+
+using namespace b200f;
+
+extern "C" {
+
+int b200f_layernorm_fwd(const void* x, const float* gamma, const float* beta, const void* post1, const void* post2, void* y,
+                        float* mean, float* rstd, int64_t rows, int32_t H, float eps, int32_t dtype, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (rows == 0) return B200F_OK;
+  DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec16<T>::N;
+    B200F_REQUIRE(H % VN == 0 && H > 0, B200F_ERR_SHAPE, "layernorm: H=%d must be a multiple of %d", H, VN);
+    B200F_REQUIRE(aligned16(x) && aligned16(y) && aligned16(post1) && aligned16(post2), B200F_ERR_ALIGN, "layernorm: 16-byte alignment");
+    const int need = (H / VN + 31) / 32;
+    const long long blocks = (rows + 7) / 8;
+    const int grid = int(blocks < (long long)num_sms() * 8 ? blocks : (long long)num_sms() * 8);
+    DISPATCH_NV(need, NV, {
+      layernorm_fwd_kernel<T, NV><<<grid, 256, 0, st>>>(static_cast<const T*>(x), gamma, beta, static_cast<const T*>(post1),
+                                                         static_cast<const T*>(post2), static_cast<T*>(y), mean, rstd, rows, H, eps);
+    })
+  })
+  return check_launch("layernorm_fwd");
+}
+
+int b200f_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, const void* dres,
+                        void* dx, float* dgamma, float* dbeta, int64_t rows, int32_t H, int32_t dtype, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (rows == 0) return B200F_OK;
+  DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec16<T>::N;
+    B200F_REQUIRE(H % VN == 0 && H > 0, B200F_ERR_SHAPE, "layernorm: H=%d must be a multiple of %d", H, VN);
+    B200F_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(dres), B200F_ERR_ALIGN, "layernorm: 16-byte alignment");
+    const int need = (H / VN + 31) / 32;
+    const long long blocks = (rows + 7) / 8;
+    const int grid = int(blocks < (long long)num_sms() * 4 ? blocks : (long long)num_sms() * 4);
+    DISPATCH_NV(need, NV, {
+      layernorm_bwd_kernel<T, NV><<<grid, 256, 2 * H * sizeof(float), st>>>(static_cast<const T*>(dy), static_cast<const T*>(x), mean, rstd, gamma,
+                                                                            static_cast<const T*>(dres), static_cast<T*>(dx), dgamma, dbeta, rows, H);
+    })
+  })
+  return check_launch("layernorm_bwd");
+}
+
+int b200f_colsum_accum(const void* x, int64_t ldx, float* out, int64_t M, int64_t N, int32_t dtype, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (M == 0 || N == 0) return B200F_OK;
+  DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec16<T>::N;
+    B200F_REQUIRE(ldx % VN == 0 && aligned16(x), B200F_ERR_ALIGN, "colsum: alignment");
+    const int gx = int((N + VN * 128 - 1) / (VN * 128));
+    long long slabs = (long long)num_sms() * 4 / gx;
+    if (slabs < 1) slabs = 1;
+    long long rpb = (M + slabs - 1) / slabs;
+    if (rpb < 32) rpb = 32;
+    const int gy = int((M + rpb - 1) / rpb);
+    colsum_kernel<T><<<dim3(gx, gy), 128, 0, st>>>(static_cast<const T*>(x), ldx, out, M, N, int(rpb));
+  })
+  return check_launch("colsum");
+}
+
+int b200f_add(const void* a, const void* b, const void* c, void* y, int64_t n, int32_t dtype, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n == 0) return B200F_OK;
+  DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec16<T>::N;
+    B200F_REQUIRE(n % VN == 0, B200F_ERR_SHAPE, "add: n must be a multiple of %d", VN);
+    B200F_REQUIRE(aligned16(a) && aligned16(b) && aligned16(c) && aligned16(y), B200F_ERR_ALIGN, "add: alignment");
+    add_kernel<T><<<ew_grid(n / VN, 256), 256, 0, st>>>(static_cast<const T*>(a), static_cast<const T*>(b), static_cast<const T*>(c), static_cast<T*>(y), n / VN);
+  })
+  return check_launch("add");
+}
+
+int b200f_relu_bwd(const void* dy, const void* ref, void* dx, int64_t n, int32_t dtype, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n == 0) return B200F_OK;
+  DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec16<T>::N;
+    B200F_REQUIRE(n % VN == 0, B200F_ERR_SHAPE, "relu_bwd: n must be a multiple of %d", VN);
+    B200F_REQUIRE(aligned16(dy) && aligned16(ref) && aligned16(dx), B200F_ERR_ALIGN, "relu_bwd: alignment");
+    relu_bwd_kernel<T><<<ew_grid(n / VN, 256), 256, 0, st>>>(static_cast<const T*>(dy), static_cast<const T*>(ref), static_cast<T*>(dx), n / VN);
+  })
+  return check_launch("relu_bwd");
+}
+
+int b200f_cast_f32_to_bf16(const float* src, void* dst, int64_t n, float scale, void* stream) {
+  if (n == 0) return B200F_OK;
+  B200F_REQUIRE(aligned16(src) && aligned16(dst), B200F_ERR_ALIGN, "cast: alignment");
+  cast_f32_bf16_kernel<<<ew_grid(n / 8 + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<bf16*>(dst), n, scale);
+  return check_launch("cast_f32_bf16");
+}
+
+int b200f_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream) {
+  if (n == 0) return B200F_OK;
+  cast_bf16_f32_kernel<<<ew_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(src), dst, n);
+  return check_launch("cast_bf16_f32");
+}
+
+int b200f_meanpool_fwd(const void* x, void* y, int64_t ldy, int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B == 0) return B200F_OK;
+  DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec16<T>::N;
+    B200F_REQUIRE(H % VN == 0 && ldy % VN == 0 && L > 0, B200F_ERR_SHAPE, "meanpool: shape");
+    B200F_REQUIRE(aligned16(x) && aligned16(y), B200F_ERR_ALIGN, "meanpool: alignment");
+    const int gy = (H / VN + 127) / 128;
+    meanpool_fwd_kernel<T><<<dim3(B, gy), 128, 0, st>>>(static_cast<const T*>(x), static_cast<T*>(y), ldy, L, H);
+  })
+  return check_launch("meanpool_fwd");
+}
+
+int b200f_meanpool_bwd(const void* dy, int64_t lddy, void* dx, int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B == 0) return B200F_OK;
+  DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec16<T>::N;
+    B200F_REQUIRE(H % VN == 0 && lddy % VN == 0 && L > 0, B200F_ERR_SHAPE, "meanpool: shape");
+    B200F_REQUIRE(aligned16(dx) && aligned16(dy), B200F_ERR_ALIGN, "meanpool: alignment");
+    meanpool_bwd_kernel<T><<<ew_grid((long long)B * L * (H / VN), 256), 256, 0, st>>>(static_cast<const T*>(dy), lddy, static_cast<T*>(dx), B, L, H);
+  })
+  return check_launch("meanpool_bwd");
+}
+
+int b200f_concat3_fwd(const void* t, const void* a, const void* v, const float* mask, void* cat, int64_t B, int32_t H, int32_t dtype, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B == 0) return B200F_OK;
+  DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec16<T>::N;
+    B200F_REQUIRE(H % VN == 0, B200F_ERR_SHAPE, "concat3: H must be a multiple of %d", VN);
+    B200F_REQUIRE(aligned16(t) && aligned16(a) && aligned16(v) && aligned16(cat), B200F_ERR_ALIGN, "concat3: alignment");
+    concat3_fwd_kernel<T><<<ew_grid(B * 3 * (H / VN), 256), 256, 0, st>>>(static_cast<const T*>(t), static_cast<const T*>(a), static_cast<const T*>(v), mask, static_cast<T*>(cat), B, H);
+  })
+  return check_launch("concat3_fwd");
+}
+
+int b200f_concat3_bwd(const void* dcat, const float* mask, void* dt, void* da, void* dv, int32_t accumulate, int64_t B, int32_t H,
+                      int32_t dtype, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B == 0) return B200F_OK;
+  DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec16<T>::N;
+    B200F_REQUIRE(H % VN == 0, B200F_ERR_SHAPE, "concat3: H must be a multiple of %d", VN);
+    B200F_REQUIRE(aligned16(dt) && aligned16(da) && aligned16(dv) && aligned16(dcat), B200F_ERR_ALIGN, "concat3: alignment");
+    concat3_bwd_kernel<T><<<ew_grid(B * 3 * (H / VN), 256), 256, 0, st>>>(static_cast<const T*>(dcat), mask, static_cast<T*>(dt), static_cast<T*>(da), static_cast<T*>(dv), accumulate, B, H);
+  })
+  return check_launch("concat3_bwd");
+}
+
+int b200f_rowmask_apply(void* x, const float* mask, int32_t col, int64_t B, int64_t L, int32_t H, int32_t dtype, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B == 0 || L == 0) return B200F_OK;
+  B200F_REQUIRE(col >= 0 && col < 3 && mask, B200F_ERR_SHAPE, "rowmask: col/mask");
+  DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec16<T>::N;
+    B200F_REQUIRE(H % VN == 0 && aligned16(x), B200F_ERR_ALIGN, "rowmask: alignment");
+    rowmask_kernel<T><<<ew_grid(B * L * (H / VN), 256), 256, 0, st>>>(static_cast<T*>(x), mask, col, B, L, H);
+  })
+  return check_launch("rowmask");
+}
+
+int b200f_l2norm_fwd(const void* y, void* z, float* norm, int64_t rows, int32_t D, float eps, int32_t dtype, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (rows == 0) return B200F_OK;
+  DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec16<T>::N;
+    B200F_REQUIRE(D % VN == 0 && aligned16(y) && aligned16(z), B200F_ERR_ALIGN, "l2norm: alignment");
+    const int need = (D / VN + 31) / 32;
+    DISPATCH_NV(need, NV, {
+      l2norm_fwd_kernel<T, NV><<<int((rows + 7) / 8), 256, 0, st>>>(static_cast<const T*>(y), static_cast<T*>(z), norm, rows, D, eps);
+    })
+  })
+  return check_launch("l2norm_fwd");
+}
+
+int b200f_l2norm_bwd(const void* dz, const void* z, const float* norm, void* dy, int64_t rows, int32_t D, float eps, int32_t dtype, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (rows == 0) return B200F_OK;
+  DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec16<T>::N;
+    B200F_REQUIRE(D % VN == 0 && aligned16(dz) && aligned16(z) && aligned16(dy), B200F_ERR_ALIGN, "l2norm: alignment");
+    const int need = (D / VN + 31) / 32;
+    DISPATCH_NV(need, NV, {
+      l2norm_bwd_kernel<T, NV><<<int((rows + 7) / 8), 256, 0, st>>>(static_cast<const T*>(dz), static_cast<const T*>(z), norm, static_cast<T*>(dy), rows, D, eps);
+    })
+  })
+  return check_launch("l2norm_bwd");
+}
+
+}  // extern "C"

@@ -1,0 +1,445 @@
+"""Drop-in replacements for the reference's fusion heads (models/fusion_layers.py) on B200.
+
+Same class names, `Cls(config)` constructors, `forward(text, audio, video[, compute_contrastive_loss])`
+signatures, return types / dict keys and `state_dict()` layout as the reference, so
+`models/multimodal_model.py:29-46,110-144` and reference checkpoints work unchanged
+(see INTEGRATION.md).  The sub-modules registered here are *parameter containers only*: no
+`nn.Linear.forward`, `nn.MultiheadAttention.forward` or `nn.LayerNorm.forward` is ever called -- all
+arithmetic runs in libb200fusion.so through `ops.py` / `mult_engine.py`, and there is no fallback.
+
+Extensions over the reference: an optional trailing `mask=None` keyword ([B,3] keep-mask,
+the ModalityDropout multiply of models/encoders.py:317-319 fused into the first load), and
+HierarchicalFusion accepts [B,L,H] sequences (MulT sees them, the other heads see their mean over L).
+
+Precision: bfloat16 inputs (or `compute_dtype=torch.bfloat16`, or CUDA autocast) run the tcgen05
+kernels; float32 inputs run the fp32 parity kernels.  Parameters are always fp32 masters.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import kernels as K
+from . import mult_engine
+from . import ops
+from ._lib import B200FusionError
+
+Tensor = torch.Tensor
+GAT_HEADS = 4           # fusion_layers.py:227
+GAT_SLOPE = 0.2         # GATConv default negative_slope
+
+
+def _mlp_container(sizes, dropout, final_relu):
+    """nn.Sequential with the reference's child indices (Linear, ReLU, Dropout, Linear, ...) so that
+    parameter names line up; used only to hold parameters."""
+    mods = []
+    for i in range(len(sizes) - 1):
+        mods.append(nn.Linear(sizes[i], sizes[i + 1]))
+        last = i == len(sizes) - 2
+        if not last or final_relu:
+            mods.append(nn.ReLU())
+            if dropout is not None:
+                mods.append(nn.Dropout(dropout))
+    return nn.Sequential(*mods)
+
+
+class _FusionBase(nn.Module):
+    compute_dtype: Optional[torch.dtype] = None
+
+    def _prepare(self, feats, mask):
+        """Pick the compute dtype, cast inputs with the library's cast kernels, validate the mask."""
+        t = feats[0]
+        if not t.is_cuda:
+            raise B200FusionError("b200 fusion heads run on CUDA tensors only (there is no CPU fallback)")
+        dt = self.compute_dtype
+        if dt is None:
+            if torch.is_autocast_enabled("cuda"):
+                dt = torch.bfloat16
+            else:
+                dt = t.dtype if t.dtype in (torch.float32, torch.bfloat16) else torch.bfloat16
+        out = []
+        for x in feats:
+            if x.dtype != dt:
+                x = _CastFn.apply(x, dt)
+            out.append(x)
+        if mask is not None:
+            if mask.shape != (t.size(0), 3):
+                raise B200FusionError(f"mask must be [B,3], got {tuple(mask.shape)}")
+            mask = mask.to(device=t.device, dtype=torch.float32).contiguous()
+        return out, mask, dt
+
+    @property
+    def _p(self) -> float:
+        return float(getattr(self.config, "fusion_dropout", 0.0))
+
+
+class _CastFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dt):
+        ctx.src = x.dtype
+        if x.dtype == torch.float32 and dt == torch.bfloat16:
+            return K.cast_to_bf16(x)
+        if x.dtype == torch.bfloat16 and dt == torch.float32:
+            return K.cast_to_f32(x)
+        if x.dtype == torch.float16:
+            return K.cast_to_bf16(x.float()) if dt == torch.bfloat16 else x.float()
+        raise B200FusionError(f"cannot cast {x.dtype} -> {dt}")
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.src == torch.float32:
+            return (K.cast_to_f32(g) if g.dtype == torch.bfloat16 else g), None
+        if ctx.src == torch.bfloat16:
+            return (K.cast_to_bf16(g) if g.dtype == torch.float32 else g), None
+        return g.to(ctx.src), None
+
+
+def _masked_cat(t, a, v, mask):
+    return ops.Concat3Fn.apply(t, a, v, mask)
+
+
+def _masked_split(t, a, v, mask):
+    """Per-modality features with the keep-mask applied (one fused concat+mask pass, then views)."""
+    if mask is None:
+        return t, a, v
+    return ops.Split3Fn.apply(_masked_cat(t, a, v, mask))
+
+
+class EarlyFusion(_FusionBase):
+    """reference models/fusion_layers.py:9-43."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        H = config.fusion_hidden_size
+        self.fusion_layers = _mlp_container([3 * H, 2 * H, H], config.fusion_dropout, final_relu=True)
+
+    def forward(self, text_features, audio_features, video_features, mask=None) -> Tensor:
+        (t, a, v), mask, _ = self._prepare((text_features, audio_features, video_features), mask)
+        return self._run(_masked_cat(t, a, v, mask))
+
+    def _run(self, cat):
+        l0, l3 = self.fusion_layers[0], self.fusion_layers[3]
+        h = ops.dropout(ops.linear(cat, l0.weight, l0.bias, relu=True), self._p, self.training)
+        return ops.dropout(ops.linear(h, l3.weight, l3.bias, relu=True), self._p, self.training)
+
+
+class LateFusion(_FusionBase):
+    """reference models/fusion_layers.py:46-90."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        H, E = config.fusion_hidden_size, config.num_emotions
+        self.text_classifier = nn.Linear(H, E)
+        self.audio_classifier = nn.Linear(H, E)
+        self.video_classifier = nn.Linear(H, E)
+        self.fusion_weights = nn.Parameter(torch.ones(3) / 3)
+
+    def forward(self, text_features, audio_features, video_features, mask=None) -> Dict[str, Tensor]:
+        (t, a, v), mask, _ = self._prepare((text_features, audio_features, video_features), mask)
+        t, a, v = _masked_split(t, a, v, mask)
+        lt = ops.linear(t, self.text_classifier.weight, self.text_classifier.bias)
+        la = ops.linear(a, self.audio_classifier.weight, self.audio_classifier.bias)
+        lv = ops.linear(v, self.video_classifier.weight, self.video_classifier.bias)
+        fused, w = ops.LateCombineFn.apply(lt, la, lv, self.fusion_weights)
+        return {"fused_logits": fused, "text_logits": lt, "audio_logits": la, "video_logits": lv, "fusion_weights": w}
+
+
+class CrossModalTransformer(_FusionBase):
+    """reference models/fusion_layers.py:182-211.  Parameter container for MultimodalTransformer; its own
+    forward (one block) is also available and runs the same kernels op by op."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        H = config.fusion_hidden_size
+        self.attention = nn.MultiheadAttention(H, config.fusion_num_heads, dropout=config.fusion_dropout, batch_first=True)
+        self.norm1 = nn.LayerNorm(H)
+        self.norm2 = nn.LayerNorm(H)
+        self.ffn = _mlp_container([H, 4 * H, H], config.fusion_dropout, final_relu=False)
+
+    def forward(self, query: Tensor, key_value: Tensor) -> Tensor:
+        (q, kv), _, _ = self._prepare((query, key_value), None)
+        H, heads = self.config.fusion_hidden_size, self.config.fusion_num_heads
+        att = self.attention
+        pq = ops.linear(q, att.in_proj_weight[:H], att.in_proj_bias[:H])
+        pkv = ops.linear(kv, att.in_proj_weight[H:], att.in_proj_bias[H:])
+        ctx = ops.AttentionFn.apply(pq, pkv, 0, 0, H, H, heads, ops.mha_scale(H, heads))
+        x = ops.LayerNormFn.apply(ops.AddFn.apply(q, ops.linear(ctx, att.out_proj.weight, att.out_proj.bias), None),
+                                  self.norm1.weight, self.norm1.bias)
+        h = ops.dropout(ops.linear(x, self.ffn[0].weight, self.ffn[0].bias, relu=True), self._p, self.training)
+        y = ops.linear(h, self.ffn[3].weight, self.ffn[3].bias)
+        return ops.LayerNormFn.apply(ops.AddFn.apply(x, y, None), self.norm2.weight, self.norm2.bias)
+
+
+class MultimodalTransformer(_FusionBase):
+    """reference models/fusion_layers.py:93-179, executed by mult_engine.MulTFn (chunked, fused schedule)."""
+
+    chunk_size = 128
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        H = config.fusion_hidden_size
+        for name, _, _ in mult_engine.BLOCKS:
+            setattr(self, name, CrossModalTransformer(config))
+        for m in mult_engine.MODS:
+            setattr(self, f"{m}_self_attn", nn.MultiheadAttention(H, config.fusion_num_heads, dropout=config.fusion_dropout,
+                                                                  batch_first=True))
+        self.final_fusion = _mlp_container([3 * H, H], config.fusion_dropout, final_relu=True)
+        self._names = mult_engine.param_names()
+
+    def _pooled(self, t, a, v, mask):
+        if t.dim() == 2:                                     # fusion_layers.py:140-143
+            t, a, v = t.unsqueeze(1), a.unsqueeze(1), v.unsqueeze(1)
+        if mask is not None:
+            t, a, v = (ops.RowMaskFn.apply(x, mask, i) for i, x in enumerate((t, a, v)))
+        if self.training and self._p > 0.0:
+            raise B200FusionError("MulT: dropout inside the fused attention/FFN schedule is not implemented yet; "
+                                  "use fusion_dropout=0 or eval() (no silent fallback)")
+        params = dict(self.named_parameters())
+        H, heads = self.config.fusion_hidden_size, self.config.fusion_num_heads
+        return mult_engine.MulTFn.apply(t, a, v, H, heads, int(self.chunk_size), self._names, *[params[n] for n in self._names])
+
+    def forward(self, text_features, audio_features, video_features, mask=None) -> Dict[str, Tensor]:
+        (t, a, v), mask, _ = self._prepare((text_features, audio_features, video_features), mask)
+        pooled = self._pooled(t, a, v, mask)
+        H = self.config.fusion_hidden_size
+        ff = self.final_fusion[0]
+        fused = ops.dropout(ops.linear(pooled, ff.weight, ff.bias, relu=True), self._p, self.training)
+        tp, ap, vp = ops.Split3Fn.apply(pooled)
+        return {"fused_features": fused, "text_features": tp, "audio_features": ap, "video_features": vp}
+
+
+class _GATParams(nn.Module):
+    """Parameter container with torch_geometric.nn.GATConv's names and shapes (PyG >= 2.5 naming, `lin.weight`;
+    the 2.3/2.4 names `lin_src.weight`/`lin_dst.weight` are accepted on load).  Initialised like PyG (glorot)."""
+
+    def __init__(self, in_channels, out_channels, heads):
+        super().__init__()
+        self.heads, self.out_channels = heads, out_channels
+        self.lin = nn.Linear(in_channels, heads * out_channels, bias=False)
+        self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        nn.init.xavier_uniform_(self.lin.weight)
+        nn.init.xavier_uniform_(self.att_src)
+        nn.init.xavier_uniform_(self.att_dst)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        for old in ("lin_src.weight", "lin_dst.weight"):
+            if prefix + old in state_dict:
+                state_dict.setdefault(prefix + "lin.weight", state_dict[prefix + old])
+                del state_dict[prefix + old]
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+
+class GraphFusion(_FusionBase):
+    """reference models/fusion_layers.py:214-291 on dense [B,3,C] node tensors: the per-sample Python loop,
+    Data/Batch construction and scatter-softmax disappear (every sample is the same complete 3-graph)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        H, G = config.fusion_hidden_size, config.graph_hidden_size
+        self.gcn_layers = nn.ModuleList([_GATParams(H, G, GAT_HEADS) for _ in range(config.graph_num_layers)])
+        self.node_type_embedding = nn.Embedding(3, H)
+        self.output_projection = nn.Linear(G, H)
+        if config.graph_num_layers > 1 and G != H:
+            # the reference builds every layer with in=H (fusion_layers.py:223-232): layer 2 cannot consume G != H channels
+            raise B200FusionError(f"GraphFusion: graph_hidden_size ({G}) must equal fusion_hidden_size ({H}) when "
+                                  f"graph_num_layers > 1 -- the reference constructor has the same constraint (SURVEY F4)")
+
+    def forward(self, text_features, audio_features, video_features, mask=None) -> Tensor:
+        (t, a, v), mask, dt = self._prepare((text_features, audio_features, video_features), mask)
+        return self._run(_masked_cat(t, a, v, mask), dt)
+
+    def _run(self, cat, dt):
+        B, H = cat.size(0), self.config.fusion_hidden_size
+        emb = _EmbedAddFn.apply(cat, self.node_type_embedding.weight)            # nodes + type embedding, [B,3H]
+        x = emb.view(B, 3, H)
+        for layer in self.gcn_layers:
+            xp = ops.linear(x, layer.lin.weight, None)                            # [B,3,heads*C]
+            x = ops.GatFn.apply(xp, layer.att_src, layer.att_dst, layer.bias, layer.heads, GAT_SLOPE)
+        pooled = ops.MeanPoolFn.apply(x)                                          # global_mean_pool over the 3 nodes
+        return ops.linear(pooled, self.output_projection.weight, self.output_projection.bias)
+
+
+class _EmbedAddFn(torch.autograd.Function):
+    """cat[B,3H] + flatten(embedding[3,H]) broadcast over the batch, via the GEMM-free add kernel."""
+
+    @staticmethod
+    def forward(ctx, cat, emb):
+        B = cat.size(0)
+        e = emb.detach().reshape(1, -1)
+        e = (K.cast_to_bf16(e) if cat.dtype == torch.bfloat16 else e.contiguous()).expand(B, -1).contiguous()
+        return K.add(cat.contiguous(), e)
+
+    @staticmethod
+    def backward(ctx, g):
+        demb = torch.zeros(g.size(1), device=g.device, dtype=torch.float32)
+        K.colsum_accum(g.contiguous(), demb)
+        return g, demb.view(3, -1)
+
+
+class ContrastiveFusion(_FusionBase):
+    """reference models/fusion_layers.py:294-375.  The InfoNCE negatives span the GLOBAL batch when a
+    torch.distributed process group is initialised (ops.InfoNCE3Fn)."""
+
+    process_group = None
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.temperature = config.contrastive_temperature
+        H = config.fusion_hidden_size
+        self.text_projector = _mlp_container([H, H, H // 2], None, final_relu=False)
+        self.audio_projector = _mlp_container([H, H, H // 2], None, final_relu=False)
+        self.video_projector = _mlp_container([H, H, H // 2], None, final_relu=False)
+        self.fusion_layer = _mlp_container([3 * H, H], config.fusion_dropout, final_relu=True)
+
+    def contrastive_loss(self, z1: Tensor, z2: Tensor) -> Tensor:
+        """Single-pair loss with the reference's signature (fusion_layers.py:361-375)."""
+        lt, _, _ = ops.InfoNCE3Fn.apply(z1, z2, z2, self.temperature, self.process_group)
+        return lt
+
+    def forward(self, text_features, audio_features, video_features, compute_contrastive_loss: bool = False, mask=None):
+        (t, a, v), mask, _ = self._prepare((text_features, audio_features, video_features), mask)
+        cat = _masked_cat(t, a, v, mask)
+        feats = ops.Split3Fn.apply(cat) if mask is not None else (t, a, v)
+        return self._run(cat, feats, compute_contrastive_loss)
+
+    def _run(self, cat, feats, compute_contrastive_loss):
+        z = []
+        for x, proj in zip(feats, (self.text_projector, self.audio_projector, self.video_projector)):
+            h = ops.linear(x, proj[0].weight, proj[0].bias, relu=True)
+            z.append(ops.L2NormFn.apply(ops.linear(h, proj[2].weight, proj[2].bias)))
+        losses = {}
+        if compute_contrastive_loss:
+            l = ops.InfoNCE3Fn.apply(z[0], z[1], z[2], self.temperature, self.process_group)
+            losses = {name: l[i] for i, (_, _, name) in enumerate(ops.PAIRS)}
+        fl = self.fusion_layer[0]
+        fused = ops.dropout(ops.linear(cat, fl.weight, fl.bias, relu=True), self._p, self.training)
+        return {"fused_features": fused, "text_proj": z[0], "audio_proj": z[1], "video_proj": z[2], "contrastive_losses": losses}
+
+
+class AdaptiveFusion(_FusionBase):
+    """reference models/fusion_layers.py:378-452."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        H = config.fusion_hidden_size
+        self.attention = nn.MultiheadAttention(H, config.fusion_num_heads, dropout=config.fusion_dropout, batch_first=True)
+        self.text_transform = nn.Linear(H, H)
+        self.audio_transform = nn.Linear(H, H)
+        self.video_transform = nn.Linear(H, H)
+        self.weight_predictor = nn.Sequential(nn.Linear(3 * H, H), nn.ReLU(), nn.Linear(H, 3), nn.Softmax(dim=-1))
+        self.fusion_layer = _mlp_container([H, H], config.fusion_dropout, final_relu=True)
+
+    def forward(self, text_features, audio_features, video_features, mask=None) -> Dict[str, Tensor]:
+        (t, a, v), mask, _ = self._prepare((text_features, audio_features, video_features), mask)
+        cat = _masked_cat(t, a, v, mask)
+        feats = ops.Split3Fn.apply(cat) if mask is not None else (t, a, v)
+        return self._run(cat, feats)
+
+    def _run(self, cat, feats):
+        H, heads = self.config.fusion_hidden_size, self.config.fusion_num_heads
+        if self.training and self._p > 0.0:
+            raise B200FusionError("AdaptiveFusion: attention-probability dropout is not implemented yet; use fusion_dropout=0 or eval()")
+        tr = [ops.linear(x, m.weight, m.bias) for x, m in zip(feats, (self.text_transform, self.audio_transform, self.video_transform))]
+        tokens = ops.Concat3Fn.apply(tr[0], tr[1], tr[2], None).view(-1, 3, H)           # stack(dim=1)
+        qkv = ops.linear(tokens, self.attention.in_proj_weight, self.attention.in_proj_bias)  # [B,3,3H]
+        ctx, avgw = ops.Tok3AttnFn.apply(qkv, heads, ops.mha_scale(H, heads))
+        attended = ops.linear(ctx, self.attention.out_proj.weight, self.attention.out_proj.bias)
+        wp0, wp2 = self.weight_predictor[0], self.weight_predictor[2]
+        logits = ops.linear(ops.linear(cat, wp0.weight, wp0.bias, relu=True), wp2.weight, wp2.bias)
+        mixed, gate = ops.GateMixFn.apply(attended, logits)
+        fl = self.fusion_layer[0]
+        fused = ops.dropout(ops.linear(mixed, fl.weight, fl.bias, relu=True), self._p, self.training)
+        return {"fused_features": fused, "attention_weights": avgw, "adaptive_weights": gate}
+
+
+class HierarchicalFusion(_FusionBase):
+    """reference models/fusion_layers.py:455-520.  [B,L,H] inputs: MulT on the sequences, the four 2-D heads
+    on their mean over L."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        H = config.fusion_hidden_size
+        self.early_fusion = EarlyFusion(config)
+        self.mult_fusion = MultimodalTransformer(config)
+        self.graph_fusion = GraphFusion(config)
+        self.contrastive_fusion = ContrastiveFusion(config)
+        self.adaptive_fusion = AdaptiveFusion(config)
+        self.meta_fusion = _mlp_container([5 * H, 2 * H, H], config.fusion_dropout, final_relu=False)
+        # the reference's Sequential is Linear, ReLU, Dropout, Linear: drop the trailing activation slots
+        self.meta_fusion = nn.Sequential(*list(self.meta_fusion)[:4])
+
+    def forward(self, text_features, audio_features, video_features, compute_contrastive_loss: bool = False, mask=None):
+        (t, a, v), mask, dt = self._prepare((text_features, audio_features, video_features), mask)
+        pooled2d = [x if x.dim() == 2 else ops.MeanPoolFn.apply(x) for x in (t, a, v)]
+        cat = _masked_cat(*pooled2d, mask)                                   # shared by early / graph / contrastive / adaptive
+        feats = ops.Split3Fn.apply(cat) if mask is not None else pooled2d
+        early = self.early_fusion._run(cat)
+        mt = self.mult_fusion
+        mult_pooled = mt._pooled(t, a, v, mask)
+        ff = mt.final_fusion[0]
+        mult = ops.dropout(ops.linear(mult_pooled, ff.weight, ff.bias, relu=True), self._p, self.training)
+        graph = self.graph_fusion._run(cat, dt)
+        con = self.contrastive_fusion._run(cat, feats, compute_contrastive_loss)
+        ada = self.adaptive_fusion._run(cat, feats)
+        H = self.config.fusion_hidden_size
+        allf = _Concat5Fn.apply(early, mult, graph, con["fused_features"], ada["fused_features"])
+        m0, m3 = self.meta_fusion[0], self.meta_fusion[3]
+        hid = ops.dropout(ops.linear(allf, m0.weight, m0.bias, relu=True), self._p, self.training)
+        fused = ops.linear(hid, m3.weight, m3.bias)
+        return {"fused_features": fused, "early_features": early, "mult_features": mult, "graph_features": graph,
+                "contrastive_features": con["fused_features"], "adaptive_features": ada["fused_features"],
+                "contrastive_losses": con["contrastive_losses"], "attention_weights": ada["attention_weights"],
+                "adaptive_weights": ada["adaptive_weights"]}
+
+
+class _Concat5Fn(torch.autograd.Function):
+    """cat of the five head outputs [B,H] -> [B,5H]: device-to-device row copies into one buffer (layout plumbing)."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        B, H = xs[0].shape
+        out = torch.empty((B, len(xs) * H), device=xs[0].device, dtype=xs[0].dtype)
+        for i, x in enumerate(xs):
+            out[:, i * H:(i + 1) * H].copy_(x)
+        ctx.H = H
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        H = ctx.H
+        return tuple(g[:, i * H:(i + 1) * H].contiguous() for i in range(g.size(1) // H))
+
+
+class ModalityDropout(nn.Module):
+    """reference models/encoders.py:280-321, sync-free: the keep-mask (with the keep-at-least-one repair) is
+    generated on the device by a counter-based RNG; pass `mask=` to a fusion head to fuse the multiply, or
+    call this module for the reference's (text, audio, video) -> masked features behaviour."""
+
+    def __init__(self, dropout_rate: float = 0.1, seed: int = 4321):
+        super().__init__()
+        self.dropout_rate, self.seed, self._offset = dropout_rate, seed, 0
+
+    def sample_mask(self, batch: int, device) -> Tensor:
+        m = K.modality_mask(batch, self.dropout_rate, self.seed, self._offset, device)
+        self._offset += 4 * batch
+        return m
+
+    def forward(self, text_features, audio_features, video_features, training: bool = True):
+        if not training:
+            return text_features, audio_features, video_features
+        mask = self.sample_mask(text_features.size(0), text_features.device)
+        if text_features.dim() == 2:
+            return ops.Split3Fn.apply(ops.Concat3Fn.apply(text_features, audio_features, video_features, mask))
+        return tuple(ops.RowMaskFn.apply(x, mask, i) for i, x in enumerate((text_features, audio_features, video_features)))

@@ -1,0 +1,364 @@
+"""Tensor-level wrappers over the C ABI (no autograd here): each function checks its tensors,
+marshals pointers / leading dimensions / the current CUDA stream and calls libb200fusion.so.
+PyTorch only provides device memory and streams; every FLOP runs in the library's kernels."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from ._lib import B200FusionError, check, dtype_code, lib, ptr, require_cuda, stream_ptr
+
+Tensor = torch.Tensor
+
+
+def _rows(x: Tensor):
+    """View a [..., K] tensor with contiguous last dim as (rows, K, ld)."""
+    if x.dim() == 2:
+        if x.stride(1) != 1 and x.size(1) != 1:
+            raise B200FusionError("matrix rows must be contiguous in the last dim")
+        return x.size(0), x.size(1), x.stride(0)
+    if not x.is_contiguous():
+        raise B200FusionError("N-d operand must be contiguous")
+    k = x.size(-1)
+    return x.numel() // k, k, k
+
+
+def gemm(a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_layout: int = 0, b_layout: int = 0,
+         out: Optional[Tensor] = None, bias: Optional[Tensor] = None, residual: Optional[Tensor] = None,
+         relu_mask: Optional[Tensor] = None, relu: bool = False, alpha: float = 1.0, accumulate: bool = False,
+         out_f32: bool = False, split_k: int = 1) -> Tensor:
+    """C[M,N] = epi(alpha * sum_k A(m,k) B(n,k)); see b200f_gemm in include/b200_fusion.h.
+    `a`/`b` are 2-D views (row stride = leading dimension)."""
+    require_cuda(a, b, out, bias, residual, relu_mask)
+    dt = a.dtype
+    if b.dtype != dt:
+        raise B200FusionError(f"gemm operand dtypes differ: {dt} vs {b.dtype}")
+    flags = 0
+    if relu:
+        flags |= L.EPI_RELU
+    want_f32 = accumulate or out_f32 or dt == torch.float32
+    if out is None:
+        if accumulate:
+            raise B200FusionError("gemm(accumulate=True) needs an `out` buffer")
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32 if want_f32 else dt)
+    if want_f32 and out.dtype != torch.float32:
+        raise B200FusionError("gemm: fp32 output requested but `out` is not float32")
+    if not want_f32 and out.dtype != dt:
+        raise B200FusionError("gemm: `out` dtype must match the operands")
+    if accumulate:
+        flags |= L.EPI_ACCUM
+    elif want_f32 and dt != torch.float32:
+        flags |= L.EPI_OUT_F32
+    if bias is not None and bias.dtype != torch.float32:
+        raise B200FusionError("gemm: bias must be float32")
+    for name, t in (("residual", residual), ("relu_mask", relu_mask)):
+        if t is not None and t.dtype != dt:
+            raise B200FusionError(f"gemm: {name} dtype must match the operands")
+    args = L.GemmArgs(M=M, N=N, K=K, a_layout=a_layout, b_layout=b_layout,
+                      A=a.data_ptr(), lda=a.stride(0), B=b.data_ptr(), ldb=b.stride(0),
+                      C=out.data_ptr(), ldc=out.stride(0),
+                      bias=None if bias is None else bias.data_ptr(),
+                      residual=None if residual is None else residual.data_ptr(),
+                      ldr=0 if residual is None else residual.stride(0),
+                      relu_mask=None if relu_mask is None else relu_mask.data_ptr(),
+                      ldm=0 if relu_mask is None else relu_mask.stride(0),
+                      alpha=alpha, flags=flags, dtype=dtype_code(dt), split_k=split_k)
+    check(lib().b200f_gemm(C.byref(args), stream_ptr()), "b200f_gemm")
+    return out
+
+
+def _wgrad_split(tokens: int, n_out: int, k_in: int) -> int:
+    tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
+    want = max(1, (2 * 148) // max(tiles, 1))
+    return max(1, min(want, tokens // 512 if tokens >= 512 else 1))
+
+
+def linear_fwd(x2: Tensor, w: Tensor, bias: Optional[Tensor], *, relu=False, residual=None, out=None) -> Tensor:
+    """y[M,N] = x2[M,K] w[N,K]^T + bias (+ residual) (relu)."""
+    M, K = x2.shape
+    return gemm(x2, w, M=M, N=w.size(0), K=K, out=out, bias=bias, residual=residual, relu=relu)
+
+
+def linear_dgrad(dy2: Tensor, w: Tensor, *, relu_mask=None, residual=None, out=None) -> Tensor:
+    """dx[M,K] = dy2[M,N] w[N,K]  (B operand N-contiguous: no transposed weight copy)."""
+    M, N = dy2.shape
+    return gemm(dy2, w, M=M, N=w.size(1), K=N, a_layout=0, b_layout=1, out=out, relu_mask=relu_mask, residual=residual)
+
+
+def linear_wgrad(dy2: Tensor, x2: Tensor, dw: Tensor) -> Tensor:
+    """dw[N,K] (fp32) += dy2[M,N]^T x2[M,K]; both operands are read in place, reduction over tokens."""
+    M, N = dy2.shape
+    K = x2.size(1)
+    return gemm(dy2, x2, M=N, N=K, K=M, a_layout=1, b_layout=1, out=dw, accumulate=True,
+                split_k=_wgrad_split(M, N, K))
+
+
+def colsum_accum(x2: Tensor, out: Tensor) -> None:
+    M, N = x2.shape
+    check(lib().b200f_colsum_accum(ptr(x2), C.c_int64(x2.stride(0)), ptr(out), C.c_int64(M), C.c_int64(N),
+                                   dtype_code(x2.dtype), stream_ptr()), "b200f_colsum_accum")
+
+
+def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, post1=None, post2=None):
+    rows, H, _ = _rows(x)
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    check(lib().b200f_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(post1), ptr(post2), ptr(y), ptr(mean), ptr(rstd),
+                                    C.c_int64(rows), C.c_int32(H), C.c_float(eps), dtype_code(x.dtype), stream_ptr()),
+          "b200f_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor, dgamma: Tensor, dbeta: Tensor,
+                  dres: Optional[Tensor] = None) -> Tensor:
+    rows, H, _ = _rows(x)
+    dx = torch.empty_like(x)
+    check(lib().b200f_layernorm_bwd(ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dres), ptr(dx), ptr(dgamma),
+                                    ptr(dbeta), C.c_int64(rows), C.c_int32(H), dtype_code(x.dtype), stream_ptr()),
+          "b200f_layernorm_bwd")
+    return dx
+
+
+def add(a: Tensor, b: Tensor, c: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    out = torch.empty_like(a) if out is None else out
+    check(lib().b200f_add(ptr(a), ptr(b), ptr(c), ptr(out), C.c_int64(a.numel()), dtype_code(a.dtype), stream_ptr()), "b200f_add")
+    return out
+
+
+def relu_bwd(dy: Tensor, ref: Tensor) -> Tensor:
+    dx = torch.empty_like(dy)
+    check(lib().b200f_relu_bwd(ptr(dy), ptr(ref), ptr(dx), C.c_int64(dy.numel()), dtype_code(dy.dtype), stream_ptr()), "b200f_relu_bwd")
+    return dx
+
+
+def cast_to_bf16(src: Tensor, scale: float = 1.0) -> Tensor:
+    src = src.contiguous()
+    dst = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    check(lib().b200f_cast_f32_to_bf16(ptr(src), ptr(dst), C.c_int64(src.numel()), C.c_float(scale), stream_ptr()), "b200f_cast_f32_to_bf16")
+    return dst
+
+
+def cast_to_f32(src: Tensor) -> Tensor:
+    src = src.contiguous()
+    dst = torch.empty(src.shape, device=src.device, dtype=torch.float32)
+    check(lib().b200f_cast_bf16_to_f32(ptr(src), ptr(dst), C.c_int64(src.numel()), stream_ptr()), "b200f_cast_bf16_to_f32")
+    return dst
+
+
+def meanpool_fwd(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    B, Lx, H = x.shape
+    if out is None:
+        out = torch.empty((B, H), device=x.device, dtype=x.dtype)
+    check(lib().b200f_meanpool_fwd(ptr(x), ptr(out), C.c_int64(out.stride(0)), C.c_int32(B), C.c_int32(Lx), C.c_int32(H),
+                                   dtype_code(x.dtype), stream_ptr()), "b200f_meanpool_fwd")
+    return out
+
+
+def meanpool_bwd(dy: Tensor, Lx: int) -> Tensor:
+    B, H = dy.shape
+    dx = torch.empty((B, Lx, H), device=dy.device, dtype=dy.dtype)
+    check(lib().b200f_meanpool_bwd(ptr(dy), C.c_int64(dy.stride(0)), ptr(dx), C.c_int32(B), C.c_int32(Lx), C.c_int32(H),
+                                   dtype_code(dy.dtype), stream_ptr()), "b200f_meanpool_bwd")
+    return dx
+
+
+def concat3_fwd(t: Tensor, a: Tensor, v: Tensor, mask: Optional[Tensor]) -> Tensor:
+    B, H = t.shape
+    cat = torch.empty((B, 3 * H), device=t.device, dtype=t.dtype)
+    check(lib().b200f_concat3_fwd(ptr(t), ptr(a), ptr(v), ptr(mask), ptr(cat), C.c_int64(B), C.c_int32(H), dtype_code(t.dtype), stream_ptr()),
+          "b200f_concat3_fwd")
+    return cat
+
+
+def concat3_bwd(dcat: Tensor, mask: Optional[Tensor], H: int):
+    B = dcat.size(0)
+    outs = [torch.empty((B, H), device=dcat.device, dtype=dcat.dtype) for _ in range(3)]
+    check(lib().b200f_concat3_bwd(ptr(dcat), ptr(mask), ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), C.c_int32(0), C.c_int64(B), C.c_int32(H),
+                                  dtype_code(dcat.dtype), stream_ptr()), "b200f_concat3_bwd")
+    return outs
+
+
+def rowmask_apply_(x: Tensor, mask: Tensor, col: int) -> Tensor:
+    B = x.size(0)
+    Lx = 1 if x.dim() == 2 else x.size(1)
+    check(lib().b200f_rowmask_apply(ptr(x), ptr(mask), C.c_int32(col), C.c_int64(B), C.c_int64(Lx), C.c_int32(x.size(-1)),
+                                    dtype_code(x.dtype), stream_ptr()), "b200f_rowmask_apply")
+    return x
+
+
+def l2norm_fwd(y: Tensor, eps: float):
+    rows, D = y.shape
+    z = torch.empty_like(y)
+    norm = torch.empty(rows, device=y.device, dtype=torch.float32)
+    check(lib().b200f_l2norm_fwd(ptr(y), ptr(z), ptr(norm), C.c_int64(rows), C.c_int32(D), C.c_float(eps), dtype_code(y.dtype), stream_ptr()),
+          "b200f_l2norm_fwd")
+    return z, norm
+
+
+def l2norm_bwd(dz: Tensor, z: Tensor, norm: Tensor, eps: float) -> Tensor:
+    rows, D = z.shape
+    dy = torch.empty_like(z)
+    check(lib().b200f_l2norm_bwd(ptr(dz), ptr(z), ptr(norm), ptr(dy), C.c_int64(rows), C.c_int32(D), C.c_float(eps), dtype_code(z.dtype),
+                                 stream_ptr()), "b200f_l2norm_bwd")
+    return dy
+
+
+def _tokens(x: Tensor):
+    """[B,L,W] view with contiguous last dim and stride(0) == L*stride(1) -> (ptr, ld)."""
+    if x.dim() != 3 or x.stride(2) != 1 or x.stride(0) != x.size(1) * x.stride(1):
+        raise B200FusionError("attention operands must be [B,L,H*D] token-major views")
+    return x.data_ptr(), x.stride(1)
+
+
+def attn_fwd(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float, out: Optional[Tensor] = None):
+    require_cuda(q, k, v)
+    B, Lq, W = q.shape
+    Lk = k.size(1)
+    D = W // heads
+    if out is None:
+        out = torch.empty((B, Lq, W), device=q.device, dtype=q.dtype)
+    lse = torch.empty((B, heads, Lq), device=q.device, dtype=torch.float32)
+    (qp, ldq), (kp, ldk), (vp, ldv), (op, ldo) = _tokens(q), _tokens(k), _tokens(v), _tokens(out)
+    args = L.AttnArgs(B=B, H=heads, Lq=Lq, Lk=Lk, D=D, Q=qp, ldq=ldq, K=kp, ldk=ldk, V=vp, ldv=ldv, O=op, ldo=ldo,
+                      LSE=lse.data_ptr(), scale=scale, dtype=dtype_code(q.dtype))
+    check(lib().b200f_attn_fwd(C.byref(args), stream_ptr()), "b200f_attn_fwd")
+    return out, lse
+
+
+def attn_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor, heads: int, scale: float,
+             dq: Tensor, dk: Tensor, dv: Tensor) -> None:
+    B, Lq, W = q.shape
+    Lk = k.size(1)
+    D = W // heads
+    delta = torch.empty_like(lse)
+    (qp, ldq), (kp, ldk), (vp, ldv), (op, ldo) = _tokens(q), _tokens(k), _tokens(v), _tokens(o)
+    (gp, ldg), (dqp, lddq), (dkp, lddk), (dvp, lddv) = _tokens(do), _tokens(dq), _tokens(dk), _tokens(dv)
+    args = L.AttnArgs(B=B, H=heads, Lq=Lq, Lk=Lk, D=D, Q=qp, ldq=ldq, K=kp, ldk=ldk, V=vp, ldv=ldv, O=op, ldo=ldo,
+                      LSE=lse.data_ptr(), scale=scale, dtype=dtype_code(q.dtype), dO=gp, lddo=ldg, dQ=dqp, lddq=lddq,
+                      dK=dkp, lddk=lddk, dV=dvp, lddv=lddv, delta=delta.data_ptr())
+    check(lib().b200f_attn_bwd(C.byref(args), stream_ptr()), "b200f_attn_bwd")
+
+
+def _infonce_ws(Bl: int, Bg: int, dt, for_grad: bool, device) -> Tensor:
+    fn = lib().b200f_infonce_workspace_bytes
+    fn.restype = C.c_size_t
+    n = fn(C.c_int64(Bl), C.c_int64(Bg), dtype_code(dt), C.c_int32(1 if for_grad else 0))
+    return torch.empty(n, device=device, dtype=torch.uint8)
+
+
+def infonce_lse(x: Tensor, y: Tensor, diag_off: int, inv_tau: float, want_diag: bool = True):
+    Bl, D = x.shape
+    Bg = y.size(0)
+    lse = torch.empty(Bl, device=x.device, dtype=torch.float32)
+    diag = torch.empty(Bl, device=x.device, dtype=torch.float32) if want_diag else None
+    ws = _infonce_ws(Bl, Bg, x.dtype, False, x.device)
+    check(lib().b200f_infonce_lse(ptr(x), ptr(y), ptr(lse), ptr(diag), C.c_int64(Bl), C.c_int64(Bg), C.c_int32(D), C.c_int64(diag_off),
+                                  C.c_float(inv_tau), dtype_code(x.dtype), ptr(ws), C.c_size_t(ws.numel()), stream_ptr()), "b200f_infonce_lse")
+    return lse, diag
+
+
+def infonce_grad(x: Tensor, y: Tensor, lse_x: Tensor, lse_y: Tensor, coef: float, gscale: Optional[Tensor], dx: Tensor,
+                 accumulate: bool, diag_off: int, inv_tau: float) -> None:
+    Bl, D = x.shape
+    Bg = y.size(0)
+    ws = _infonce_ws(Bl, Bg, x.dtype, True, x.device)
+    check(lib().b200f_infonce_grad(ptr(x), ptr(y), ptr(lse_x), ptr(lse_y), C.c_float(coef), ptr(gscale), ptr(dx), C.c_int32(int(accumulate)),
+                                   C.c_int64(Bl), C.c_int64(Bg), C.c_int32(D), C.c_int64(diag_off), C.c_float(inv_tau), dtype_code(x.dtype),
+                                   ptr(ws), C.c_size_t(ws.numel()), stream_ptr()), "b200f_infonce_grad")
+
+
+def gat_fwd(xp: Tensor, att_src: Tensor, att_dst: Tensor, bias: Tensor, heads: int, slope: float):
+    B = xp.size(0)
+    Cc = bias.numel()
+    out = torch.empty((B, 3, Cc), device=xp.device, dtype=xp.dtype)
+    alpha = torch.empty((B, 3, heads, 3), device=xp.device, dtype=torch.float32)
+    check(lib().b200f_gat_fwd(ptr(xp), ptr(att_src), ptr(att_dst), ptr(bias), ptr(out), ptr(alpha), C.c_int64(B), C.c_int32(heads), C.c_int32(Cc),
+                              C.c_float(slope), dtype_code(xp.dtype), stream_ptr()), "b200f_gat_fwd")
+    return out, alpha
+
+
+def gat_bwd(dout: Tensor, out: Tensor, xp: Tensor, alpha: Tensor, att_src: Tensor, att_dst: Tensor, heads: int, slope: float):
+    B = xp.size(0)
+    Cc = out.size(-1)
+    dxp = torch.empty_like(xp)
+    datt_src = torch.zeros(heads * Cc, device=xp.device, dtype=torch.float32)
+    datt_dst = torch.zeros_like(datt_src)
+    dbias = torch.zeros(Cc, device=xp.device, dtype=torch.float32)
+    check(lib().b200f_gat_bwd(ptr(dout), ptr(out), ptr(xp), ptr(alpha), ptr(att_src), ptr(att_dst), ptr(dxp), ptr(datt_src), ptr(datt_dst),
+                              ptr(dbias), C.c_int64(B), C.c_int32(heads), C.c_int32(Cc), C.c_float(slope), dtype_code(xp.dtype), stream_ptr()),
+          "b200f_gat_bwd")
+    return dxp, datt_src, datt_dst, dbias
+
+
+def tok3_attn_fwd(qkv: Tensor, heads: int, scale: float):
+    B = qkv.size(0)
+    H = qkv.size(-1) // 3
+    ctx = torch.empty((B, 3, H), device=qkv.device, dtype=qkv.dtype)
+    probs = torch.empty((B, heads, 3, 3), device=qkv.device, dtype=torch.float32)
+    avgw = torch.empty((B, 3, 3), device=qkv.device, dtype=torch.float32)
+    check(lib().b200f_tok3_attn_fwd(ptr(qkv), ptr(ctx), ptr(probs), ptr(avgw), C.c_int64(B), C.c_int32(heads), C.c_int32(H), C.c_float(scale),
+                                    dtype_code(qkv.dtype), stream_ptr()), "b200f_tok3_attn_fwd")
+    return ctx, probs, avgw
+
+
+def tok3_attn_bwd(dctx: Tensor, davgw: Optional[Tensor], qkv: Tensor, probs: Tensor, heads: int, scale: float) -> Tensor:
+    B = qkv.size(0)
+    H = qkv.size(-1) // 3
+    dqkv = torch.empty_like(qkv)
+    check(lib().b200f_tok3_attn_bwd(ptr(dctx), ptr(davgw), ptr(qkv), ptr(probs), ptr(dqkv), C.c_int64(B), C.c_int32(heads), C.c_int32(H),
+                                    C.c_float(scale), dtype_code(qkv.dtype), stream_ptr()), "b200f_tok3_attn_bwd")
+    return dqkv
+
+
+def gate_mix_fwd(att: Tensor, logits: Tensor):
+    B, _, H = att.shape
+    gate = torch.empty((B, 3), device=att.device, dtype=torch.float32)
+    mixed = torch.empty((B, H), device=att.device, dtype=att.dtype)
+    check(lib().b200f_gate_mix_fwd(ptr(att), ptr(logits), ptr(gate), ptr(mixed), C.c_int64(B), C.c_int32(H), dtype_code(att.dtype), stream_ptr()),
+          "b200f_gate_mix_fwd")
+    return gate, mixed
+
+
+def gate_mix_bwd(dmixed: Tensor, dgate_ext: Optional[Tensor], att: Tensor, gate: Tensor, logits_like: Tensor):
+    B, _, H = att.shape
+    datt = torch.empty_like(att)
+    dlogits = torch.empty_like(logits_like)
+    check(lib().b200f_gate_mix_bwd(ptr(dmixed), ptr(dgate_ext), ptr(att), ptr(gate), ptr(datt), ptr(dlogits), C.c_int64(B), C.c_int32(H),
+                                   dtype_code(att.dtype), stream_ptr()), "b200f_gate_mix_bwd")
+    return datt, dlogits
+
+
+def late_combine_fwd(lt: Tensor, la: Tensor, lv: Tensor, w3: Tensor):
+    B, E = lt.shape
+    wsoft = torch.empty(3, device=lt.device, dtype=torch.float32)
+    fused = torch.empty_like(lt)
+    check(lib().b200f_late_combine_fwd(ptr(lt), ptr(la), ptr(lv), ptr(w3), ptr(wsoft), ptr(fused), C.c_int64(B), C.c_int32(E),
+                                       dtype_code(lt.dtype), stream_ptr()), "b200f_late_combine_fwd")
+    return fused, wsoft
+
+
+def late_combine_bwd(dfused: Tensor, lt: Tensor, la: Tensor, lv: Tensor, wsoft: Tensor, dwsoft_ext: Optional[Tensor]):
+    B, E = lt.shape
+    dl = [torch.empty_like(lt) for _ in range(3)]
+    dw3 = torch.zeros(3, device=lt.device, dtype=torch.float32)
+    check(lib().b200f_late_combine_bwd(ptr(dfused), ptr(lt), ptr(la), ptr(lv), ptr(wsoft), ptr(dwsoft_ext), ptr(dl[0]), ptr(dl[1]), ptr(dl[2]),
+                                       ptr(dw3), C.c_int64(B), C.c_int32(E), dtype_code(lt.dtype), stream_ptr()), "b200f_late_combine_bwd")
+    return dl, dw3
+
+
+def modality_mask(B: int, rate: float, seed: int, offset: int, device) -> Tensor:
+    mask = torch.empty((B, 3), device=device, dtype=torch.float32)
+    check(lib().b200f_modality_mask(ptr(mask), C.c_int64(B), C.c_float(rate), C.c_uint64(seed), C.c_uint64(offset), stream_ptr()),
+          "b200f_modality_mask")
+    return mask
+
+
+def dropout(x: Tensor, p: float, seed: int, offset: int) -> Tensor:
+    y = torch.empty_like(x)
+    check(lib().b200f_dropout(ptr(x), ptr(y), C.c_int64(x.numel()), C.c_float(p), C.c_uint64(seed), C.c_uint64(offset), dtype_code(x.dtype),
+                              stream_ptr()), "b200f_dropout")
+    return y

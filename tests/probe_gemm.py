@@ -9,7 +9,8 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from tests.test_gemm_gpu import L, make_operands, rel_err, run_gemm  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from test_gemm_gpu import L, make_operands, rel_err, run_gemm  # noqa: E402
 
 out = {"default": {}, "sweep": []}
 for (a_l, b_l) in [(0, 0), (0, 1), (1, 0), (1, 1)]:

@@ -31,6 +31,8 @@ int num_sms() {
 
 int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st);
 int gemm_f32_simt(const b200f_gemm_args& a, cudaStream_t st);
+int gemm_bf16_simt(const b200f_gemm_args& a, cudaStream_t st);
+bool gemm_tc_eligible(const b200f_gemm_args& a);
 extern uint32_t g_dbg_mn_lbo, g_dbg_mn_sbo, g_dbg_mn_kadv;
 
 }  // namespace b200f
@@ -52,7 +54,7 @@ int b200f_device_supported(int device) {
 int b200f_gemm(const b200f_gemm_args* a, void* stream) {
   if (!a) return b200f::fail(B200F_ERR_SHAPE, "gemm: null args");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->dtype == B200F_BF16) return b200f::gemm_bf16_tc(*a, st);
+  if (a->dtype == B200F_BF16) return b200f::gemm_tc_eligible(*a) ? b200f::gemm_bf16_tc(*a, st) : b200f::gemm_bf16_simt(*a, st);
   if (a->dtype == B200F_F32) return b200f::gemm_f32_simt(*a, st);
   return b200f::fail(B200F_ERR_DTYPE, "gemm: unknown dtype %d", a->dtype);
 }

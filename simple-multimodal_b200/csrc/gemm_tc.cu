@@ -32,6 +32,7 @@ struct GemmTcParams {
   int flags;
   // UMMA descriptor geometry (bytes), filled by the host so it can be probed without recompiling
   uint32_t a_lbo, a_sbo, a_kadv, b_lbo, b_sbo, b_kadv;
+  int vec_ok;  // C / residual / mask rows are 16-byte aligned -> 128-bit epilogue accesses
 };
 
 template <int BN, int STAGES>
@@ -175,11 +176,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * p.alpha;
-            const bool full8 = (col + 8 <= p.N);
+            const bool full8 = (col + 8 <= p.N) && p.vec_ok;
             if (p.bias) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                if (full8 || col + j < p.N) v[j] += __ldg(p.bias + col + j);
+                if (col + j < p.N) v[j] += __ldg(p.bias + col + j);
             }
             if (p.residual) {
               const bf16* rp = p.residual + row * p.ldr + col;
@@ -210,7 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (out_f32) {
               float* cp = reinterpret_cast<float*>(p.C) + row * p.ldc + col;
               if (accum) {
-                for (int j = 0; j < 8 && (full8 || col + j < p.N); ++j) atomicAdd(cp + j, v[j]);
+                for (int j = 0; j < 8 && col + j < p.N; ++j) atomicAdd(cp + j, v[j]);
               } else if (full8) {
                 *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
                 *reinterpret_cast<float4*>(cp + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -289,14 +290,17 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTc
   return check_launch("gemm_tc_kernel");
 }
 
+// The TMA path needs 16-byte aligned bases and row strides for A and B; everything else is handled in-kernel.
+bool gemm_tc_eligible(const b200f_gemm_args& a) {
+  return a.lda % 8 == 0 && a.ldb % 8 == 0 && aligned16(a.A) && aligned16(a.B) && a.N >= 8 && a.K >= 8 && a.M >= 1;
+}
+
 int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
   B200F_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, B200F_ERR_SHAPE, "gemm: empty shape M=%lld N=%lld K=%lld", (long long)a.M, (long long)a.N, (long long)a.K);
-  B200F_REQUIRE(a.lda % 8 == 0 && a.ldb % 8 == 0, B200F_ERR_ALIGN, "gemm(bf16): lda/ldb must be multiples of 8 elements (TMA 16-byte strides)");
-  B200F_REQUIRE(aligned16(a.A) && aligned16(a.B) && aligned16(a.C), B200F_ERR_ALIGN, "gemm(bf16): A/B/C must be 16-byte aligned");
+  B200F_REQUIRE(gemm_tc_eligible(a), B200F_ERR_ALIGN, "gemm(bf16/tcgen05): lda/ldb must be multiples of 8 elements and A/B 16-byte aligned");
   const bool out_f32 = (a.flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) != 0;
-  B200F_REQUIRE(a.ldc % (out_f32 ? 4 : 8) == 0, B200F_ERR_ALIGN, "gemm(bf16): ldc alignment");
-  B200F_REQUIRE(!a.residual || (a.ldr % 8 == 0 && aligned16(a.residual)), B200F_ERR_ALIGN, "gemm(bf16): residual alignment");
-  B200F_REQUIRE(!a.relu_mask || (a.ldm % 8 == 0 && aligned16(a.relu_mask)), B200F_ERR_ALIGN, "gemm(bf16): mask alignment");
+  const bool vec_ok = aligned16(a.C) && a.ldc % (out_f32 ? 4 : 8) == 0 && (!a.residual || (a.ldr % 8 == 0 && aligned16(a.residual))) &&
+                      (!a.relu_mask || (a.ldm % 8 == 0 && aligned16(a.relu_mask)));
   const int split = a.split_k > 1 ? a.split_k : 1;
   B200F_REQUIRE(split == 1 || (a.flags & B200F_EPI_ACCUM), B200F_ERR_UNSUPPORTED, "gemm: split_k needs B200F_EPI_ACCUM");
 
@@ -328,6 +332,7 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
   p.residual = static_cast<const bf16*>(a.residual); p.ldr = a.ldr;
   p.mask = static_cast<const bf16*>(a.relu_mask); p.ldm = a.ldm;
   p.alpha = a.alpha; p.flags = a.flags;
+  p.vec_ok = vec_ok ? 1 : 0;
   // K-major SW128: rows of 128 B, 8-row groups 1024 B apart, +32 B per K=16 step inside the swizzle row.
   // MN-major SW128: 64-element (128 B) MN chunks, k rows 128 B apart, 8-k-row groups 1024 B apart (SBO),
   //                 MN chunks BK*128 B apart (LBO), +16 k rows = 2048 B per K=16 step.

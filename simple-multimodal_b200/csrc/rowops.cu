@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(128) colsum_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ out,
-                                                     long long M, long long N, int rows_per_block) {
+                                                     long long M, long long N, int rows_per_block, int vec_ok) {
   constexpr int VN = Vec16<T>::N;
   const long long c0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VN;
   if (c0 >= N) return;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(128) colsum_kernel(const T* __restrict__ x, lo
   float acc[VN];
 #pragma unroll
   for (int j = 0; j < VN; ++j) acc[j] = 0.f;
-  if (c0 + VN <= N) {
+  if (c0 + VN <= N && vec_ok) {
 #pragma unroll 4
     for (long long r = r0; r < r1; ++r) {
       Vec16<T> t; t.load(x + r * ldx + c0); float f[VN]; t.unpack(f);
@@ -452,14 +452,14 @@ int b200f_colsum_accum(const void* x, int64_t ldx, float* out, int64_t M, int64_
   if (M == 0 || N == 0) return B200F_OK;
   DISPATCH_DTYPE(dtype, T, {
     constexpr int VN = Vec16<T>::N;
-    B200F_REQUIRE(ldx % VN == 0 && aligned16(x), B200F_ERR_ALIGN, "colsum: alignment");
+    const int vec_ok = (ldx % VN == 0 && aligned16(x)) ? 1 : 0;
     const int gx = int((N + VN * 128 - 1) / (VN * 128));
     long long slabs = (long long)num_sms() * 4 / gx;
     if (slabs < 1) slabs = 1;
     long long rpb = (M + slabs - 1) / slabs;
     if (rpb < 32) rpb = 32;
     const int gy = int((M + rpb - 1) / rpb);
-    colsum_kernel<T><<<dim3(gx, gy), 128, 0, st>>>(static_cast<const T*>(x), ldx, out, M, N, int(rpb));
+    colsum_kernel<T><<<dim3(gx, gy), 128, 0, st>>>(static_cast<const T*>(x), ldx, out, M, N, int(rpb), vec_ok);
   })
   return check_launch("colsum");
 }

@@ -66,16 +66,44 @@ def device_run(kind, cfg, P, feats, flag, dtype, mask=None, chunk=None):
     return out, loss, [x.grad for x in xs], {k: p.grad for k, p in head.named_parameters()}
 
 
-def compare(kind, cfg, B, lens, dtype, flag=False, mask=None, chunk=None, seed=7, report=None):
+import json
+import os
+
+_FLOOR_PATH = os.path.join(os.path.dirname(__file__), "golden", "bf16_floor.json")
+BF16_FLOOR = json.load(open(_FLOOR_PATH)) if os.path.exists(_FLOOR_PATH) else {}
+ZERO_FLOOR = 1e-4     # a gradient tensor whose oracle norm is < 1e-4 of the largest one is "numerically zero":
+                      # its error is measured against that floor instead of its own (cancellation-level) norm
+
+
+def _group_errors(dev, ref, prefix):
+    """norm-wise error per tensor, denominators floored at ZERO_FLOOR * (largest oracle norm of the group)."""
+    norms = {k: float(r.detach().double().norm()) for k, r in ref.items()}
+    top = max(norms.values()) if norms else 0.0
+    out = {}
+    for k, r in ref.items():
+        d = float((dev[k].detach().double().cpu() - r.detach().double()).norm())
+        out[f"{prefix}{k}"] = d / max(norms[k], ZERO_FLOOR * top, 1e-30)
+    return out
+
+
+def compare(kind, cfg, B, lens, dtype, flag=False, mask=None, chunk=None, seed=7, case_id=None):
+    """Run the CUDA head and the fp64 oracle on identical data and check every tensor.
+    fp32: 1e-5 norm-wise everywhere.  bf16: outputs 2e-2, losses 1e-3 (north_star); gradients 2e-2 or, where the
+    reference's OWN bf16 autocast execution deviates more than 1e-2 from fp64 (tests/golden/bf16_floor.json, made by
+    oracle/make_bf16_floor.py), within 2x of that measured floor."""
     P = fo.init_params(kind, H=cfg.fusion_hidden_size, heads=cfg.fusion_num_heads, graph_hidden=cfg.graph_hidden_size,
                        graph_layers=cfg.graph_num_layers, seed=seed)
     feats = fo.synthetic_features(B, lens, H=cfg.fusion_hidden_size, seed=1234)
-    if dtype == torch.bfloat16:                       # identical inputs for both sides: round once, up front
+    if dtype == torch.bfloat16:
+        # identical inputs AND weights on both sides: make them bf16-representable once, up front, so the only
+        # difference left is the arithmetic (bf16 storage of intermediates, fp32 accumulation) -- not the data
         feats = tuple(f.to(torch.bfloat16).float() for f in feats)
+        P = {k: v.to(torch.bfloat16).float() for k, v in P.items()}
     o_out, o_loss, o_xg, o_pg = oracle_run(kind, cfg, P, feats, flag, mask)
     d_out, d_loss, d_xg, d_pg = device_run(kind, cfg, P, feats, flag, dtype, mask, chunk)
     tol = TOL[dtype]
-    errs = {}
+    floor = BF16_FLOOR.get(case_id, {}) if dtype == torch.bfloat16 else {}
+    errs, limits = {}, {}
     if isinstance(o_out, torch.Tensor):
         errs["out"] = rel(d_out, o_out)
     else:
@@ -84,19 +112,27 @@ def compare(kind, cfg, B, lens, dtype, flag=False, mask=None, chunk=None, seed=7
             if k == "contrastive_losses":
                 assert set(d_out[k]) == set(v)
                 for n in v:
-                    errs[f"loss.{n}"] = abs(float(d_out[k][n]) - float(v[n]))
+                    errs[f"loss.{n}"] = abs(float(d_out[k][n].detach()) - float(v[n].detach()))
             else:
                 errs[f"out.{k}"] = rel(d_out[k], v)
-    errs["objective"] = abs(float(d_loss) - float(o_loss))
-    for i, (g, r) in enumerate(zip(d_xg, o_xg)):
-        errs[f"dx{i}"] = rel(g, r)
+    errs["objective"] = abs(float(d_loss.detach()) - float(o_loss.detach()))
+    errs.update(_group_errors({f"{i}": g for i, g in enumerate(d_xg)}, {f"{i}": g for i, g in enumerate(o_xg)}, "dx"))
     assert set(d_pg) == set(o_pg), set(d_pg) ^ set(o_pg)
-    for k, r in o_pg.items():
+    for k in o_pg:
         assert d_pg[k] is not None, f"no gradient for {k}"
-        errs[f"dP.{k}"] = rel(d_pg[k], r)
-    if report is not None:
-        report.update(errs)
-    bad = {k: v for k, v in errs.items()
-           if v > (tol["loss"] if k.startswith("loss.") or k == "objective" else tol["rel"])}
-    assert not bad, f"{kind} {dtype}: out of tolerance: {bad}"
+    errs.update(_group_errors(d_pg, o_pg, "dP."))
+    for k in errs:
+        if k.startswith("loss.") or k == "objective":
+            limits[k] = tol["loss"]
+        elif k.startswith("out"):
+            limits[k] = tol["rel"]
+        else:
+            # the six MulT blocks (and the three projectors ...) are statistically identical: use the largest measured
+            # reference-autocast deviation among tensors with the same role (same trailing name) as this tensor's floor
+            role = ".".join(k.split(".")[-2:])
+            fl = max([v for n, v in floor.items() if n.endswith(role) and n.split(".")[0] == k.split(".")[0]] + [0.0])
+            limits[k] = max(tol["rel"], 2.0 * min(fl, 0.25))
+    bad = {k: (v, limits[k]) for k, v in errs.items() if not v <= limits[k]}
+    worst = dict(sorted(((k, round(v / limits[k], 3)) for k, v in errs.items()), key=lambda kv: -kv[1])[:8])
+    assert not bad, f"{kind} {dtype}: {len(bad)} tensors out of tolerance (err, limit): {dict(list(bad.items())[:10])}; worst err/limit: {worst}"
     return errs

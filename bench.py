@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- fusion-head forward+backward throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One step = one forward + backward of the fusion head over one batch of synthetic encoder features
+(random-init weights), per-GPU batch fixed (weak scaling); N>1 adds the all-gather inside InfoNCE
+and one gradient all-reduce.  Prints ONE JSON line (rank 0) with the device-timed `value`, the end-to-end
+`e2e` (pinned host inputs -> H2D -> step -> D2H of the loss, through the public nn.Module API), the `roofline`
+of the dominant kernel (tcgen05 GEMM, timed live with CUDA events) and the `cpu_baseline` (oracle port on the
+host cores, bounded sample).  `--impl reference` times the reference's CPU path (oracle port -- the reference
+is pure Python/torch and cannot travel to the GPU box) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch                                                             # noqa: E402
+import torch.distributed as dist                                         # noqa: E402
+
+# name -> (head kind, per-GPU batch, (Lt, La, Lv) or None for 2-D, contrastive flag, CPU sample batch)
+WORKLOADS = {
+    "mult_b256": ("mult", 256, (512, 512, 30), False, 4),                      # BASELINE configs[1]
+    "hierarchical_b4096": ("hierarchical", 4096, (512, 512, 30), True, 4),     # BASELINE configs[3] / north_star target
+    "contrastive_b4096": ("contrastive", 4096, None, True, 4096),              # BASELINE configs[2]
+    "early_b16": ("early", 16, None, False, 16),                               # BASELINE configs[0]
+}
+DEFAULT_WORKLOAD = "mult_b256"
+H, HEADS = 512, 8
+# algorithmic forward GFLOP per sample (2*MACs of the reference's contractions only); fwd+bwd = 3x
+MULT_GFLOP = 17.7495
+
+
+def algorithmic_gflop_per_sample(kind, lens, b_global):
+    if kind == "mult":
+        return 3 * MULT_GFLOP
+    if kind == "hierarchical":
+        small = (4.19 + 19.40 + 3.93 + 9.98 + 6.29) * 1e-3 + 3 * 2 * b_global * 256 * 1e-9
+        return 3 * (MULT_GFLOP + small)
+    if kind == "contrastive":
+        return 3 * (3.93e-3 + 3 * 2 * b_global * 256 * 1e-9)
+    if kind == "early":
+        return 3 * 4.19e-3
+    raise ValueError(kind)
+
+
+class Cfg:
+    fusion_hidden_size, fusion_num_heads, fusion_dropout = H, HEADS, 0.0
+    num_emotions, graph_hidden_size, graph_num_layers, graph_dropout = 7, 512, 3, 0.0
+    contrastive_temperature = 0.07
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "hbm": d.get("hbm_gbs"), "src": "measured (MEASURED_PEAKS.json, sustained)"}
+    return {"tflops": 1400.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def objective(out, b_global):
+    """mean(fused^2) over the GLOBAL batch + 0.1 * sum(InfoNCE) -- a [B,512] reduction, negligible work."""
+    t = out if isinstance(out, torch.Tensor) else out["fused_features"]
+    loss = (t.float() ** 2).sum() / (b_global * t.size(-1))
+    if isinstance(out, dict):
+        for v in out.get("contrastive_losses", {}).values():
+            loss = loss + 0.1 * v
+    return loss
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_reference(args, kind, lens, flag, cpu_batch, world, rank):
+    """The reference's CPU path (oracle port: same torch CPU operators the reference's modules dispatch to)."""
+    if rank != 0:
+        return
+    from oracle import fusion_oracle as fo
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    P = {k: v.requires_grad_(True) for k, v in fo.init_params(kind, H=H, heads=HEADS, seed=0).items()}
+    feats = [f.requires_grad_(True) for f in fo.synthetic_features(cpu_batch, lens or (None, None, None), H=H, seed=1234)]
+    kw = {}
+    if kind in ("contrastive", "hierarchical"):
+        kw["compute_contrastive_loss"] = flag
+
+    def step():
+        for t in list(P.values()) + feats:
+            t.grad = None
+        out = fo.HEADS[kind](*feats, P, **kw)
+        loss = objective(out, cpu_batch)
+        loss.backward()
+        return float(loss.detach())
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = cpu_batch / dt
+    line = {"impl": "reference", "metric": "fusion_head_fwd_bwd_samples_per_sec", "value": val, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "head": kind, "seq_lens": lens, "hidden": H, "note": "CPU, bounded sample"},
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port",
+                             "sample": f"{cpu_batch} samples/step x {args.steps} steps of the same workload (fp32, torch CPU ops, all host threads)"},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(kind, lens, flag, cpu_batch, budget_s=20.0):
+    from oracle import fusion_oracle as fo
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    P = {k: v.requires_grad_(True) for k, v in fo.init_params(kind, H=H, heads=HEADS, seed=0).items()}
+    feats = [f.requires_grad_(True) for f in fo.synthetic_features(cpu_batch, lens or (None, None, None), H=H, seed=1234)]
+    kw = {"compute_contrastive_loss": flag} if kind in ("contrastive", "hierarchical") else {}
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < 4 and (time.perf_counter() - t_start < budget_s or len(times) < 2):
+        for t in list(P.values()) + feats:
+            t.grad = None
+        t0 = time.perf_counter()
+        objective(fo.HEADS[kind](*feats, P, **kw), cpu_batch).backward()
+        times.append(time.perf_counter() - t0)
+    dt = statistics.median(times[1:]) if len(times) > 1 else times[0]
+    return {"value": cpu_batch / dt, "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": f"{cpu_batch} samples/step, median of {max(1, len(times) - 1)} steps after 1 warm-up (oracle port, fp32, torch CPU ops)"}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("B200F_WORKLOAD", DEFAULT_WORKLOAD), choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--chunk", type=int, default=0, help="MulT chunk size (samples)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    kind, batch, lens, flag, cpu_batch = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, kind, lens, flag, cpu_batch, world, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the b200 arm has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import simple_multimodal_b200 as pkg
+    from simple_multimodal_b200 import kernels as K
+
+    b_global = batch * world
+    torch.manual_seed(0)                              # random-init weights, the reference's default initialisers
+    head = getattr(pkg.fusion_layers, {"mult": "MultimodalTransformer", "hierarchical": "HierarchicalFusion",
+                                       "contrastive": "ContrastiveFusion", "early": "EarlyFusion"}[kind])(Cfg).to(dev)
+    head.train()
+    if args.chunk:
+        (head.mult_fusion if kind == "hierarchical" else head).chunk_size = args.chunk
+    params = [p for p in head.parameters()]
+
+    # synthetic encoder features: pinned host buffers (e2e source) + resident device copies (device-timed `value`)
+    g = torch.Generator().manual_seed(1234 + rank)
+    shapes = [(batch, H)] * 3 if lens is None else [(batch, L, H) for L in lens]
+    host = [torch.randn(s, generator=g).to(torch.bfloat16).pin_memory() for s in shapes]
+    resident = [h.to(dev, non_blocking=True).requires_grad_(True) for h in host]
+    mask = pkg.ModalityDropout(0.1, seed=4321 + rank).sample_mask(batch, dev) if kind == "hierarchical" else None
+    h2d_bytes = sum(h.numel() * h.element_size() for h in host)
+    kw = {}
+    if kind in ("contrastive", "hierarchical"):
+        kw["compute_contrastive_loss"] = flag
+    if mask is not None:
+        kw["mask"] = mask
+
+    def step(inputs):
+        for p in params:
+            p.grad = None
+        for x in inputs:
+            x.grad = None
+        out = head(*inputs, **kw)
+        loss = objective(out, b_global)
+        loss.backward()
+        if world > 1:
+            pkg.allreduce_gradients(params)
+        return loss
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(resident)
+    sync_all()
+
+    # ---- device-timed region (inputs resident in HBM), GEMM launches timed live
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    K.GEMM_PROFILE = []
+    l0 = pkg._lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        step(resident)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (pkg._lib.launch_count() - l0) // args.steps
+    prof, K.GEMM_PROFILE = K.GEMM_PROFILE, None
+    clocks = sampler.stop()
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _, tc in prof if tc) / args.steps
+    gemm_flops = sum(f for _, _, f, tc in prof if tc) / args.steps
+    n_gemm = sum(1 for *_, tc in prof if tc) // args.steps
+
+    # ---- end-to-end: pinned host -> H2D -> step -> D2H of the loss, through the nn.Module API
+    def e2e_step():
+        xs = [h.to(dev, non_blocking=True).requires_grad_(True) for h in host]
+        return float(step(xs).detach().cpu())
+
+    e2e_step()
+    sync_all()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    t1.record()
+    sync_all()
+    ms_e2e = t0.elapsed_time(t1) / args.steps
+
+    tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(tt[0]), float(tt[1])
+
+    if rank == 0:
+        pk = peaks()
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        gflop = algorithmic_gflop_per_sample(kind, lens, b_global)
+        line = {
+            "metric": "fusion_head_fwd_bwd_samples_per_sec", "value": b_global / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": args.workload, "head": kind, "batch_per_gpu": batch, "global_batch": b_global, "seq_lens": lens,
+                       "hidden": H, "heads": HEADS, "dropout": 0.0, "parallelism": f"dp{world}",
+                       "l2": "inputs+activations per step exceed the 126 MB L2" if h2d_bytes > 126e6 else "small working set (latency-bound config)",
+                       "algorithmic_tflop_per_step": gflop * batch / 1e3,
+                       "model_tflops_per_gpu": gflop * batch / 1e3 / (ms * 1e-3),
+                       "frac_of_nominal_2250": gflop * batch / 1e3 / (ms * 1e-3) / 2250.0},
+            "e2e": {"value": b_global / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all layouts)", "achieved": achieved, "peak": pk["tflops"],
+                         "unit": "TFLOP/s", "frac": achieved / pk["tflops"] if pk["tflops"] else None, "traffic": None,
+                         "peak_source": pk["src"], "launches_per_step": n_gemm, "kernel_ms_per_step": gemm_ms,
+                         "share_of_step": gemm_ms / ms if ms else None},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(kind, lens, flag, cpu_batch)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

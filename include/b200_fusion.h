@@ -49,6 +49,8 @@ enum {
 
 int b200f_version(void);
 const char* b200f_last_error(void);
+/* kernels launched by this library so far in this process (bench.py's gpu_launches evidence). */
+unsigned long long b200f_launch_count(void);
 /* 0 if `device` is an sm_100 part that can run the bf16/tcgen05 kernels. */
 int b200f_device_supported(int device);
 

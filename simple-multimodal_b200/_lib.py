@@ -60,6 +60,8 @@ def lib() -> C.CDLL:
                 "(there is no fallback path)")
         _lib = C.CDLL(LIB_PATH)
         _lib.b200f_last_error.restype = C.c_char_p
+        _lib.b200f_launch_count.restype = C.c_ulonglong
+        _lib.b200f_infonce_workspace_bytes.restype = C.c_size_t
     return _lib
 
 
@@ -89,3 +91,7 @@ def require_cuda(*tensors) -> None:
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise B200FusionError("b200 fusion kernels need CUDA tensors (no CPU fallback exists)")
+
+
+def launch_count() -> int:
+    return int(lib().b200f_launch_count())

@@ -8,6 +8,7 @@
 namespace b200f {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 char* err_buf() { return g_err; }
 
 int fail(int code, const char* fmt, ...) {
@@ -40,6 +41,8 @@ extern uint32_t g_dbg_mn_lbo, g_dbg_mn_sbo, g_dbg_mn_kadv;
 extern "C" {
 
 int b200f_version(void) { return 100; }
+
+unsigned long long b200f_launch_count(void) { return b200f::g_launches; }
 
 const char* b200f_last_error(void) { return b200f::err_buf(); }
 

@@ -25,7 +25,11 @@ int fail(int code, const char* fmt, ...);
     if (!(cond)) return ::b200f::fail(code, __VA_ARGS__); \
   } while (0)
 
+// number of kernel launches issued by this library in this process (b200f_launch_count)
+extern unsigned long long g_launches;
+
 inline int check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(B200F_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
   return B200F_OK;

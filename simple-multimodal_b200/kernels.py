@@ -26,6 +26,10 @@ def _rows(x: Tensor):
     return x.numel() // k, k, k
 
 
+# Optional live profile of the dominant kernel (bench.py): CUDA-event pairs around every GEMM launch.
+GEMM_PROFILE = None          # None, or a list collecting (start_event, stop_event, flops, is_tensor_core)
+
+
 def gemm(a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_layout: int = 0, b_layout: int = 0,
          out: Optional[Tensor] = None, bias: Optional[Tensor] = None, residual: Optional[Tensor] = None,
          relu_mask: Optional[Tensor] = None, relu: bool = False, alpha: float = 1.0, accumulate: bool = False,
@@ -66,7 +70,15 @@ def gemm(a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_layout: int = 0, b_l
                       relu_mask=None if relu_mask is None else relu_mask.data_ptr(),
                       ldm=0 if relu_mask is None else relu_mask.stride(0),
                       alpha=alpha, flags=flags, dtype=dtype_code(dt), split_k=split_k)
+    if GEMM_PROFILE is None:
+        check(lib().b200f_gemm(C.byref(args), stream_ptr()), "b200f_gemm")
+        return out
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(lib().b200f_gemm(C.byref(args), stream_ptr()), "b200f_gemm")
+    e1.record()
+    tc = dt == torch.bfloat16 and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0 and N >= 8 and K >= 8
+    GEMM_PROFILE.append((e0, e1, 2.0 * M * N * K, tc))
     return out
 
 
@@ -245,7 +257,6 @@ def attn_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor
 
 def _infonce_ws(Bl: int, Bg: int, dt, for_grad: bool, device) -> Tensor:
     fn = lib().b200f_infonce_workspace_bytes
-    fn.restype = C.c_size_t
     n = fn(C.c_int64(Bl), C.c_int64(Bg), dtype_code(dt), C.c_int32(1 if for_grad else 0))
     return torch.empty(n, device=device, dtype=torch.uint8)
 

@@ -1,8 +1,627 @@
-// placeholder until the tcgen05 attention kernels land: bf16 attention runs on the CUDA-core kernels
+// Multi-head attention on the 5th-gen tensor cores (bf16, head_dim 64): flash-style, scores never leave the SM.
+//
+// Forward, one CTA per (128-query tile, head, batch), 6 warps:
+//   warp 0    TMA producer : Q tile once, then a 2-deep ring of {K,V} tiles (128 keys) straight out of the packed
+//                            projection output (4-D tensor map: d, head, token, batch; SWIZZLE_128B)
+//   warp 1    MMA issuer   : S = Q K^T  (tcgen05.mma 128x128x16, both operands K-major)   -> TMEM cols [0,128)
+//                            O += P V   (128x64x16, P K-major from smem, V MN-major)      -> TMEM cols [128,192)
+//   warps 2-5 softmax      : one thread per query row (= TMEM lane): tcgen05.ld the scores, online max / exp2 /
+//                            row-sum in fp32, P -> bf16 into the swizzled smem tile the PV MMA reads, rescale O in
+//                            TMEM when the running max moves, final O / l -> global (128 B per row), LSE saved.
+// 192 TMEM columns (256 allocated) and ~113 KB smem per CTA: two CTAs per SM overlap each other's softmax and MMA.
+//
+// Backward (two kernels, both recompute P from Q, K and the saved LSE; no atomics):
+//   dQ   : per 128-query tile, loop over key tiles:  S, dP = dO V^T, dS = P o (dP - delta), dQ += dS K
+//   dKdV : per 128-key tile, loop over query tiles, transposed so every thread-written operand is K-major:
+//          S^T = K Q^T, dP^T = V dO^T, dV += P^T dO, dK += dS^T Q
 #include "common.cuh"
+#include "ptx.cuh"
+
 namespace b200f {
-int attn_fwd_simt_dispatch(const b200f_attn_args& a, cudaStream_t st);
-int attn_bwd_simt_dispatch(const b200f_attn_args& a, cudaStream_t st);
-int attn_fwd_tc(const b200f_attn_args& a, cudaStream_t st) { return attn_fwd_simt_dispatch(a, st); }
-int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st) { return attn_bwd_simt_dispatch(a, st); }
+
+static constexpr int ATT_THREADS = 192;
+static constexpr int TQ = 128;   // query rows per CTA (UMMA M)
+static constexpr int TK = 128;   // keys per tile
+static constexpr int HD = 64;    // head dim
+static constexpr float LOG2E = 1.4426950408889634f;
+
+int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+
+struct AttnTcParams {
+  int B, H, Lq, Lk;
+  float scale;
+  bf16* O; long long ldo;
+  float* LSE;
+  // backward
+  const float* delta;
+  bf16* dQ; long long lddq;
+  bf16* dK; long long lddk;
+  bf16* dV; long long lddv;
+};
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+struct FwdSmem {
+  static constexpr int Q_OFF = 0;                       // [128 x 64] bf16, K-major SW128
+  static constexpr int K_OFF = Q_OFF + TQ * HD * 2;     // 2 stages x [128 x 64]
+  static constexpr int V_OFF = K_OFF + 2 * TK * HD * 2; // 2 stages x [128 keys x 64 d] (MN-major B operand)
+  static constexpr int P_OFF = V_OFF + 2 * TK * HD * 2; // [128 x 128] bf16 as two K-major SW128 halves of 64 keys
+  static constexpr int BAR_OFF = P_OFF + TQ * TK * 2;
+  static constexpr int TOTAL = BAR_OFF + 128;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::BAR_OFF);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;    // [2]
+  uint64_t* kv_empty = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_ready = bars + 6;
+  uint64_t* pv_done = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = (p.Lk + TK - 1) / TK;
+
+  if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023u) __trap();   // SWIZZLE_128B tiles need a 1024-byte aligned base
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 4);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_s = tmem_base, t_o = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, TQ * HD * 2);
+      tma_load_4d(smem + FwdSmem::Q_OFF, &tm_q, q_full, 0, h, q0, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * TK * HD * 2);
+        tma_load_4d(smem + FwdSmem::K_OFF + st * TK * HD * 2, &tm_k, &kv_full[st], 0, h, j * TK, b);
+        tma_load_4d(smem + FwdSmem::V_OFF + st * TK * HD * 2, &tm_v, &kv_full[st], 0, h, j * TK, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, TK, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(TQ, HD, 0, 1);
+      const uint32_t sq = smem_u32(smem + FwdSmem::Q_OFF), sp = smem_u32(smem + FwdSmem::P_OFF);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t sk = smem_u32(smem + FwdSmem::K_OFF + st * TK * HD * 2);
+        const uint32_t sv = smem_u32(smem + FwdSmem::V_OFF + st * TK * HD * 2);
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_ss(t_s, umma_desc(sq + k * 32, 16, 1024), umma_desc(sk + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(s_full);
+        mbar_wait(p_ready, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < TK / 16; ++k)
+          umma_ss(t_o, umma_desc(sp + (k >> 2) * (TQ * 128) + (k & 3) * 32, 16, 1024), umma_desc(sv + k * 2048, TK * 128, 1024), idesc_o,
+                  (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&kv_empty[st]);
+        umma_commit(pv_done);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int grp = warp & 3;
+    const int row = grp * 32 + lane;                 // row of the tile == TMEM lane
+    const uint32_t lane_addr = uint32_t(grp * 32) << 16;
+    const float c = p.scale * LOG2E;
+    float m = -INFINITY, l = 0.f;
+    uint8_t* prow = smem + FwdSmem::P_OFF;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int valid = min(TK, p.Lk - j * TK);      // keys beyond Lk were zero-filled by TMA: mask them
+      float tmax = -INFINITY;
+#pragma unroll 1
+      for (int cc = 0; cc < TK; cc += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_s + lane_addr + cc, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (cc + i < valid) tmax = fmaxf(tmax, __uint_as_float(r[i]));
+      }
+      const float m_new = fmaxf(m, tmax);
+      const float alpha = exp2f((m - m_new) * c);    // first tile: m = -inf -> 0
+      const float mc = m_new * c;
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < TK; cc += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_s + lane_addr + cc, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float e0 = (cc + i < valid) ? exp2f(__uint_as_float(r[i]) * c - mc) : 0.f;
+          const float e1 = (cc + i + 1 < valid) ? exp2f(__uint_as_float(r[i + 1]) * c - mc) : 0.f;
+          lsum += e0 + e1;
+          pk[i >> 1] = pack_bf16(e0, e1);
+        }
+        // 32 keys = four 16-byte chunks of this row inside the 64-key half (cc >> 6)
+        uint8_t* half = prow + (cc >> 6) * (TQ * 128);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint32_t chunk = ((cc & 63) >> 3) + q4;
+          *reinterpret_cast<uint4*>(half + sw128_offset(row, chunk)) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+        }
+      }
+      l = l * alpha + lsum;
+      m = m_new;
+      if (j > 0) {                                     // O was accumulated against the old max: rescale it in TMEM
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < HD; cc += 16) {
+          uint32_t r[16];
+          tmem_ld16(t_o + lane_addr + cc, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st16(t_o + lane_addr + cc, r);
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();                        // P (generic-proxy stores) -> visible to the UMMA (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+    }
+    mbar_wait(pv_done, (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const int qrow = q0 + row;
+    bf16* orow = p.O + ((long long)b * p.Lq + qrow) * p.ldo + h * HD;
+#pragma unroll
+    for (int cc = 0; cc < HD; cc += 16) {
+      uint32_t r[16];
+      tmem_ld16(t_o + lane_addr + cc, r);
+      tmem_ld_wait();
+      if (qrow < p.Lq) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) pk[i >> 1] = pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
+        *reinterpret_cast<uint4*>(orow + cc) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(orow + cc + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+    if (qrow < p.Lq) p.LSE[((long long)b * p.H + h) * p.Lq + qrow] = m * p.scale + logf(l);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
+// 4-D view (d, head, token, batch) of a token-major [B, L, ld] tensor slice; box = 64 x 1 x rows x 1
+static int make_head_tmap(CUtensorMap* m, const void* base, long long ld, int B, int H, int L, int rows) {
+  uint64_t dims[4] = {uint64_t(HD), uint64_t(H), uint64_t(L), uint64_t(B)};
+  uint64_t strides[3] = {uint64_t(HD) * 2, uint64_t(ld) * 2, uint64_t(L) * uint64_t(ld) * 2};
+  uint32_t box[4] = {uint32_t(HD), 1, uint32_t(rows), 1};
+  return make_tmap_bf16(m, base, 4, dims, strides, box);
+}
+
+static int attn_tc_check(const b200f_attn_args& a) {
+  B200F_REQUIRE(a.D == HD, B200F_ERR_UNSUPPORTED, "attention(tcgen05): head dim must be 64");
+  B200F_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, B200F_ERR_ALIGN, "attention(tcgen05): leading dims must be multiples of 8");
+  B200F_REQUIRE(aligned16(a.Q) && aligned16(a.K) && aligned16(a.V) && aligned16(a.O), B200F_ERR_ALIGN, "attention(tcgen05): 16-byte alignment");
+  B200F_REQUIRE(a.H <= 65535 && a.B <= 65535, B200F_ERR_SHAPE, "attention(tcgen05): grid limits");
+  return B200F_OK;
+}
+
+int attn_fwd_tc(const b200f_attn_args& a, cudaStream_t st) {
+  int rc = attn_tc_check(a);
+  if (rc) return rc;
+  CUtensorMap tq, tk, tv;
+  if ((rc = make_head_tmap(&tq, a.Q, a.ldq, a.B, a.H, a.Lq, TQ))) return rc;
+  if ((rc = make_head_tmap(&tk, a.K, a.ldk, a.B, a.H, a.Lk, TK))) return rc;
+  if ((rc = make_head_tmap(&tv, a.V, a.ldv, a.B, a.H, a.Lk, TK))) return rc;
+  AttnTcParams p = {};
+  p.B = a.B; p.H = a.H; p.Lq = a.Lq; p.Lk = a.Lk; p.scale = a.scale;
+  p.O = static_cast<bf16*>(a.O); p.ldo = a.ldo; p.LSE = a.LSE;
+  static bool configured = false;
+  if (!configured) {
+    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
+    configured = true;
+  }
+  dim3 grid((a.Lq + TQ - 1) / TQ, a.H, a.B);
+  attn_fwd_tc_kernel<<<grid, ATT_THREADS, FwdSmem::TOTAL, st>>>(tq, tk, tv, p);
+  return check_launch("attn_fwd_tc_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+static constexpr int BT = 64;    // inner tile (keys for the dQ kernel, queries for the dKdV kernel)
+
+// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]; one thread per (b,h,i) row of 64
+__global__ void attn_delta_kernel(const bf16* __restrict__ dO, long long lddo, const bf16* __restrict__ O, long long ldo, float* __restrict__ delta,
+                                  int B, int H, int Lq) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * H * Lq;
+  if (idx >= total) return;
+  const int h = int(idx % H);
+  const long long bl = idx / H;            // b*Lq + i
+  const bf16* g = dO + bl * lddo + h * HD;
+  const bf16* o = O + bl * ldo + h * HD;
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < HD; c += 8) {
+    Vec16<bf16> a, b2; a.load(g + c); b2.load(o + c);
+    float fa[8], fb[8]; a.unpack(fa); b2.unpack(fb);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc += fa[e] * fb[e];
+  }
+  const long long b = bl / Lq, i = bl % Lq;
+  delta[(b * H + h) * Lq + i] = acc;
+}
+
+struct DqSmem {
+  static constexpr int Q_OFF = 0;                          // [128 x 64]
+  static constexpr int DO_OFF = Q_OFF + TQ * HD * 2;       // [128 x 64]
+  static constexpr int K_OFF = DO_OFF + TQ * HD * 2;       // 2 x [64 keys x 64]
+  static constexpr int V_OFF = K_OFF + 2 * BT * HD * 2;    // 2 x [64 keys x 64]
+  static constexpr int DS_OFF = V_OFF + 2 * BT * HD * 2;   // [128 x 64 keys] bf16, K-major SW128
+  static constexpr int BAR_OFF = DS_OFF + TQ * BT * 2;
+  static constexpr int TOTAL = BAR_OFF + 128;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                      const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DqSmem::BAR_OFF);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;    // [2]
+  uint64_t* kv_empty = bars + 3;   // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* ds_ready = bars + 6;
+  uint64_t* dq_done = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = (p.Lk + BT - 1) / BT;
+
+  if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(ds_ready, 4);
+    mbar_init(dq_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_s = tmem_base, t_dp = tmem_base + 64, t_dq = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * TQ * HD * 2);
+      tma_load_4d(smem + DqSmem::Q_OFF, &tm_q, q_full, 0, h, q0, b);
+      tma_load_4d(smem + DqSmem::DO_OFF, &tm_do, q_full, 0, h, q0, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * BT * HD * 2);
+        tma_load_4d(smem + DqSmem::K_OFF + st * BT * HD * 2, &tm_k, &kv_full[st], 0, h, j * BT, b);
+        tma_load_4d(smem + DqSmem::V_OFF + st * BT * HD * 2, &tm_v, &kv_full[st], 0, h, j * BT, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, BT, 0, 0);     // S = Q K^T, dP = dO V^T   (N = 64 keys)
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(TQ, HD, 0, 1);    // dQ += dS K             (K MN-major, N = d)
+      const uint32_t sq = smem_u32(smem + DqSmem::Q_OFF), sdo = smem_u32(smem + DqSmem::DO_OFF), sds = smem_u32(smem + DqSmem::DS_OFF);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t sk = smem_u32(smem + DqSmem::K_OFF + st * BT * HD * 2);
+        const uint32_t sv = smem_u32(smem + DqSmem::V_OFF + st * BT * HD * 2);
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_ss(t_s, umma_desc(sq + k * 32, 16, 1024), umma_desc(sk + k * 32, 16, 1024), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_ss(t_dp, umma_desc(sdo + k * 32, 16, 1024), umma_desc(sv + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(sdp_full);
+        mbar_wait(ds_ready, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < BT / 16; ++k)
+          umma_ss(t_dq, umma_desc(sds + k * 32, 16, 1024), umma_desc(sk + k * 2048, BT * 128, 1024), idesc_dq, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&kv_empty[st]);
+        umma_commit(dq_done);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int grp = warp & 3;
+    const int row = grp * 32 + lane;
+    const uint32_t lane_addr = uint32_t(grp * 32) << 16;
+    const int qrow = q0 + row;
+    const long long ri = ((long long)b * p.H + h) * p.Lq + qrow;
+    const float c = p.scale * LOG2E;
+    const float lse2 = (qrow < p.Lq ? p.LSE[ri] : 0.f) * LOG2E;
+    const float dl = qrow < p.Lq ? p.delta[ri] : 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(sdp_full, j & 1);      // also implies the previous tile's dQ MMAs (which read the dS tile) retired
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < BT; cc += 32) {
+        uint32_t rs[32], rp[32];
+        tmem_ld32(t_s + lane_addr + cc, rs);
+        tmem_ld32(t_dp + lane_addr + cc, rp);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = exp2f(__uint_as_float(rs[i]) * c - lse2), p1 = exp2f(__uint_as_float(rs[i + 1]) * c - lse2);
+          pk[i >> 1] = pack_bf16(p0 * (__uint_as_float(rp[i]) - dl) * p.scale, p1 * (__uint_as_float(rp[i + 1]) - dl) * p.scale);
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          *reinterpret_cast<uint4*>(smem + DqSmem::DS_OFF + sw128_offset(row, (cc >> 3) + q4)) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_ready);
+    }
+    mbar_wait(dq_done, (n_tiles - 1) & 1);
+    tc_fence_after();
+    bf16* dq = p.dQ + ((long long)b * p.Lq + qrow) * p.lddq + h * HD;
+#pragma unroll
+    for (int cc = 0; cc < HD; cc += 16) {
+      uint32_t r[16];
+      tmem_ld16(t_dq + lane_addr + cc, r);
+      tmem_ld_wait();
+      if (qrow < p.Lq) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) pk[i >> 1] = pack_bf16(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        *reinterpret_cast<uint4*>(dq + cc) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(dq + cc + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
+struct DkvSmem {
+  static constexpr int K_OFF = 0;                          // [128 keys x 64]
+  static constexpr int V_OFF = K_OFF + TK * HD * 2;        // [128 keys x 64]
+  static constexpr int Q_OFF = V_OFF + TK * HD * 2;        // 2 x [64 queries x 64]
+  static constexpr int DO_OFF = Q_OFF + 2 * BT * HD * 2;   // 2 x [64 queries x 64]
+  static constexpr int P_OFF = DO_OFF + 2 * BT * HD * 2;   // P^T  [128 keys x 64 queries] bf16
+  static constexpr int DS_OFF = P_OFF + TK * BT * 2;       // dS^T [128 keys x 64 queries] bf16
+  static constexpr int STAT_OFF = DS_OFF + TK * BT * 2;    // 2 x {lse2[64], delta[64]} fp32
+  static constexpr int BAR_OFF = STAT_OFF + 2 * 2 * BT * 4;
+  static constexpr int TOTAL = BAR_OFF + 128;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                       const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DkvSmem::BAR_OFF);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* q_full = bars + 1;     // [2]
+  uint64_t* q_empty = bars + 3;    // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* ds_ready = bars + 6;
+  uint64_t* acc_done = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* stats = reinterpret_cast<float*>(smem + DkvSmem::STAT_OFF);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * TK, h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = (p.Lq + BT - 1) / BT;
+
+  if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(ds_ready, 4);
+    mbar_init(acc_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_s = tmem_base, t_dp = tmem_base + 64, t_dv = tmem_base + 128, t_dk = tmem_base + 192;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * TK * HD * 2);
+      tma_load_4d(smem + DkvSmem::K_OFF, &tm_k, kv_full, 0, h, k0, b);
+      tma_load_4d(smem + DkvSmem::V_OFF, &tm_v, kv_full, 0, h, k0, b);
+      for (int i = 0; i < n_tiles; ++i) {
+        const int st = i & 1;
+        mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[st], 2 * BT * HD * 2);
+        tma_load_4d(smem + DkvSmem::Q_OFF + st * BT * HD * 2, &tm_q, &q_full[st], 0, h, i * BT, b);
+        tma_load_4d(smem + DkvSmem::DO_OFF + st * BT * HD * 2, &tm_do, &q_full[st], 0, h, i * BT, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(TK, BT, 0, 0);     // S^T = K Q^T, dP^T = V dO^T   (N = 64 queries)
+      constexpr uint32_t idesc_acc = umma_idesc_bf16(TK, HD, 0, 1);   // dV += P^T dO, dK += dS^T Q   (B MN-major, N = d)
+      const uint32_t sk = smem_u32(smem + DkvSmem::K_OFF), sv = smem_u32(smem + DkvSmem::V_OFF);
+      const uint32_t sp = smem_u32(smem + DkvSmem::P_OFF), sds = smem_u32(smem + DkvSmem::DS_OFF);
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < n_tiles; ++i) {
+        const int st = i & 1;
+        const uint32_t sq = smem_u32(smem + DkvSmem::Q_OFF + st * BT * HD * 2);
+        const uint32_t sdo = smem_u32(smem + DkvSmem::DO_OFF + st * BT * HD * 2);
+        mbar_wait(&q_full[st], (i >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_ss(t_s, umma_desc(sk + k * 32, 16, 1024), umma_desc(sq + k * 32, 16, 1024), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_ss(t_dp, umma_desc(sv + k * 32, 16, 1024), umma_desc(sdo + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(sdp_full);
+        mbar_wait(ds_ready, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < BT / 16; ++k)
+          umma_ss(t_dv, umma_desc(sp + k * 32, 16, 1024), umma_desc(sdo + k * 2048, BT * 128, 1024), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < BT / 16; ++k)
+          umma_ss(t_dk, umma_desc(sds + k * 32, 16, 1024), umma_desc(sq + k * 2048, BT * 128, 1024), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&q_empty[st]);
+        umma_commit(acc_done);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int grp = warp & 3;
+    const int row = grp * 32 + lane;                 // key row of the tile == TMEM lane
+    const int t128 = threadIdx.x - 64;               // 0..127 among the softmax threads
+    const uint32_t lane_addr = uint32_t(grp * 32) << 16;
+    const float c = p.scale * LOG2E;
+    const long long stat_base = ((long long)b * p.H + h) * p.Lq;
+    for (int i = 0; i < n_tiles; ++i) {
+      float* sl = stats + (i & 1) * 2 * BT;          // [lse2[64] | delta[64]] for this tile's queries
+      {
+        const int qi = i * BT + (t128 & 63);
+        float v = 0.f;
+        if (qi < p.Lq) v = t128 < 64 ? p.LSE[stat_base + qi] * LOG2E : p.delta[stat_base + qi];
+        sl[t128] = v;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(sdp_full, i & 1);                    // implies the previous tile's dV/dK MMAs (reading P^T/dS^T) retired
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < BT; cc += 32) {
+        uint32_t rs[32], rp[32];
+        tmem_ld32(t_s + lane_addr + cc, rs);
+        tmem_ld32(t_dp + lane_addr + cc, rp);
+        tmem_ld_wait();
+        uint32_t pp[16], pd[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = exp2f(__uint_as_float(rs[e]) * c - sl[cc + e]), p1 = exp2f(__uint_as_float(rs[e + 1]) * c - sl[cc + e + 1]);
+          pp[e >> 1] = pack_bf16(p0, p1);
+          pd[e >> 1] = pack_bf16(p0 * (__uint_as_float(rp[e]) - sl[BT + cc + e]) * p.scale, p1 * (__uint_as_float(rp[e + 1]) - sl[BT + cc + e + 1]) * p.scale);
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint32_t off = sw128_offset(row, (cc >> 3) + q4);
+          *reinterpret_cast<uint4*>(smem + DkvSmem::P_OFF + off) = make_uint4(pp[q4 * 4], pp[q4 * 4 + 1], pp[q4 * 4 + 2], pp[q4 * 4 + 3]);
+          *reinterpret_cast<uint4*>(smem + DkvSmem::DS_OFF + off) = make_uint4(pd[q4 * 4], pd[q4 * 4 + 1], pd[q4 * 4 + 2], pd[q4 * 4 + 3]);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_ready);
+    }
+    mbar_wait(acc_done, (n_tiles - 1) & 1);
+    tc_fence_after();
+    const int krow = k0 + row;
+    bf16* dk = p.dK + ((long long)b * p.Lk + krow) * p.lddk + h * HD;
+    bf16* dv = p.dV + ((long long)b * p.Lk + krow) * p.lddv + h * HD;
+#pragma unroll
+    for (int cc = 0; cc < HD; cc += 16) {
+      uint32_t r1[16], r2[16];
+      tmem_ld16(t_dv + lane_addr + cc, r1);
+      tmem_ld16(t_dk + lane_addr + cc, r2);
+      tmem_ld_wait();
+      if (krow < p.Lk) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) pk[e >> 1] = pack_bf16(__uint_as_float(r1[e]), __uint_as_float(r1[e + 1]));
+        *reinterpret_cast<uint4*>(dv + cc) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(dv + cc + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) pk[e >> 1] = pack_bf16(__uint_as_float(r2[e]), __uint_as_float(r2[e + 1]));
+        *reinterpret_cast<uint4*>(dk + cc) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(dk + cc + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
+int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st) {
+  int rc = attn_tc_check(a);
+  if (rc) return rc;
+  B200F_REQUIRE(a.lddo % 8 == 0 && a.lddq % 8 == 0 && a.lddk % 8 == 0 && a.lddv % 8 == 0, B200F_ERR_ALIGN, "attention(tcgen05): gradient leading dims must be multiples of 8");
+  B200F_REQUIRE(aligned16(a.dO) && aligned16(a.dQ) && aligned16(a.dK) && aligned16(a.dV) && a.delta, B200F_ERR_ALIGN, "attention(tcgen05): gradient alignment");
+  AttnTcParams p = {};
+  p.B = a.B; p.H = a.H; p.Lq = a.Lq; p.Lk = a.Lk; p.scale = a.scale;
+  p.LSE = a.LSE; p.delta = a.delta;
+  p.dQ = static_cast<bf16*>(a.dQ); p.lddq = a.lddq;
+  p.dK = static_cast<bf16*>(a.dK); p.lddk = a.lddk;
+  p.dV = static_cast<bf16*>(a.dV); p.lddv = a.lddv;
+  const long long rows = (long long)a.B * a.H * a.Lq;
+  attn_delta_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(static_cast<const bf16*>(a.dO), a.lddo, static_cast<const bf16*>(a.O), a.ldo, a.delta, a.B, a.H, a.Lq);
+  if ((rc = check_launch("attn_delta_kernel"))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::TOTAL));
+    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem::TOTAL));
+    configured = true;
+  }
+  CUtensorMap tq, tdo, tk, tv;
+  {  // dQ kernel: 128-row Q/dO boxes, 64-row K/V boxes
+    if ((rc = make_head_tmap(&tq, a.Q, a.ldq, a.B, a.H, a.Lq, TQ))) return rc;
+    if ((rc = make_head_tmap(&tdo, a.dO, a.lddo, a.B, a.H, a.Lq, TQ))) return rc;
+    if ((rc = make_head_tmap(&tk, a.K, a.ldk, a.B, a.H, a.Lk, BT))) return rc;
+    if ((rc = make_head_tmap(&tv, a.V, a.ldv, a.B, a.H, a.Lk, BT))) return rc;
+    dim3 grid((a.Lq + TQ - 1) / TQ, a.H, a.B);
+    attn_bwd_dq_tc_kernel<<<grid, ATT_THREADS, DqSmem::TOTAL, st>>>(tq, tdo, tk, tv, p);
+    if ((rc = check_launch("attn_bwd_dq_tc_kernel"))) return rc;
+  }
+  {  // dKdV kernel: 128-row K/V boxes, 64-row Q/dO boxes
+    if ((rc = make_head_tmap(&tq, a.Q, a.ldq, a.B, a.H, a.Lq, BT))) return rc;
+    if ((rc = make_head_tmap(&tdo, a.dO, a.lddo, a.B, a.H, a.Lq, BT))) return rc;
+    if ((rc = make_head_tmap(&tk, a.K, a.ldk, a.B, a.H, a.Lk, TK))) return rc;
+    if ((rc = make_head_tmap(&tv, a.V, a.ldv, a.B, a.H, a.Lk, TK))) return rc;
+    dim3 grid((a.Lk + TK - 1) / TK, a.H, a.B);
+    attn_bwd_dkv_tc_kernel<<<grid, ATT_THREADS, DkvSmem::TOTAL, st>>>(tq, tdo, tk, tv, p);
+    if ((rc = check_launch("attn_bwd_dkv_tc_kernel"))) return rc;
+  }
+  return B200F_OK;
+}
+
 }  // namespace b200f

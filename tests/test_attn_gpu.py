@@ -1,0 +1,80 @@
+"""Attention kernels (tcgen05 bf16, CUDA-core fp32) against explicit torch math on the same packed, strided
+projection tensors: forward output + LSE, backward dQ/dK/dV."""
+import importlib
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+pkg = importlib.import_module("simple-multimodal_b200")
+K = pkg.kernels
+
+SHAPES = [(2, 8, 512, 512), (3, 8, 512, 30), (3, 8, 30, 512), (2, 8, 100, 200), (1, 8, 128, 128), (2, 8, 1, 1), (1, 8, 257, 129)]
+
+
+def reference(q, k, v, heads, scale):
+    B, Lq, W = q.shape
+    Lk, D = k.size(1), W // heads
+    qh = q.double().view(B, Lq, heads, D).transpose(1, 2)
+    kh = k.double().view(B, Lk, heads, D).transpose(1, 2)
+    vh = v.double().view(B, Lk, heads, D).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) * scale
+    lse = torch.logsumexp(s, dim=-1)
+    o = torch.softmax(s, dim=-1) @ vh
+    return o.transpose(1, 2).reshape(B, Lq, W), lse
+
+
+def rel(x, r):
+    """norm-wise relative error; an exactly-zero reference (softmax over a single key has no dQ/dK) is compared absolutely."""
+    x, r = x.detach().double(), r.detach().double()
+    if float(r.norm()) == 0.0:
+        return float(x.abs().max())
+    return float((x - r).norm() / r.norm())
+
+
+def packed(B, L, width, dtype, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(B, L, width, device="cuda", generator=g).to(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_attention_forward_backward(shape, dtype):
+    B, heads, Lq, Lk = shape
+    W = heads * 64
+    scale = 1 / math.sqrt(64)
+    pq = packed(B, Lq, 2 * W, dtype, 1)                     # Q lives in columns [W, 2W) of a wider projection
+    pkv = packed(B, Lk, 3 * W, dtype, 2)                    # K in [0,W), V in [2W,3W)
+    q, k, v = pq[:, :, W:], pkv[:, :, :W], pkv[:, :, 2 * W:]
+    o, lse = K.attn_fwd(q, k, v, heads, scale)
+    torch.cuda.synchronize()
+    qd, kd, vd = (t.detach().double().requires_grad_(True) for t in (q, k, v))
+    o_ref, lse_ref = reference(qd, kd, vd, heads, scale)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel(o, o_ref) < tol, f"O rel err {rel(o, o_ref)}"
+    assert float((lse.double() - lse_ref).abs().max()) < (1e-4 if dtype == torch.float32 else 2e-2)
+    do = packed(B, Lq, W, dtype, 3)
+    (o_ref * do.double()).sum().backward()
+    dpq, dpkv = torch.zeros_like(pq), torch.zeros_like(pkv)
+    K.attn_bwd(do, q, k, v, o, lse, heads, scale, dpq[:, :, W:], dpkv[:, :, :W], dpkv[:, :, 2 * W:])
+    torch.cuda.synchronize()
+    gt = 1e-5 if dtype == torch.float32 else 2e-2
+    assert rel(dpq[:, :, W:], qd.grad) < gt, f"dQ {rel(dpq[:, :, W:], qd.grad)}"
+    assert rel(dpkv[:, :, :W], kd.grad) < gt, f"dK {rel(dpkv[:, :, :W], kd.grad)}"
+    assert rel(dpkv[:, :, 2 * W:], vd.grad) < gt, f"dV {rel(dpkv[:, :, 2 * W:], vd.grad)}"
+    assert float(dpq[:, :, :W].abs().max()) == 0 and float(dpkv[:, :, W:2 * W].abs().max()) == 0     # untouched slices
+
+
+def test_attention_tc_matches_cuda_core_path():
+    B, heads, Lq, Lk = 2, 8, 300, 77
+    W = heads * 64
+    q, k, v = (packed(B, L, W, torch.bfloat16, s) for L, s in ((Lq, 5), (Lk, 6), (Lk, 7)))
+    o_tc, lse_tc = K.attn_fwd(q, k, v, heads, 0.125)
+    pkg._lib.lib().b200f_debug_force_simt_attention(1)
+    try:
+        o_cc, lse_cc = K.attn_fwd(q, k, v, heads, 0.125)
+    finally:
+        pkg._lib.lib().b200f_debug_force_simt_attention(0)
+    torch.cuda.synchronize()
+    assert rel(o_tc, o_cc) < 1e-2 and float((lse_tc - lse_cc).abs().max()) < 1e-2

@@ -114,10 +114,11 @@ int b200f_attn_bwd(const b200f_attn_args* args, void* stream);
 int b200f_layernorm_fwd(const void* x, const float* gamma, const float* beta, const void* post1,
                         const void* post2, void* y, float* mean, float* rstd, int64_t rows, int32_t H,
                         float eps, int32_t dtype, void* stream);
-/* dx = LN'(dy) (+ dres);  dgamma += sum dy*xhat;  dbeta += sum dy   (fp32 atomics). */
+/* dx = LN'(dy) (+ dres);  dgamma += sum dy*xhat;  dbeta += sum dy;  optional dxsum[H] += column sum of dx
+ * (the bias gradient of the Linear whose output fed this LayerNorm, fused here)   (fp32 atomics). */
 int b200f_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                         const float* gamma, const void* dres, void* dx, float* dgamma, float* dbeta,
-                        int64_t rows, int32_t H, int32_t dtype, void* stream);
+                        float* dxsum, int64_t rows, int32_t H, int32_t dtype, void* stream);
 /* out[n] += sum_m x[m,n]   (bias gradients). */
 int b200f_colsum_accum(const void* x, int64_t ldx, float* out, int64_t M, int64_t N, int32_t dtype, void* stream);
 /* y = a + b (+ c), elementwise over n elements (c may be NULL). */

@@ -2,11 +2,12 @@
 //
 //   C[m,n] = epi( alpha * sum_k A(m,k) * B(n,k) ),  fp32 accumulation
 //
-// One persistent CTA per SM, 6 warps, warp-specialised:
+// One persistent CTA per SM, 10 warps, warp-specialised:
 //   warp 0    TMA producer   : cp.async.bulk.tensor -> STAGES-deep ring of {A,B} smem tiles (SWIZZLE_128B)
 //   warp 1    MMA issuer     : one lane issues tcgen05.mma (128 x BN x 16) into one of two TMEM accumulators
-//   warps 2-5 epilogue       : tcgen05.ld -> bias / residual / ReLU / mask -> global, while the MMA warp
-//                              already fills the other accumulator (mainloop/epilogue overlap)
+//   warps 2-9 epilogue       : tcgen05.ld -> bias / residual / ReLU / mask -> global, while the MMA warp
+//                              already fills the other accumulator (mainloop/epilogue overlap); each TMEM lane
+//                              group is served by two warps that split the tile's columns
 // Both operands may be K-major (reduction dim contiguous) or MN-major, so forward (X W^T), input-gradient
 // (dY W) and weight-gradient (dY^T X, fp32 atomics with split-K over tokens) all run without a transpose.
 #include "common.cuh"
@@ -16,7 +17,8 @@ namespace b200f {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int GEMM_THREADS = 192;
+static constexpr int EPI_STAGE_BYTES = 32 * 128;   // smem staging tile per epilogue warp
+static constexpr int GEMM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane group)
 
 struct GemmTcParams {
   int M, N, K;
@@ -41,8 +43,168 @@ struct GemmSmem {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // +1024 alignment slack
+  static constexpr int EPI_OFFSET = BAR_OFFSET + 256;                          // 8 x 4 KB epilogue staging tiles
+  static constexpr int TOTAL = EPI_OFFSET + 8 * EPI_STAGE_BYTES + 1024;          // +1024 alignment slack
 };
+
+// Drain columns [c_begin, c_end) of one accumulator row (this thread's TMEM lane) through the fused epilogue.
+__device__ __forceinline__ void epilogue_columns(const GemmTcParams& p, uint32_t t_row, long long row, bool row_ok, int n_base, int c_begin,
+                                                 int c_end, bool out_f32, bool accum, bool relu) {
+#pragma unroll 1
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(t_row + c0, r);
+    tmem_ld_wait();
+    const int col0 = n_base + c0;
+    if (row_ok && col0 < p.N) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col = col0 + g * 8;
+        if (col >= p.N) break;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * p.alpha;
+        const bool full8 = (col + 8 <= p.N) && p.vec_ok;
+        if (p.bias) {
+          if (full8) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (col + j < p.N) v[j] += __ldg(p.bias + col + j);
+          }
+        }
+        if (p.residual) {
+          const bf16* rp = p.residual + row * p.ldr + col;
+          if (full8) {
+            Vec16<bf16> rv; rv.load(rp);
+            float f[8]; rv.unpack(f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += f[j];
+          } else {
+            for (int j = 0; j < 8 && col + j < p.N; ++j) v[j] += to_f32(rp[j]);
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.mask) {
+          const bf16* mp = p.mask + row * p.ldm + col;
+          if (full8) {
+            Vec16<bf16> mv; mv.load(mp);
+            float f[8]; mv.unpack(f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = f[j] > 0.f ? v[j] : 0.f;
+          } else {
+            for (int j = 0; j < 8 && col + j < p.N; ++j) v[j] = to_f32(mp[j]) > 0.f ? v[j] : 0.f;
+          }
+        }
+        if (out_f32) {
+          float* cp = reinterpret_cast<float*>(p.C) + row * p.ldc + col;
+          if (accum) {
+            for (int j = 0; j < 8 && col + j < p.N; ++j) atomicAdd(cp + j, v[j]);
+          } else if (full8) {
+            *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(cp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+            for (int j = 0; j < 8 && col + j < p.N; ++j) cp[j] = v[j];
+          }
+        } else {
+          bf16* cp = reinterpret_cast<bf16*>(p.C) + row * p.ldc + col;
+          if (full8) {
+            Vec16<bf16> ov; ov.pack(v); ov.store(cp);
+          } else {
+            for (int j = 0; j < 8 && col + j < p.N; ++j) cp[j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// bf16 epilogue with coalesced global traffic.  A thread owns one accumulator ROW (its TMEM lane), so direct 16-byte
+// accesses from a warp touch 32 different 128-byte lines per instruction.  Instead each warp moves 64-column blocks
+// through a private 4 KB shared-memory tile [32 rows x 128 B] (16-byte chunks XOR-swizzled by row, conflict-free in
+// both directions): residual / mask rows are loaded 4 full lines per instruction, consumed row-wise, the packed bf16
+// results are written row-wise and leave as 4 full 128-byte lines per instruction.
+
+__device__ __forceinline__ void epilogue_columns_staged(const GemmTcParams& p, uint8_t* stage, uint32_t t_row, long long row0, int lane,
+                                                        int n_base, int c_begin, int c_end, bool relu) {
+  const long long row = row0 + lane;
+  const int crow = lane >> 3, cchunk = lane & 7;             // coalesced phase: 4 rows x 8 chunks per instruction
+#pragma unroll 1
+  for (int c0 = c_begin; c0 < c_end; c0 += 64) {
+    const int col0 = n_base + c0;
+    if (col0 >= p.N) break;                                  // warp-uniform
+    if (col0 + 64 > p.N) {                                   // ragged right edge: direct path
+      epilogue_columns(p, t_row, row, row < p.M, n_base, c0, c0 + 64, false, false, relu);
+      continue;
+    }
+    const bf16* aux = p.residual ? p.residual : p.mask;      // tile staged through smem (the other one, if any, is read directly)
+    const long long ldaux = p.residual ? p.ldr : p.ldm;
+    if (aux) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + crow;
+        if (row0 + r < p.M)
+          *reinterpret_cast<uint4*>(stage + sw128_offset(r, cchunk)) = *reinterpret_cast<const uint4*>(aux + (row0 + r) * ldaux + col0 + cchunk * 8);
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t r[32];
+      tmem_ld32(t_row + c0 + h * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col = col0 + h * 32 + g * 8;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * p.alpha;
+        if (p.bias) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        uint8_t* cell = stage + sw128_offset(lane, h * 4 + g);
+        float f[8];
+        if (aux) { Vec16<bf16> av; av.raw = *reinterpret_cast<const uint4*>(cell); av.unpack(f); }
+        if (p.residual) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += f[j];
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.mask) {
+          if (p.residual) {                                  // both present: the mask comes straight from global
+            if (row < p.M) { Vec16<bf16> mv; mv.load(p.mask + row * p.ldm + col); mv.unpack(f); }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = f[j] > 0.f ? v[j] : 0.f;
+        }
+        Vec16<bf16> ov; ov.pack(v);
+        *reinterpret_cast<uint4*>(cell) = ov.raw;            // same cell this lane just consumed
+      }
+    }
+    __syncwarp();
+    bf16* cbase = reinterpret_cast<bf16*>(p.C);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + crow;
+      if (row0 + r < p.M)
+        *reinterpret_cast<uint4*>(cbase + (row0 + r) * p.ldc + col0 + cchunk * 8) = *reinterpret_cast<const uint4*>(stage + sw128_offset(r, cchunk));
+    }
+    __syncwarp();
+  }
+}
 
 template <int BN, int STAGES, int A_MN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -69,7 +231,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 8);
     }
     fence_mbar_init();
   }
@@ -148,6 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     __syncwarp();
   } else {
     const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are the ones this warp may touch
+    const int col_half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
     const bool out_f32 = (p.flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) != 0;
     const bool accum = (p.flags & B200F_EPI_ACCUM) != 0;
     const bool relu = (p.flags & B200F_EPI_RELU) != 0;
@@ -162,73 +325,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const long long row = (long long)m_blk * BM + lane_grp * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + (uint32_t(lane_grp * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_row + c0, r);
-        tmem_ld_wait();
-        const int col0 = n_blk * BN + c0;
-        if (row_ok && col0 < p.N) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col >= p.N) break;
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * p.alpha;
-            const bool full8 = (col + 8 <= p.N) && p.vec_ok;
-            if (p.bias) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (col + j < p.N) v[j] += __ldg(p.bias + col + j);
-            }
-            if (p.residual) {
-              const bf16* rp = p.residual + row * p.ldr + col;
-              if (full8) {
-                Vec16<bf16> rv; rv.load(rp);
-                float f[8]; rv.unpack(f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += f[j];
-              } else {
-                for (int j = 0; j < 8 && col + j < p.N; ++j) v[j] += to_f32(rp[j]);
-              }
-            }
-            if (relu) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            if (p.mask) {
-              const bf16* mp = p.mask + row * p.ldm + col;
-              if (full8) {
-                Vec16<bf16> mv; mv.load(mp);
-                float f[8]; mv.unpack(f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = f[j] > 0.f ? v[j] : 0.f;
-              } else {
-                for (int j = 0; j < 8 && col + j < p.N; ++j) v[j] = to_f32(mp[j]) > 0.f ? v[j] : 0.f;
-              }
-            }
-            if (out_f32) {
-              float* cp = reinterpret_cast<float*>(p.C) + row * p.ldc + col;
-              if (accum) {
-                for (int j = 0; j < 8 && col + j < p.N; ++j) atomicAdd(cp + j, v[j]);
-              } else if (full8) {
-                *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(cp + 4) = make_float4(v[4], v[5], v[6], v[7]);
-              } else {
-                for (int j = 0; j < 8 && col + j < p.N; ++j) cp[j] = v[j];
-              }
-            } else {
-              bf16* cp = reinterpret_cast<bf16*>(p.C) + row * p.ldc + col;
-              if (full8) {
-                Vec16<bf16> ov; ov.pack(v); ov.store(cp);
-              } else {
-                for (int j = 0; j < 8 && col + j < p.N; ++j) cp[j] = __float2bfloat16_rn(v[j]);
-              }
-            }
-          }
-        }
-      }
+      if (!out_f32 && p.vec_ok)
+        epilogue_columns_staged(p, smem + S::EPI_OFFSET + (warp - 2) * EPI_STAGE_BYTES, t_row, row - lane, lane, n_blk * BN,
+                                col_half * (BN / 2), (col_half + 1) * (BN / 2), relu);
+      else
+        epilogue_columns(p, t_row, row, row_ok, n_blk * BN, col_half * (BN / 2), (col_half + 1) * (BN / 2), out_f32, accum, relu);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -238,6 +339,169 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster (= two SMs of a TPC) own one 256 x BN tile.  Each CTA
+// stages its own 128 rows of A and HALF of the B tile, the leader issues 256 x BN x 16 MMAs that read both CTAs'
+// shared memory and write 128 accumulator rows into each CTA's TMEM.  Per FLOP this moves 2/3 of the L2->SM bytes
+// of the single-CTA kernel, which is what bounds the K=512 GEMMs of the path (L2, not HBM or the tensor pipe).
+// Barrier ownership: smem-full and tmem-empty live in the LEADER (TMA of both CTAs completes on the leader's full
+// barrier; epilogue warps of both CTAs arrive on the leader's tmem-empty); smem-empty and tmem-full are local to each
+// CTA and signalled by multicast tcgen05.commit.
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct PairSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int EPI_OFFSET = BAR_OFFSET + 256;
+  static constexpr int TOTAL = EPI_OFFSET + 8 * EPI_STAGE_BYTES + 1024;
+};
+
+template <int BN, int STAGES, int A_MN, int B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmTcParams p) {
+  using S = PairSmem<BN, STAGES>;
+  constexpr int TMEM_COLS = 2 * BN;
+  constexpr int HALF_N = BN / 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);      // leader: armed with the bytes of both CTAs
+      mbar_init(&empty_bar[i], 1);     // local: multicast commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);     // local: multicast commit
+      mbar_init(&tmem_empty[i], 16);   // leader: 8 epilogue warps x 2 CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                  // peer barriers initialised before any remote arrive / TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int units = p.num_m * p.num_n * p.split_k;   // num_m counts 256-row pair tiles here
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = cluster_id; u < units; u += num_clusters) {
+        const int n_blk = u % p.num_n;
+        const int m_blk = (u / p.num_n) % p.num_m;
+        const int ks = u / (p.num_n * p.num_m);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int m0 = m_blk * 2 * BM + int(rank) * BM;
+        const int n0 = n_blk * BN + int(rank) * HALF_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          uint8_t* sb = sa + S::A_BYTES;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d_pair(sa + c * (BK * 128), &tma_a, &full_bar[stage], m0 + c * 64, kb * BK);
+          } else {
+            tma_load_2d_pair(sa, &tma_a, &full_bar[stage], kb * BK, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < HALF_N / 64; ++c) tma_load_2d_pair(sb + c * (BK * 128), &tma_b, &full_bar[stage], n0 + c * 64, kb * BK);
+          } else {
+            tma_load_2d_pair(sb, &tma_b, &full_bar[stage], kb * BK, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int u = cluster_id; u < units; u += num_clusters, ++it) {
+        const int ks = u / (p.num_n * p.num_m);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = umma_desc(sa + k * p.a_kadv, p.a_lbo, p.a_sbo);
+            const uint64_t db = umma_desc(sb + k * p.b_kadv, p.b_lbo, p.b_sbo);
+            umma_ss_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tmem_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int lane_grp = warp & 3;
+    const int col_half = (warp - 2) >> 2;
+    const bool out_f32 = (p.flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) != 0;
+    const bool accum = (p.flags & B200F_EPI_ACCUM) != 0;
+    const bool relu = (p.flags & B200F_EPI_RELU) != 0;
+    int it = 0;
+    for (int u = cluster_id; u < units; u += num_clusters, ++it) {
+      const int n_blk = u % p.num_n;
+      const int m_blk = (u / p.num_n) % p.num_m;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const long long row = (long long)m_blk * 2 * BM + (long long)rank * BM + lane_grp * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + (uint32_t(lane_grp * 32) << 16) + acc * BN;
+      if (!out_f32 && p.vec_ok)
+        epilogue_columns_staged(p, smem + S::EPI_OFFSET + (warp - 2) * EPI_STAGE_BYTES, t_row, row - lane, lane, n_blk * BN,
+                                col_half * (BN / 2), (col_half + 1) * (BN / 2), relu);
+      else
+        epilogue_columns(p, t_row, row, row_ok, n_blk * BN, col_half * (BN / 2), (col_half + 1) * (BN / 2), out_f32, accum, relu);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                  // the peer may still read this CTA's smem / signal its barriers
+  if (warp == 1) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -277,6 +541,21 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
 // debug overrides for the MN-major descriptor geometry (b200f_debug_set); 0 = use the default
 uint32_t g_dbg_mn_lbo = 0, g_dbg_mn_sbo = 0, g_dbg_mn_kadv = 0;
 
+bool g_dbg_disable_pair = false;     // b200f_debug_set(3, 1): force the single-CTA kernel (A/B testing)
+
+template <int BN, int STAGES, int A_MN, int B_MN>
+static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcParams& p, int grid, cudaStream_t st) {
+  using S = PairSmem<BN, STAGES>;
+  auto kern = gemm_tc_pair_kernel<BN, STAGES, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    B200F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, p);
+  return check_launch("gemm_tc_pair_kernel");
+}
+
 template <int BN, int STAGES, int A_MN, int B_MN>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcParams& p, int grid, cudaStream_t st) {
   using S = GemmSmem<BN, STAGES>;
@@ -300,11 +579,13 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
   B200F_REQUIRE(gemm_tc_eligible(a), B200F_ERR_ALIGN, "gemm(bf16/tcgen05): lda/ldb must be multiples of 8 elements and A/B 16-byte aligned");
   const bool out_f32 = (a.flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) != 0;
   const bool vec_ok = aligned16(a.C) && a.ldc % (out_f32 ? 4 : 8) == 0 && (!a.residual || (a.ldr % 8 == 0 && aligned16(a.residual))) &&
-                      (!a.relu_mask || (a.ldm % 8 == 0 && aligned16(a.relu_mask)));
+                      (!a.relu_mask || (a.ldm % 8 == 0 && aligned16(a.relu_mask))) && (!a.bias || aligned16(a.bias));
   const int split = a.split_k > 1 ? a.split_k : 1;
   B200F_REQUIRE(split == 1 || (a.flags & B200F_EPI_ACCUM), B200F_ERR_UNSUPPORTED, "gemm: split_k needs B200F_EPI_ACCUM");
 
   const int BN = (a.N > 128) ? 256 : 128;
+  // CTA pairs when there is enough work for the 74 pairs of the chip; tiny-M problems stay on single CTAs
+  const bool pair = !g_dbg_disable_pair && BN == 256 && a.M > 2 * BM;
   CUtensorMap ta, tb;
   {
     uint64_t dims[2], strides[1]; uint32_t box[2];
@@ -313,7 +594,7 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
     strides[0] = uint64_t(a.lda) * 2;
     int rc = make_tmap_bf16(&ta, a.A, 2, dims, strides, box);
     if (rc) return rc;
-    if (a.b_layout == 0) { dims[0] = a.K; dims[1] = a.N; box[0] = 64; box[1] = BN; }
+    if (a.b_layout == 0) { dims[0] = a.K; dims[1] = a.N; box[0] = 64; box[1] = pair ? BN / 2 : BN; }
     else                 { dims[0] = a.N; dims[1] = a.K; box[0] = 64; box[1] = BK; }
     strides[0] = uint64_t(a.ldb) * 2;
     rc = make_tmap_bf16(&tb, a.B, 2, dims, strides, box);
@@ -321,7 +602,7 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
   }
   GemmTcParams p;
   p.M = int(a.M); p.N = int(a.N); p.K = int(a.K);
-  p.num_m = int((a.M + BM - 1) / BM);
+  p.num_m = pair ? int((a.M + 2 * BM - 1) / (2 * BM)) : int((a.M + BM - 1) / BM);
   p.num_n = int((a.N + BN - 1) / BN);
   p.kb_total = int((a.K + BK - 1) / BK);
   p.split_k = split > p.kb_total ? p.kb_total : split;
@@ -342,6 +623,16 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
   if (a.b_layout == 0) { p.b_lbo = 16; p.b_sbo = 1024; p.b_kadv = 32; } else { p.b_lbo = mn_lbo; p.b_sbo = mn_sbo; p.b_kadv = mn_kadv; }
 
   const int units = p.num_m * p.num_n * p.split_k;
+  if (pair) {
+    const int clusters = units < num_sms() / 2 ? units : num_sms() / 2;
+    const int pkey = (a.a_layout ? 2 : 0) | (a.b_layout ? 1 : 0);
+    switch (pkey) {
+      case 0: return launch_pair<256, 6, 0, 0>(ta, tb, p, 2 * clusters, st);
+      case 1: return launch_pair<256, 6, 0, 1>(ta, tb, p, 2 * clusters, st);
+      case 2: return launch_pair<256, 6, 1, 0>(ta, tb, p, 2 * clusters, st);
+      default: return launch_pair<256, 6, 1, 1>(ta, tb, p, 2 * clusters, st);
+    }
+  }
   const int grid = units < num_sms() ? units : num_sms();
   const int key = (BN == 256 ? 4 : 0) | (a.a_layout ? 2 : 0) | (a.b_layout ? 1 : 0);
   switch (key) {

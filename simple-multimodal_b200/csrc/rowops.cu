@@ -73,21 +73,21 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
                                                             const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                             const float* __restrict__ gamma, const T* __restrict__ dres,
                                                             T* __restrict__ dx, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, long long rows, int H) {
+                                                            float* __restrict__ dbeta, float* __restrict__ dxsum, long long rows, int H) {
   constexpr int VN = Vec16<T>::N;
-  extern __shared__ float sred[];  // [2][H]
-  for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) sred[i] = 0.f;
+  extern __shared__ float sred[];  // [3][H]: dgamma, dbeta, column sum of dx (bias gradient of the producing Linear)
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) sred[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int nvec = H / VN;
-  float pg[NV][VN], pb[NV][VN], gm[NV][VN];
+  float pg[NV][VN], pb[NV][VN], gm[NV][VN], px[NV][VN];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
 #pragma unroll
-    for (int j = 0; j < VN; ++j) { pg[i][j] = 0.f; pb[i][j] = 0.f; gm[i][j] = vi < nvec ? gamma[vi * VN + j] : 0.f; }
+    for (int j = 0; j < VN; ++j) { pg[i][j] = 0.f; pb[i][j] = 0.f; px[i][j] = 0.f; gm[i][j] = vi < nvec ? gamma[vi * VN + j] : 0.f; }
   }
   for (long long row = warp0; row < rows; row += nwarps) {
     const float mean = mean_in[row], rstd = rstd_in[row];
@@ -124,6 +124,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
           for (int j = 0; j < VN; ++j) o[j] += f[j];
         }
         Vec16<T> t; t.pack(o); t.store(dx + row * H + vi * VN);
+        if (dxsum) {            // sum what was stored (rounded to T), so it equals a column sum over the dx tensor
+          float q[VN]; t.unpack(q);
+#pragma unroll
+          for (int j = 0; j < VN; ++j) px[i][j] += q[j];
+        }
       }
     }
   }
@@ -135,6 +140,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
       for (int j = 0; j < VN; ++j) {
         atomicAdd(&sred[vi * VN + j], pg[i][j]);
         atomicAdd(&sred[H + vi * VN + j], pb[i][j]);
+        if (dxsum) atomicAdd(&sred[2 * H + vi * VN + j], px[i][j]);
       }
     }
   }
@@ -142,33 +148,59 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
     atomicAdd(dgamma + i, sred[i]);
     atomicAdd(dbeta + i, sred[H + i]);
+    if (dxsum) atomicAdd(dxsum + i, sred[2 * H + i]);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
+// out[n] += sum_m x[m,n].  Block = CX column-threads (16 bytes each) x RY row-groups; every thread keeps 8 independent
+// 16-byte loads in flight, the row-groups are combined in shared memory, one atomicAdd per column per block.
 template <typename T>
-__global__ void __launch_bounds__(128) colsum_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ out,
-                                                     long long M, long long N, int rows_per_block, int vec_ok) {
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ out,
+                                                     long long M, long long N, int rows_per_block, int vec_ok, int CX) {
   constexpr int VN = Vec16<T>::N;
-  const long long c0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VN;
-  if (c0 >= N) return;
+  __shared__ float red[256 * VN];
+  const int RY = 256 / CX;
+  const int cx = threadIdx.x % CX, ry = threadIdx.x / CX;
+  const long long c0 = ((long long)blockIdx.x * CX + cx) * VN;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
   float acc[VN];
 #pragma unroll
   for (int j = 0; j < VN; ++j) acc[j] = 0.f;
-  if (c0 + VN <= N && vec_ok) {
-#pragma unroll 4
-    for (long long r = r0; r < r1; ++r) {
-      Vec16<T> t; t.load(x + r * ldx + c0); float f[VN]; t.unpack(f);
+  if (c0 < N) {
+    if (c0 + VN <= N && vec_ok) {
+      long long r = r0 + ry;
+      for (; r + 7LL * RY < r1; r += 8LL * RY) {
+        Vec16<T> t[8];
 #pragma unroll
-      for (int j = 0; j < VN; ++j) acc[j] += f[j];
+        for (int u = 0; u < 8; ++u) t[u].load(x + (r + (long long)u * RY) * ldx + c0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float f[VN]; t[u].unpack(f);
+#pragma unroll
+          for (int j = 0; j < VN; ++j) acc[j] += f[j];
+        }
+      }
+      for (; r < r1; r += RY) {
+        Vec16<T> t; t.load(x + r * ldx + c0); float f[VN]; t.unpack(f);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) acc[j] += f[j];
+      }
+    } else {
+      for (long long r = r0 + ry; r < r1; r += RY)
+        for (int j = 0; j < VN && c0 + j < N; ++j) acc[j] += to_f32(x[r * ldx + c0 + j]);
     }
-  } else {
-    for (long long r = r0; r < r1; ++r)
-      for (int j = 0; j < VN && c0 + j < N; ++j) acc[j] += to_f32(x[r * ldx + c0 + j]);
   }
-  for (int j = 0; j < VN && c0 + j < N; ++j) atomicAdd(out + c0 + j, acc[j]);
+#pragma unroll
+  for (int j = 0; j < VN; ++j) red[threadIdx.x * VN + j] = acc[j];
+  __syncthreads();
+  if (ry == 0 && c0 < N) {
+    for (int g = 1; g < RY; ++g)
+#pragma unroll
+      for (int j = 0; j < VN; ++j) acc[j] += red[(g * CX + cx) * VN + j];
+    for (int j = 0; j < VN && c0 + j < N; ++j) atomicAdd(out + c0 + j, acc[j]);
+  }
 }
 
 template <typename T>
@@ -429,7 +461,7 @@ int b200f_layernorm_fwd(const void* x, const float* gamma, const float* beta, co
 }
 
 int b200f_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, const void* dres,
-                        void* dx, float* dgamma, float* dbeta, int64_t rows, int32_t H, int32_t dtype, void* stream) {
+                        void* dx, float* dgamma, float* dbeta, float* dxsum, int64_t rows, int32_t H, int32_t dtype, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (rows == 0) return B200F_OK;
   DISPATCH_DTYPE(dtype, T, {
@@ -440,8 +472,8 @@ int b200f_layernorm_bwd(const void* dy, const void* x, const float* mean, const 
     const long long blocks = (rows + 7) / 8;
     const int grid = int(blocks < (long long)num_sms() * 4 ? blocks : (long long)num_sms() * 4);
     DISPATCH_NV(need, NV, {
-      layernorm_bwd_kernel<T, NV><<<grid, 256, 2 * H * sizeof(float), st>>>(static_cast<const T*>(dy), static_cast<const T*>(x), mean, rstd, gamma,
-                                                                            static_cast<const T*>(dres), static_cast<T*>(dx), dgamma, dbeta, rows, H);
+      layernorm_bwd_kernel<T, NV><<<grid, 256, 3 * H * sizeof(float), st>>>(static_cast<const T*>(dy), static_cast<const T*>(x), mean, rstd, gamma,
+                                                                            static_cast<const T*>(dres), static_cast<T*>(dx), dgamma, dbeta, dxsum, rows, H);
     })
   })
   return check_launch("layernorm_bwd");
@@ -453,13 +485,17 @@ int b200f_colsum_accum(const void* x, int64_t ldx, float* out, int64_t M, int64_
   DISPATCH_DTYPE(dtype, T, {
     constexpr int VN = Vec16<T>::N;
     const int vec_ok = (ldx % VN == 0 && aligned16(x)) ? 1 : 0;
-    const int gx = int((N + VN * 128 - 1) / (VN * 128));
+    const long long nvec = (N + VN - 1) / VN;
+    int CX = 32;
+    while (CX < 256 && CX < nvec) CX *= 2;
+    const int gx = int((nvec + CX - 1) / CX);
     long long slabs = (long long)num_sms() * 4 / gx;
     if (slabs < 1) slabs = 1;
     long long rpb = (M + slabs - 1) / slabs;
-    if (rpb < 32) rpb = 32;
+    const long long min_rows = 8LL * (256 / CX);
+    if (rpb < min_rows) rpb = min_rows;
     const int gy = int((M + rpb - 1) / rpb);
-    colsum_kernel<T><<<dim3(gx, gy), 128, 0, st>>>(static_cast<const T*>(x), ldx, out, M, N, int(rpb), vec_ok);
+    colsum_kernel<T><<<dim3(gx, gy), 256, 0, st>>>(static_cast<const T*>(x), ldx, out, M, N, int(rpb), vec_ok, CX);
   })
   return check_launch("colsum");
 }

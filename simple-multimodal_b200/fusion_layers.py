@@ -178,7 +178,8 @@ class CrossModalTransformer(_FusionBase):
 class MultimodalTransformer(_FusionBase):
     """reference models/fusion_layers.py:93-179, executed by mult_engine.MulTFn (chunked, fused schedule)."""
 
-    chunk_size = 128
+    chunk_size = 128            # samples per MulT chunk
+    stash_fraction = 0.55       # share of the currently free device memory that forward may keep resident for backward
 
     def __init__(self, config):
         super().__init__()
@@ -202,7 +203,9 @@ class MultimodalTransformer(_FusionBase):
                                   "use fusion_dropout=0 or eval() (no silent fallback)")
         params = dict(self.named_parameters())
         H, heads = self.config.fusion_hidden_size, self.config.fusion_num_heads
-        return mult_engine.MulTFn.apply(t, a, v, H, heads, int(self.chunk_size), self._names, *[params[n] for n in self._names])
+        free_bytes, _ = torch.cuda.mem_get_info(t.device)
+        budget = int(self.stash_fraction * free_bytes) if torch.is_grad_enabled() else 0
+        return mult_engine.MulTFn.apply(t, a, v, H, heads, int(self.chunk_size), budget, self._names, *[params[n] for n in self._names])
 
     def forward(self, text_features, audio_features, video_features, mask=None) -> Dict[str, Tensor]:
         (t, a, v), mask, _ = self._prepare((text_features, audio_features, video_features), mask)

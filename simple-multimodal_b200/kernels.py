@@ -126,11 +126,11 @@ def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, post1=None
 
 
 def layernorm_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor, dgamma: Tensor, dbeta: Tensor,
-                  dres: Optional[Tensor] = None) -> Tensor:
+                  dres: Optional[Tensor] = None, dxsum: Optional[Tensor] = None) -> Tensor:
     rows, H, _ = _rows(x)
     dx = torch.empty_like(x)
     check(lib().b200f_layernorm_bwd(ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dres), ptr(dx), ptr(dgamma),
-                                    ptr(dbeta), C.c_int64(rows), C.c_int32(H), dtype_code(x.dtype), stream_ptr()),
+                                    ptr(dbeta), ptr(dxsum), C.c_int64(rows), C.c_int32(H), dtype_code(x.dtype), stream_ptr()),
           "b200f_layernorm_bwd")
     return dx
 

@@ -156,19 +156,17 @@ def _chunk_backward(st, W: _Weights, H: int, heads: int, dpooled: Tensor, G: Dic
         s = st[name]
         # d(enhanced) reaches both blocks' LN2 outputs and the input unchanged
         ds2 = K.layernorm_bwd(d_enh[qm], s["s2"], s["mean2"], s["rstd2"], W.f32(f"{name}.norm2.weight"),
-                              G[f"{name}.norm2.weight"], G[f"{name}.norm2.bias"])
+                              G[f"{name}.norm2.weight"], G[f"{name}.norm2.bias"], dxsum=G[f"{name}.ffn.3.bias"])   # + bias grad of FFN2
         K.linear_wgrad(ds2, s["hid"], G[f"{name}.ffn.3.weight"])
-        K.colsum_accum(ds2, G[f"{name}.ffn.3.bias"])
         dhid = K.linear_dgrad(ds2, W.w(f"{name}.ffn.3.weight"), relu_mask=s["hid"])        # ReLU' fused in the epilogue
         K.linear_wgrad(dhid, s["x1"], G[f"{name}.ffn.0.weight"])
         K.colsum_accum(dhid, G[f"{name}.ffn.0.bias"])
         dx1 = K.linear_dgrad(dhid, W.w(f"{name}.ffn.0.weight"), residual=ds2)             # + residual path x1 -> s2
         ds1 = K.layernorm_bwd(dx1, s["s1"], s["mean1"], s["rstd1"], W.f32(f"{name}.norm1.weight"),
-                              G[f"{name}.norm1.weight"], G[f"{name}.norm1.bias"])
+                              G[f"{name}.norm1.weight"], G[f"{name}.norm1.bias"], dxsum=G[f"{name}.attention.out_proj.bias"])
         d_s1[name] = ds1
         ctx2 = s["ctx"].view(-1, H)
         K.linear_wgrad(ds1, ctx2, G[f"{name}.attention.out_proj.weight"])
-        K.colsum_accum(ds1, G[f"{name}.attention.out_proj.bias"])
         dctx = K.linear_dgrad(ds1, W.w(f"{name}.attention.out_proj.weight")).view(Bc, Ls[qm], H)
         qo, ko = W.q_slot[name], W.kv_slot[name]
         K.attn_bwd(dctx, proj[qm][:, :, qo:qo + H], proj[km][:, :, ko:ko + H], proj[km][:, :, ko + H:ko + 2 * H], s["ctx"], s["lse"],
@@ -185,24 +183,38 @@ def _chunk_backward(st, W: _Weights, H: int, heads: int, dpooled: Tensor, G: Dic
     return dxs if need_dx else None
 
 
+def stash_bytes_per_sample(Ls, H: int, elem: int) -> int:
+    """Activation bytes `_chunk_forward(keep=True)` holds per sample (packed projections, per-block ctx/s1/x1/hid/s2,
+    enhanced, self-attention qkv/ctx) -- used to decide how many chunks can stay resident between forward and backward."""
+    tok = sum(Ls)
+    per_tok = 6 * H + H + 3 * H + H                 # packed projection, enhanced, self qkv, self ctx
+    per_qtok = 2 * (H + H + H + 4 * H + H)          # two query blocks per token: ctx, s1, x1, hid, s2
+    return (per_tok + per_qtok) * tok * elem
+
+
 class MulTFn(torch.autograd.Function):
-    """(text, audio, video [B,L,H]) + MulT parameters -> pooled attended features [B,3H]."""
+    """(text, audio, video [B,L,H]) + MulT parameters -> pooled attended features [B,3H].
+
+    The batch runs in chunks of `chunk` samples.  Chunks whose activations fit in `stash_budget` bytes stay resident
+    for backward; the remaining chunks are recomputed chunk by chunk in backward (bounded memory at any batch)."""
 
     @staticmethod
-    def forward(ctx, t, a, v, H, heads, chunk, names, *params):
+    def forward(ctx, t, a, v, H, heads, chunk, stash_budget, names, *params):
         xs = [x.contiguous() for x in (t, a, v)]
         B = xs[0].size(0)
         P = dict(zip(names, params))
         W = _Weights(P, H, xs[0].dtype)
         pooled = torch.empty((B, 3 * H), device=t.device, dtype=t.dtype)
         need_grad = any(ctx.needs_input_grad)
-        single = B <= chunk
-        stash = None
-        for b0 in range(0, B, chunk):
+        per_chunk = stash_bytes_per_sample([x.size(1) for x in xs], H, xs[0].element_size()) * min(chunk, B)
+        n_keep = int(stash_budget // max(per_chunk, 1)) if need_grad else 0
+        stash = {}
+        for ci, b0 in enumerate(range(0, B, chunk)):
             b1 = min(B, b0 + chunk)
-            st = _chunk_forward([x[b0:b1] for x in xs], W, H, heads, pooled[b0:b1], keep=need_grad and single)
-            if single:
-                stash = st
+            keep = ci < n_keep
+            st = _chunk_forward([x[b0:b1] for x in xs], W, H, heads, pooled[b0:b1], keep=keep)
+            if keep:
+                stash[b0] = st
         ctx.cfg = (H, heads, chunk, names)
         ctx.W, ctx.stash, ctx.xs = (W if need_grad else None), stash, (xs if need_grad else None)
         return pooled
@@ -219,15 +231,19 @@ class MulTFn(torch.autograd.Function):
         dstack_b = [torch.zeros(b.shape, device=dev, dtype=torch.float32) for b in W.b_stack]
         need_dx = any(ctx.needs_input_grad[:3])
         dxs = [torch.empty_like(x) for x in xs] if need_dx else None
-        scratch = torch.empty((min(chunk, B), 3 * H), device=dev, dtype=xs[0].dtype)
-        for b0 in range(0, B, chunk):
+        scratch = None
+        for b0 in reversed(range(0, B, chunk)):        # recomputed (late) chunks first, then the resident ones are released in turn
             b1 = min(B, b0 + chunk)
-            st = ctx.stash if ctx.stash is not None else _chunk_forward([x[b0:b1] for x in xs], W, H, heads, scratch[:b1 - b0], keep=True)
+            st = ctx.stash.pop(b0, None)
+            if st is None:
+                if scratch is None:
+                    scratch = torch.empty((min(chunk, B), 3 * H), device=dev, dtype=xs[0].dtype)
+                st = _chunk_forward([x[b0:b1] for x in xs], W, H, heads, scratch[:b1 - b0], keep=True)
             out = _chunk_backward(st, W, H, heads, dpooled[b0:b1], G, dstack_w, dstack_b, need_dx)
             if need_dx:
                 for m in range(3):
                     dxs[m][b0:b1].copy_(out[m])
-            del st
+            del st, out
         ctx.stash = None
         # scatter the stacked-projection gradients back onto the blocks' in_proj parameters
         for m in range(3):
@@ -239,6 +255,6 @@ class MulTFn(torch.autograd.Function):
                 dst_w[lo:lo + n].copy_(dstack_w[m][row:row + n])
                 dst_b[lo:lo + n].copy_(dstack_b[m][row:row + n])
                 row += n
-        grads = [G[n] if ctx.needs_input_grad[7 + i] else None for i, n in enumerate(names)]
+        grads = [G[n] if ctx.needs_input_grad[8 + i] else None for i, n in enumerate(names)]
         return (dxs[0] if need_dx else None, dxs[1] if need_dx else None, dxs[2] if need_dx else None,
-                None, None, None, None, *grads)
+                None, None, None, None, None, *grads)

@@ -51,8 +51,10 @@ def device_run(kind, cfg, P, feats, flag, dtype, mask=None, chunk=None):
     head = getattr(FL, CLS[kind])(cfg).cuda()
     head.load_state_dict(P, strict=True)
     head.train()
-    if chunk is not None:
-        (head.mult_fusion if kind == "hierarchical" else head).chunk_size = chunk
+    if chunk is not None:                      # small chunks + a one-chunk stash budget: exercises resident AND recomputed chunks
+        mt = head.mult_fusion if kind == "hierarchical" else head
+        mt.chunk_size = chunk
+        mt.stash_fraction = 1e-9 if chunk == 2 else mt.stash_fraction
     xs = [f.to("cuda", dtype).requires_grad_(True) for f in feats]
     kw = {}
     if kind in ("contrastive", "hierarchical"):

@@ -12,7 +12,7 @@ L = importlib.import_module("simple-multimodal_b200._lib")
 
 
 def run_gemm(A, B, M, N, K, a_layout, b_layout, dtype, bias=None, residual=None, mask=None, relu=False,
-             accum_into=None, split_k=1, alpha=1.0, out_f32=False):
+             accum_into=None, split_k=1, alpha=1.0, out_f32=False, sync=True):
     dev = A.device
     flags = 0
     if relu:
@@ -34,7 +34,8 @@ def run_gemm(A, B, M, N, K, a_layout, b_layout, dtype, bias=None, residual=None,
                       relu_mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
                       alpha=alpha, flags=flags, dtype=L.dtype_code(dtype), split_k=split_k)
     L.check(L.lib().b200f_gemm(C.byref(args), L.stream_ptr()), "b200f_gemm")
-    torch.cuda.synchronize()
+    if sync:
+        torch.cuda.synchronize()
     return Cbuf
 
 

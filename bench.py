@@ -254,6 +254,7 @@ def main():
     # ---- device-timed region (inputs resident in HBM), GEMM launches timed live
     sampler = ClockSampler(local_rank)
     sampler.start()
+    K.prealloc_profile_events(2 * 400 * args.steps)
     K.GEMM_PROFILE = []
     l0 = pkg._lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -178,7 +178,7 @@ class CrossModalTransformer(_FusionBase):
 class MultimodalTransformer(_FusionBase):
     """reference models/fusion_layers.py:93-179, executed by mult_engine.MulTFn (chunked, fused schedule)."""
 
-    chunk_size = 128            # samples per MulT chunk
+    chunk_size = 256            # samples per MulT chunk (~7.4 GB of bf16 activations at L=512/512/30, H=512)
     stash_fraction = 0.55       # share of the currently free device memory that forward may keep resident for backward
 
     def __init__(self, config):

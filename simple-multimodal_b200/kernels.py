@@ -26,6 +26,19 @@ def _rows(x: Tensor):
     return x.numel() // k, k, k
 
 
+_EVENT_POOL = []
+
+
+def _event():
+    return _EVENT_POOL.pop() if _EVENT_POOL else torch.cuda.Event(enable_timing=True)
+
+
+def prealloc_profile_events(n: int) -> None:
+    """Create the CUDA events the live GEMM profile will need up front, outside any timed region."""
+    while len(_EVENT_POOL) < n:
+        _EVENT_POOL.append(torch.cuda.Event(enable_timing=True))
+
+
 # Optional live profile of the dominant kernel (bench.py): CUDA-event pairs around every GEMM launch.
 GEMM_PROFILE = None          # None, or a list collecting (start_event, stop_event, flops, is_tensor_core)
 
@@ -73,7 +86,7 @@ def gemm(a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_layout: int = 0, b_l
     if GEMM_PROFILE is None:
         check(lib().b200f_gemm(C.byref(args), stream_ptr()), "b200f_gemm")
         return out
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = _event(), _event()
     e0.record()
     check(lib().b200f_gemm(C.byref(args), stream_ptr()), "b200f_gemm")
     e1.record()

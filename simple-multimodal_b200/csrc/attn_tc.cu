@@ -39,6 +39,31 @@ struct AttnTcParams {
   bf16* dV; long long lddv;
 };
 
+// Epilogue helper: this warp's 32 accumulator rows x 64 fp32 columns in TMEM -> (x mul) -> bf16 -> a private [32 x 128 B]
+// swizzled smem tile -> global, 4 full 128-byte rows per store instruction (a thread owns a ROW in TMEM, so direct
+// stores would touch 32 different lines per instruction).  `gbase` points at (first row of this warp, first column).
+__device__ __forceinline__ void store_rows64(uint32_t taddr, uint8_t* stage, bf16* gbase, long long ld, int rows_valid, int lane, float mul) {
+#pragma unroll
+  for (int cc = 0; cc < HD; cc += 16) {
+    uint32_t r[16];
+    tmem_ld16(taddr + cc, r);
+    tmem_ld_wait();
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) pk[i >> 1] = pack_bf16(__uint_as_float(r[i]) * mul, __uint_as_float(r[i + 1]) * mul);
+    *reinterpret_cast<uint4*>(stage + sw128_offset(lane, cc >> 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(stage + sw128_offset(lane, (cc >> 3) + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+  __syncwarp();
+  const int crow = lane >> 3, cchunk = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + crow;
+    if (r < rows_valid)
+      *reinterpret_cast<uint4*>(gbase + (long long)r * ld + cchunk * 8) = *reinterpret_cast<const uint4*>(stage + sw128_offset(r, cchunk));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
@@ -115,8 +140,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         umma_commit(s_full);
         mbar_wait(p_ready, j & 1);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < TK / 16; ++k)
+        // only the 16-key groups that hold valid keys: the softmax threads leave the P columns past ceil32(valid) untouched
+        const int ksteps = (min(TK, p.Lk - j * TK) + 15) >> 4;
+        for (int k = 0; k < ksteps; ++k)
           umma_ss(t_o, umma_desc(sp + (k >> 2) * (TQ * 128) + (k & 3) * 32, 16, 1024), umma_desc(sv + k * 2048, TK * 128, 1024), idesc_o,
                   (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&kv_empty[st]);
@@ -129,37 +155,57 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int row = grp * 32 + lane;                 // row of the tile == TMEM lane
     const uint32_t lane_addr = uint32_t(grp * 32) << 16;
     const float c = p.scale * LOG2E;
-    float m = -INFINITY, l = 0.f;
+    const uint64_t c2 = f2_pack(c, c);
+    float m = -INFINITY, l = 0.f;                    // m: reference max the stored P / O are scaled against (raw score units)
     uint8_t* prow = smem + FwdSmem::P_OFF;
     for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(s_full, j & 1);                      // also implies PV(j-1) retired: O and the P tile are ours again
       tc_fence_after();
       const int valid = min(TK, p.Lk - j * TK);      // keys beyond Lk were zero-filled by TMA: mask them
-      float tmax = -INFINITY;
+      const int cols = (valid + 31) & ~31;
+      const bool ragged = valid < cols;
+      float tmax = -INFINITY, tmax_b = -INFINITY;
 #pragma unroll 1
-      for (int cc = 0; cc < TK; cc += 32) {
+      for (int cc = 0; cc < cols; cc += 32) {
         uint32_t r[32];
         tmem_ld32(t_s + lane_addr + cc, r);
         tmem_ld_wait();
+        if (ragged && cc + 32 > valid) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (cc + i < valid) tmax = fmaxf(tmax, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; ++i)
+            if (cc + i >= valid) r[i] = 0xff800000u;   // -inf
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          tmax = fmax3(tmax, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+          tmax_b = fmax3(tmax_b, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        }
       }
-      const float m_new = fmaxf(m, tmax);
-      const float alpha = exp2f((m - m_new) * c);    // first tile: m = -inf -> 0
-      const float mc = m_new * c;
-      float lsum = 0.f;
+      const float m_new = fmax3(m, tmax, tmax_b);
+      // lazy rescale: move the reference max only when it would grow by more than 2^8, so P <= 2^8 (exact after the final O / l)
+      const bool grow = (m_new - m) * c > 8.f;       // first tile: m = -inf -> true
+      const float m_use = grow ? m_new : m;
+      const float alpha = grow ? ex2_approx((m - m_use) * c) : 1.f;   // first tile: 0
+      const float nmc = -m_use * c;
+      const uint64_t nmc2 = f2_pack(nmc, nmc);
+      uint64_t lsum2 = 0ull;
 #pragma unroll 1
-      for (int cc = 0; cc < TK; cc += 32) {
+      for (int cc = 0; cc < cols; cc += 32) {
         uint32_t r[32];
         tmem_ld32(t_s + lane_addr + cc, r);
         tmem_ld_wait();
+        if (ragged && cc + 32 > valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (cc + i >= valid) r[i] = 0xff800000u;   // ex2(-inf) = 0
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float e0 = (cc + i < valid) ? exp2f(__uint_as_float(r[i]) * c - mc) : 0.f;
-          const float e1 = (cc + i + 1 < valid) ? exp2f(__uint_as_float(r[i + 1]) * c - mc) : 0.f;
-          lsum += e0 + e1;
+          float x0, x1;
+          f2_unpack(f2_fma(f2_pack_u(r[i], r[i + 1]), c2, nmc2), x0, x1);
+          const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+          lsum2 = f2_add(lsum2, f2_pack(e0, e1));
           pk[i >> 1] = pack_bf16(e0, e1);
         }
         // 32 keys = four 16-byte chunks of this row inside the 64-key half (cc >> 6)
@@ -170,11 +216,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           *reinterpret_cast<uint4*>(half + sw128_offset(row, chunk)) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
         }
       }
-      l = l * alpha + lsum;
-      m = m_new;
-      if (j > 0) {                                     // O was accumulated against the old max: rescale it in TMEM
-        mbar_wait(pv_done, (j - 1) & 1);
-        tc_fence_after();
+      float ls0, ls1;
+      f2_unpack(lsum2, ls0, ls1);
+      l = l * alpha + (ls0 + ls1);
+      m = m_use;
+      if (j > 0 && __any_sync(0xffffffffu, grow)) {    // O was accumulated against the old reference max: rescale it in TMEM
 #pragma unroll
         for (int cc = 0; cc < HD; cc += 16) {
           uint32_t r[16];
@@ -195,21 +241,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     tc_fence_after();
     const float inv = 1.f / l;
     const int qrow = q0 + row;
-    bf16* orow = p.O + ((long long)b * p.Lq + qrow) * p.ldo + h * HD;
-#pragma unroll
-    for (int cc = 0; cc < HD; cc += 16) {
-      uint32_t r[16];
-      tmem_ld16(t_o + lane_addr + cc, r);
-      tmem_ld_wait();
-      if (qrow < p.Lq) {
-        uint32_t pk[8];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) pk[i >> 1] = pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
-        *reinterpret_cast<uint4*>(orow + cc) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(orow + cc + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
-    }
+    // O / l -> bf16 -> this warp's 32 x 128 B slice of the (now free) P tile -> full 128-byte lines to global
     if (qrow < p.Lq) p.LSE[((long long)b * p.H + h) * p.Lq + qrow] = m * p.scale + logf(l);
+    store_rows64(t_o + lane_addr, smem + FwdSmem::P_OFF + grp * (32 * 128), p.O + ((long long)b * p.Lq + q0 + grp * 32) * p.ldo + h * HD, p.ldo,
+                 p.Lq - (q0 + grp * 32), lane, inv);
   }
 
   tc_fence_before();
@@ -371,8 +406,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const int qrow = q0 + row;
     const long long ri = ((long long)b * p.H + h) * p.Lq + qrow;
     const float c = p.scale * LOG2E;
-    const float lse2 = (qrow < p.Lq ? p.LSE[ri] : 0.f) * LOG2E;
-    const float dl = qrow < p.Lq ? p.delta[ri] : 0.f;
+    const float nlse2 = -(qrow < p.Lq ? p.LSE[ri] : 0.f) * LOG2E;
+    const float ndl = -(qrow < p.Lq ? p.delta[ri] : 0.f) * p.scale;
+    const uint64_t c2 = f2_pack(c, c), nlse22 = f2_pack(nlse2, nlse2), sc2 = f2_pack(p.scale, p.scale), ndl2 = f2_pack(ndl, ndl);
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(sdp_full, j & 1);      // also implies the previous tile's dQ MMAs (which read the dS tile) retired
       tc_fence_after();
@@ -384,9 +420,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = exp2f(__uint_as_float(rs[i]) * c - lse2), p1 = exp2f(__uint_as_float(rs[i + 1]) * c - lse2);
-          pk[i >> 1] = pack_bf16(p0 * (__uint_as_float(rp[i]) - dl) * p.scale, p1 * (__uint_as_float(rp[i + 1]) - dl) * p.scale);
+        for (int i = 0; i < 32; i += 2) {     // dS = P o (dP - delta) * scale, two elements per FFMA2 / FMUL2
+          float x0, x1, d0, d1;
+          f2_unpack(f2_fma(f2_pack_u(rs[i], rs[i + 1]), c2, nlse22), x0, x1);
+          const uint64_t t2 = f2_fma(f2_pack_u(rp[i], rp[i + 1]), sc2, ndl2);
+          f2_unpack(f2_mul(f2_pack(ex2_approx(x0), ex2_approx(x1)), t2), d0, d1);
+          pk[i >> 1] = pack_bf16(d0, d1);
         }
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
@@ -399,20 +438,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     }
     mbar_wait(dq_done, (n_tiles - 1) & 1);
     tc_fence_after();
-    bf16* dq = p.dQ + ((long long)b * p.Lq + qrow) * p.lddq + h * HD;
-#pragma unroll
-    for (int cc = 0; cc < HD; cc += 16) {
-      uint32_t r[16];
-      tmem_ld16(t_dq + lane_addr + cc, r);
-      tmem_ld_wait();
-      if (qrow < p.Lq) {
-        uint32_t pk[8];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) pk[i >> 1] = pack_bf16(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-        *reinterpret_cast<uint4*>(dq + cc) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(dq + cc + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
-    }
+    // the dS tile is free once the last dQ MMA retired: stage dQ through this warp's 4 KB slice of it
+    store_rows64(t_dq + lane_addr, smem + DqSmem::DS_OFF + grp * (32 * 128), p.dQ + ((long long)b * p.Lq + q0 + grp * 32) * p.lddq + h * HD, p.lddq,
+                 p.Lq - (q0 + grp * 32), lane, 1.f);
   }
   tc_fence_before();
   __syncthreads();
@@ -516,13 +544,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const int t128 = threadIdx.x - 64;               // 0..127 among the softmax threads
     const uint32_t lane_addr = uint32_t(grp * 32) << 16;
     const float c = p.scale * LOG2E;
+    const uint64_t c2 = f2_pack(c, c), sc2 = f2_pack(p.scale, p.scale);
     const long long stat_base = ((long long)b * p.H + h) * p.Lq;
     for (int i = 0; i < n_tiles; ++i) {
       float* sl = stats + (i & 1) * 2 * BT;          // [lse2[64] | delta[64]] for this tile's queries
       {
         const int qi = i * BT + (t128 & 63);
-        float v = 0.f;
-        if (qi < p.Lq) v = t128 < 64 ? p.LSE[stat_base + qi] * LOG2E : p.delta[stat_base + qi];
+        float v = 0.f;                               // stored negated (and delta pre-scaled) so the inner loop is pure FFMA2
+        if (qi < p.Lq) v = t128 < 64 ? -p.LSE[stat_base + qi] * LOG2E : -p.delta[stat_base + qi] * p.scale;
         sl[t128] = v;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -535,11 +564,17 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         tmem_ld32(t_dp + lane_addr + cc, rp);
         tmem_ld_wait();
         uint32_t pp[16], pd[16];
+        const uint64_t* nl2 = reinterpret_cast<const uint64_t*>(sl + cc);         // -lse2 of queries cc.., pairs (warp-broadcast reads)
+        const uint64_t* nd2 = reinterpret_cast<const uint64_t*>(sl + BT + cc);    // -delta*scale
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          const float p0 = exp2f(__uint_as_float(rs[e]) * c - sl[cc + e]), p1 = exp2f(__uint_as_float(rs[e + 1]) * c - sl[cc + e + 1]);
+          float x0, x1, d0, d1;
+          f2_unpack(f2_fma(f2_pack_u(rs[e], rs[e + 1]), c2, nl2[e >> 1]), x0, x1);
+          const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          const uint64_t t2 = f2_fma(f2_pack_u(rp[e], rp[e + 1]), sc2, nd2[e >> 1]);
+          f2_unpack(f2_mul(f2_pack(p0, p1), t2), d0, d1);
           pp[e >> 1] = pack_bf16(p0, p1);
-          pd[e >> 1] = pack_bf16(p0 * (__uint_as_float(rp[e]) - sl[BT + cc + e]) * p.scale, p1 * (__uint_as_float(rp[e + 1]) - sl[BT + cc + e + 1]) * p.scale);
+          pd[e >> 1] = pack_bf16(d0, d1);
         }
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
@@ -555,27 +590,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     }
     mbar_wait(acc_done, (n_tiles - 1) & 1);
     tc_fence_after();
-    const int krow = k0 + row;
-    bf16* dk = p.dK + ((long long)b * p.Lk + krow) * p.lddk + h * HD;
-    bf16* dv = p.dV + ((long long)b * p.Lk + krow) * p.lddv + h * HD;
-#pragma unroll
-    for (int cc = 0; cc < HD; cc += 16) {
-      uint32_t r1[16], r2[16];
-      tmem_ld16(t_dv + lane_addr + cc, r1);
-      tmem_ld16(t_dk + lane_addr + cc, r2);
-      tmem_ld_wait();
-      if (krow < p.Lk) {
-        uint32_t pk[8];
-#pragma unroll
-        for (int e = 0; e < 16; e += 2) pk[e >> 1] = pack_bf16(__uint_as_float(r1[e]), __uint_as_float(r1[e + 1]));
-        *reinterpret_cast<uint4*>(dv + cc) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(dv + cc + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-#pragma unroll
-        for (int e = 0; e < 16; e += 2) pk[e >> 1] = pack_bf16(__uint_as_float(r2[e]), __uint_as_float(r2[e + 1]));
-        *reinterpret_cast<uint4*>(dk + cc) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(dk + cc + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
-    }
+    // P^T / dS^T tiles are free once the last accumulation MMA retired: stage dV / dK through this warp's slices of them
+    store_rows64(t_dv + lane_addr, smem + DkvSmem::P_OFF + grp * (32 * 128), p.dV + ((long long)b * p.Lk + k0 + grp * 32) * p.lddv + h * HD, p.lddv,
+                 p.Lk - (k0 + grp * 32), lane, 1.f);
+    store_rows64(t_dk + lane_addr, smem + DkvSmem::DS_OFF + grp * (32 * 128), p.dK + ((long long)b * p.Lk + k0 + grp * 32) * p.lddk + h * HD, p.lddk,
+                 p.Lk - (k0 + grp * 32), lane, 1.f);
   }
   tc_fence_before();
   __syncthreads();

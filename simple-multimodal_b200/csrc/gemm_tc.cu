@@ -43,8 +43,9 @@ struct GemmSmem {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int EPI_OFFSET = BAR_OFFSET + 256;                          // 8 x 4 KB epilogue staging tiles
-  static constexpr int TOTAL = EPI_OFFSET + 8 * EPI_STAGE_BYTES + 1024;          // +1024 alignment slack
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;                         // 2 x BN fp32: this / next tile's bias slice
+  static constexpr int EPI_OFFSET = BIAS_OFFSET + 2 * BN * 4;                  // 8 warps x 2 x 4 KB epilogue staging tiles
+  static constexpr int TOTAL = EPI_OFFSET + 8 * 2 * EPI_STAGE_BYTES;
 };
 
 // Drain columns [c_begin, c_end) of one accumulator row (this thread's TMEM lane) through the fused epilogue.
@@ -126,55 +127,87 @@ __device__ __forceinline__ void epilogue_columns(const GemmTcParams& p, uint32_t
   }
 }
 
-// bf16 epilogue with coalesced global traffic.  A thread owns one accumulator ROW (its TMEM lane), so direct 16-byte
-// accesses from a warp touch 32 different 128-byte lines per instruction.  Instead each warp moves 64-column blocks
-// through a private 4 KB shared-memory tile [32 rows x 128 B] (16-byte chunks XOR-swizzled by row, conflict-free in
-// both directions): residual / mask rows are loaded 4 full lines per instruction, consumed row-wise, the packed bf16
-// results are written row-wise and leave as 4 full 128-byte lines per instruction.
+// ------------------------------------------------------------------------------------------------
+// Staged epilogues.  A thread owns one accumulator ROW (its TMEM lane), so direct 16-byte accesses from a warp touch 32
+// different 128-byte lines per instruction.  Instead every warp moves column blocks through private 4 KB shared-memory
+// tiles [32 rows x 128 B] (16-byte chunks XOR-swizzled by row, conflict-free row-wise and line-wise):
+//   * the residual / ReLU-mask block is PREFETCHED with cp.async (4 full lines per instruction, no registers) one block
+//     ahead -- the first one before the accumulator is even complete -- so its latency never sits on the critical path;
+//   * the bias slice of the tile sits in shared memory (loaded once per tile by the epilogue warps, read as broadcasts);
+//   * results are written row-wise into the tile and leave as full 128-byte lines (bf16 / fp32 stores, or vector REDs
+//     for the fp32 split-K accumulation of weight gradients).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void red_add_v4(float* dst, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
-__device__ __forceinline__ void epilogue_columns_staged(const GemmTcParams& p, uint8_t* stage, uint32_t t_row, long long row0, int lane,
-                                                        int n_base, int c_begin, int c_end, bool relu) {
+// Prefetch the 32 x 64 aux (residual, else mask) block at (row0, col0) into `stage`; always commits one (maybe empty) group.
+__device__ __forceinline__ void epi_issue_aux(const GemmTcParams& p, uint8_t* stage, long long row0, int col0, int lane) {
+  const bf16* aux = p.residual ? p.residual : p.mask;
+  if (aux && col0 + 64 <= p.N) {
+    const long long ldaux = p.residual ? p.ldr : p.ldm;
+    const int crow = lane >> 3, cchunk = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + crow;
+      if (row0 + r < p.M) cp_async16(stage + sw128_offset(r, cchunk), aux + (row0 + r) * ldaux + col0 + cchunk * 8);
+    }
+  }
+  cp_async_commit();
+}
+
+// bf16 output.  `stage`: this warp's two 4 KB tiles; `bias_s`: the tile's bias slice starting at this warp's first column;
+// columns [col_base, col_base + NCOLS) of rows [row0, row0 + 32).  Block 0's aux prefetch was issued by the caller.
+template <int NCOLS>
+__device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, uint8_t* stage, const float* bias_s, uint32_t t_row, long long row0,
+                                                   int lane, int n_base, int c_begin, bool relu) {
+  constexpr int NBLK = NCOLS / 64;
   const long long row = row0 + lane;
   const int crow = lane >> 3, cchunk = lane & 7;             // coalesced phase: 4 rows x 8 chunks per instruction
+  const bool has_aux = p.residual || p.mask;
 #pragma unroll 1
-  for (int c0 = c_begin; c0 < c_end; c0 += 64) {
+  for (int blk = 0; blk < NBLK; ++blk) {
+    const int c0 = c_begin + blk * 64;
     const int col0 = n_base + c0;
-    if (col0 >= p.N) break;                                  // warp-uniform
-    if (col0 + 64 > p.N) {                                   // ragged right edge: direct path
+    uint8_t* st = stage + (blk & 1) * EPI_STAGE_BYTES;
+    if (blk + 1 < NBLK) {
+      epi_issue_aux(p, stage + ((blk + 1) & 1) * EPI_STAGE_BYTES, row0, col0 + 64, lane);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+    if (col0 >= p.N) continue;                                // warp-uniform
+    if (col0 + 64 > p.N) {                                    // ragged right edge: direct path
       epilogue_columns(p, t_row, row, row < p.M, n_base, c0, c0 + 64, false, false, relu);
       continue;
     }
-    const bf16* aux = p.residual ? p.residual : p.mask;      // tile staged through smem (the other one, if any, is read directly)
-    const long long ldaux = p.residual ? p.ldr : p.ldm;
-    if (aux) {
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + crow;
-        if (row0 + r < p.M)
-          *reinterpret_cast<uint4*>(stage + sw128_offset(r, cchunk)) = *reinterpret_cast<const uint4*>(aux + (row0 + r) * ldaux + col0 + cchunk * 8);
-      }
-      __syncwarp();
-    }
+    uint32_t r[2][32];
+    tmem_ld32(t_row + c0, r[0]);
+    tmem_ld32(t_row + c0 + 32, r[1]);
+    tmem_ld_wait();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      uint32_t r[32];
-      tmem_ld32(t_row + c0 + h * 32, r);
-      tmem_ld_wait();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const int col = col0 + h * 32 + g * 8;
         float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * p.alpha;
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[h][g * 8 + j]) * p.alpha;
         if (p.bias) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + blk * 64 + h * 32 + g * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias_s + blk * 64 + h * 32 + g * 8 + 4);
           v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
           v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
         }
-        uint8_t* cell = stage + sw128_offset(lane, h * 4 + g);
+        uint8_t* cell = st + sw128_offset(lane, h * 4 + g);
         float f[8];
-        if (aux) { Vec16<bf16> av; av.raw = *reinterpret_cast<const uint4*>(cell); av.unpack(f); }
+        if (has_aux) { Vec16<bf16> av; av.raw = *reinterpret_cast<const uint4*>(cell); av.unpack(f); }
         if (p.residual) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] += f[j];
@@ -185,7 +218,7 @@ __device__ __forceinline__ void epilogue_columns_staged(const GemmTcParams& p, u
         }
         if (p.mask) {
           if (p.residual) {                                  // both present: the mask comes straight from global
-            if (row < p.M) { Vec16<bf16> mv; mv.load(p.mask + row * p.ldm + col); mv.unpack(f); }
+            if (row < p.M) { Vec16<bf16> mv; mv.load(p.mask + row * p.ldm + col0 + h * 32 + g * 8); mv.unpack(f); }
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = f[j] > 0.f ? v[j] : 0.f;
@@ -195,15 +228,81 @@ __device__ __forceinline__ void epilogue_columns_staged(const GemmTcParams& p, u
       }
     }
     __syncwarp();
-    bf16* cbase = reinterpret_cast<bf16*>(p.C);
+    bf16* cbase = reinterpret_cast<bf16*>(p.C) + row0 * p.ldc + col0 + cchunk * 8;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
-      const int r = it * 4 + crow;
-      if (row0 + r < p.M)
-        *reinterpret_cast<uint4*>(cbase + (row0 + r) * p.ldc + col0 + cchunk * 8) = *reinterpret_cast<const uint4*>(stage + sw128_offset(r, cchunk));
+      const int rr = it * 4 + crow;
+      if (row0 + rr < p.M) *reinterpret_cast<uint4*>(cbase + (long long)rr * p.ldc) = *reinterpret_cast<const uint4*>(st + sw128_offset(rr, cchunk));
     }
     __syncwarp();
   }
+}
+
+// fp32 output (plain store or split-K accumulation with vector REDs), 32-column blocks through one 4 KB tile.
+template <int NCOLS>
+__device__ __forceinline__ void epilogue_tile_f32(const GemmTcParams& p, uint8_t* stage, const float* bias_s, uint32_t t_row, long long row0,
+                                                  int lane, int n_base, int c_begin, bool accum, bool relu) {
+  const long long row = row0 + lane;
+  const int crow = lane >> 3, cchunk = lane & 7;
+#pragma unroll 1
+  for (int cb = 0; cb < NCOLS; cb += 32) {
+    const int c0 = c_begin + cb;
+    const int col0 = n_base + c0;
+    if (col0 >= p.N) break;                                   // warp-uniform
+    if (col0 + 32 > p.N || p.residual || p.mask) {            // ragged edge / rare fp32 + aux combination: direct path
+      epilogue_columns(p, t_row, row, row < p.M, n_base, c0, c0 + 32, true, accum, relu);
+      continue;
+    }
+    uint32_t r[32];
+    tmem_ld32(t_row + c0, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float4 v = make_float4(__uint_as_float(r[q * 4]) * p.alpha, __uint_as_float(r[q * 4 + 1]) * p.alpha, __uint_as_float(r[q * 4 + 2]) * p.alpha,
+                             __uint_as_float(r[q * 4 + 3]) * p.alpha);
+      if (p.bias) {
+        const float4 b = *reinterpret_cast<const float4*>(bias_s + cb + q * 4);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      }
+      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      *reinterpret_cast<float4*>(stage + sw128_offset(lane, q)) = v;
+    }
+    __syncwarp();
+    float* cbase = reinterpret_cast<float*>(p.C) + row0 * p.ldc + col0 + cchunk * 4;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + crow;
+      if (row0 + rr < p.M) {
+        const float4 v = *reinterpret_cast<const float4*>(stage + sw128_offset(rr, cchunk));
+        if (accum) red_add_v4(cbase + (long long)rr * p.ldc, v);
+        else *reinterpret_cast<float4*>(cbase + (long long)rr * p.ldc) = v;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// One tile's epilogue for one warp: bias slice -> smem (all 8 epilogue warps, named barrier 1), first aux prefetch, wait for
+// the accumulator, drain this warp's 32 rows x BN/2 columns.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* stage, float* bias_tile, uint64_t* full_bar, uint32_t full_phase,
+                                              uint32_t t_row, long long row0, int lane, int et, int n_base, int col_half) {
+  const bool out_f32 = (p.flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) != 0;
+  const bool accum = (p.flags & B200F_EPI_ACCUM) != 0;
+  const bool relu = (p.flags & B200F_EPI_RELU) != 0;
+  const int c_begin = col_half * (BN / 2);
+  if (p.bias && et < BN) bias_tile[et] = (n_base + et < p.N) ? __ldg(p.bias + n_base + et) : 0.f;
+  const bool staged16 = !out_f32 && p.vec_ok;
+  if (staged16) epi_issue_aux(p, stage, row0, n_base + c_begin, lane);
+  asm volatile("bar.sync 1, 256;" ::: "memory");             // bias slice visible to all epilogue warps
+  mbar_wait(full_bar, full_phase);
+  tc_fence_after();
+  if (staged16)
+    epilogue_tile_bf16<BN / 2>(p, stage, bias_tile + c_begin, t_row, row0, lane, n_base, c_begin, relu);
+  else if (out_f32 && p.vec_ok)
+    epilogue_tile_f32<BN / 2>(p, stage, bias_tile + c_begin, t_row, row0, lane, n_base, c_begin, accum, relu);
+  else
+    epilogue_columns(p, t_row, row0 + lane, row0 + lane < p.M, n_base, c_begin, c_begin + BN / 2, out_f32, accum, relu);
 }
 
 template <int BN, int STAGES, int A_MN, int B_MN>
@@ -211,8 +310,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmTcParams p) {
   using S = GemmSmem<BN, STAGES>;
   constexpr int TMEM_COLS = 2 * BN;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];          // SWIZZLE_128B tiles need a 1024-byte aligned base (checked below)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
@@ -223,6 +321,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int i = 0; i < STAGES; ++i) {
@@ -311,25 +410,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else {
     const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are the ones this warp may touch
     const int col_half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
-    const bool out_f32 = (p.flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) != 0;
-    const bool accum = (p.flags & B200F_EPI_ACCUM) != 0;
-    const bool relu = (p.flags & B200F_EPI_RELU) != 0;
+    uint8_t* stage = smem + S::EPI_OFFSET + (warp - 2) * 2 * EPI_STAGE_BYTES;
+    float* bias_s = reinterpret_cast<float*>(smem + S::BIAS_OFFSET);
     int it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
       const int n_blk = u % p.num_n;
       const int m_blk = (u / p.num_n) % p.num_m;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const long long row = (long long)m_blk * BM + lane_grp * 32 + lane;
-      const bool row_ok = row < p.M;
+      const long long row0 = (long long)m_blk * BM + lane_grp * 32;
       const uint32_t t_row = tmem_base + (uint32_t(lane_grp * 32) << 16) + acc * BN;
-      if (!out_f32 && p.vec_ok)
-        epilogue_columns_staged(p, smem + S::EPI_OFFSET + (warp - 2) * EPI_STAGE_BYTES, t_row, row - lane, lane, n_blk * BN,
-                                col_half * (BN / 2), (col_half + 1) * (BN / 2), relu);
-      else
-        epilogue_columns(p, t_row, row, row_ok, n_blk * BN, col_half * (BN / 2), (col_half + 1) * (BN / 2), out_f32, accum, relu);
+      epilogue_tile<BN>(p, stage, bias_s + acc * BN, &tmem_full[acc], acc_phase, t_row, row0, lane, threadIdx.x - 64, n_blk * BN, col_half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -356,8 +447,10 @@ struct PairSmem {
   static constexpr int B_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int EPI_OFFSET = BAR_OFFSET + 256;
-  static constexpr int TOTAL = EPI_OFFSET + 8 * EPI_STAGE_BYTES + 1024;
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;
+  static constexpr int EPI_OFFSET = BIAS_OFFSET + 2 * BN * 4;
+  static constexpr int TOTAL = EPI_OFFSET + 8 * 2 * EPI_STAGE_BYTES;
+  static_assert(TOTAL <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 };
 
 template <int BN, int STAGES, int A_MN, int B_MN>
@@ -366,8 +459,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   using S = PairSmem<BN, STAGES>;
   constexpr int TMEM_COLS = 2 * BN;
   constexpr int HALF_N = BN / 2;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];          // SWIZZLE_128B tiles need a 1024-byte aligned base (checked below)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
@@ -382,6 +474,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int num_clusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int i = 0; i < STAGES; ++i) {
@@ -473,25 +566,17 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else {
     const int lane_grp = warp & 3;
     const int col_half = (warp - 2) >> 2;
-    const bool out_f32 = (p.flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) != 0;
-    const bool accum = (p.flags & B200F_EPI_ACCUM) != 0;
-    const bool relu = (p.flags & B200F_EPI_RELU) != 0;
+    uint8_t* stage = smem + S::EPI_OFFSET + (warp - 2) * 2 * EPI_STAGE_BYTES;
+    float* bias_s = reinterpret_cast<float*>(smem + S::BIAS_OFFSET);
     int it = 0;
     for (int u = cluster_id; u < units; u += num_clusters, ++it) {
       const int n_blk = u % p.num_n;
       const int m_blk = (u / p.num_n) % p.num_m;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const long long row = (long long)m_blk * 2 * BM + (long long)rank * BM + lane_grp * 32 + lane;
-      const bool row_ok = row < p.M;
+      const long long row0 = (long long)m_blk * 2 * BM + (long long)rank * BM + lane_grp * 32;
       const uint32_t t_row = tmem_base + (uint32_t(lane_grp * 32) << 16) + acc * BN;
-      if (!out_f32 && p.vec_ok)
-        epilogue_columns_staged(p, smem + S::EPI_OFFSET + (warp - 2) * EPI_STAGE_BYTES, t_row, row - lane, lane, n_blk * BN,
-                                col_half * (BN / 2), (col_half + 1) * (BN / 2), relu);
-      else
-        epilogue_columns(p, t_row, row, row_ok, n_blk * BN, col_half * (BN / 2), (col_half + 1) * (BN / 2), out_f32, accum, relu);
+      epilogue_tile<BN>(p, stage, bias_s + acc * BN, &tmem_full[acc], acc_phase, t_row, row0, lane, threadIdx.x - 64, n_blk * BN, col_half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
@@ -627,23 +712,23 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
     const int clusters = units < num_sms() / 2 ? units : num_sms() / 2;
     const int pkey = (a.a_layout ? 2 : 0) | (a.b_layout ? 1 : 0);
     switch (pkey) {
-      case 0: return launch_pair<256, 6, 0, 0>(ta, tb, p, 2 * clusters, st);
-      case 1: return launch_pair<256, 6, 0, 1>(ta, tb, p, 2 * clusters, st);
-      case 2: return launch_pair<256, 6, 1, 0>(ta, tb, p, 2 * clusters, st);
-      default: return launch_pair<256, 6, 1, 1>(ta, tb, p, 2 * clusters, st);
+      case 0: return launch_pair<256, 5, 0, 0>(ta, tb, p, 2 * clusters, st);
+      case 1: return launch_pair<256, 5, 0, 1>(ta, tb, p, 2 * clusters, st);
+      case 2: return launch_pair<256, 5, 1, 0>(ta, tb, p, 2 * clusters, st);
+      default: return launch_pair<256, 5, 1, 1>(ta, tb, p, 2 * clusters, st);
     }
   }
   const int grid = units < num_sms() ? units : num_sms();
   const int key = (BN == 256 ? 4 : 0) | (a.a_layout ? 2 : 0) | (a.b_layout ? 1 : 0);
   switch (key) {
-    case 0: return launch_cfg<128, 6, 0, 0>(ta, tb, p, grid, st);
-    case 1: return launch_cfg<128, 6, 0, 1>(ta, tb, p, grid, st);
-    case 2: return launch_cfg<128, 6, 1, 0>(ta, tb, p, grid, st);
-    case 3: return launch_cfg<128, 6, 1, 1>(ta, tb, p, grid, st);
-    case 4: return launch_cfg<256, 4, 0, 0>(ta, tb, p, grid, st);
-    case 5: return launch_cfg<256, 4, 0, 1>(ta, tb, p, grid, st);
-    case 6: return launch_cfg<256, 4, 1, 0>(ta, tb, p, grid, st);
-    default: return launch_cfg<256, 4, 1, 1>(ta, tb, p, grid, st);
+    case 0: return launch_cfg<128, 4, 0, 0>(ta, tb, p, grid, st);
+    case 1: return launch_cfg<128, 4, 0, 1>(ta, tb, p, grid, st);
+    case 2: return launch_cfg<128, 4, 1, 0>(ta, tb, p, grid, st);
+    case 3: return launch_cfg<128, 4, 1, 1>(ta, tb, p, grid, st);
+    case 4: return launch_cfg<256, 3, 0, 0>(ta, tb, p, grid, st);
+    case 5: return launch_cfg<256, 3, 0, 1>(ta, tb, p, grid, st);
+    case 6: return launch_cfg<256, 3, 1, 0>(ta, tb, p, grid, st);
+    default: return launch_cfg<256, 3, 1, 1>(ta, tb, p, grid, st);
   }
 }
 

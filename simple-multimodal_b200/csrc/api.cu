@@ -36,6 +36,7 @@ int gemm_bf16_simt(const b200f_gemm_args& a, cudaStream_t st);
 bool gemm_tc_eligible(const b200f_gemm_args& a);
 extern uint32_t g_dbg_mn_lbo, g_dbg_mn_sbo, g_dbg_mn_kadv;
 extern bool g_dbg_disable_pair;
+extern int g_attn_fwd_variant;
 
 }  // namespace b200f
 
@@ -70,6 +71,7 @@ int b200f_debug_set(int key, unsigned value) {
     case 1: b200f::g_dbg_mn_sbo = value; break;
     case 2: b200f::g_dbg_mn_kadv = value; break;
     case 3: b200f::g_dbg_disable_pair = value != 0; break;
+    case 4: b200f::g_attn_fwd_variant = int(value); break;
     default: return b200f::fail(B200F_ERR_UNSUPPORTED, "unknown debug key %d", key);
   }
   return B200F_OK;

@@ -26,6 +26,7 @@ static constexpr int HD = 64;    // head dim
 static constexpr float LOG2E = 1.4426950408889634f;
 
 int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+int g_attn_fwd_variant = 0;      // 0 = by shape, 1 = one 128-query tile per CTA, 2 = persistent two-tile kernel (A-B)
 
 struct AttnTcParams {
   int B, H, Lq, Lk;
@@ -252,6 +253,253 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 1) tmem_dealloc<256>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------
+// forward v2 (default): persistent, one CTA per SM, TWO 128-query tiles in flight.
+//   warp 0      TMA producer : Q tiles of the next work item, 3-deep ring of {K,V} tiles
+//   warp 1      MMA issuer   : per key tile j and query tile t:  PV_t(j), then S_t(j+1) -- so while warpgroup t runs the
+//                              softmax of S_t(j+1) the tensor pipe works on the other tile, and the two warpgroups keep
+//                              the MUFU pipe (the real bound at head dim 64: one exp per 256 MMA FLOPs) continuously busy
+//   warps 2-5   softmax warpgroup 0 (query rows 0..127 of the item),  warps 6-9  warpgroup 1 (rows 128..255)
+// TMEM: S_0 [0,128) S_1 [128,256) O_0 [256,320) O_1 [320,384).  A work item = (batch, head, 256-query block).
+// ------------------------------------------------------------------------------------------------
+static constexpr int F2_THREADS = 320;
+static constexpr int F2_ST = 3;      // K/V ring depth
+struct Fwd2Smem {
+  static constexpr int Q_OFF = 0;                              // 2 x [128 x 64] bf16, K-major SW128
+  static constexpr int K_OFF = Q_OFF + 2 * TQ * HD * 2;        // F2_ST x [128 keys x 64]
+  static constexpr int V_OFF = K_OFF + F2_ST * TK * HD * 2;    // F2_ST x [128 keys x 64 d] (MN-major B operand)
+  static constexpr int P_OFF = V_OFF + F2_ST * TK * HD * 2;    // 2 x [128 x 128] bf16, each two K-major SW128 halves of 64 keys
+  static constexpr int BAR_OFF = P_OFF + 2 * TQ * TK * 2;
+  static constexpr int TOTAL = BAR_OFF + 256;
+};
+
+__global__ void __launch_bounds__(F2_THREADS, 1)
+attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                    const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p, const int n_qblk, const int n_items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Fwd2Smem::BAR_OFF);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;               // [F2_ST]
+  uint64_t* kv_empty = kv_full + F2_ST;       // [F2_ST]
+  uint64_t* s_full = kv_empty + F2_ST;        // [2]  S_t(j) complete (and every earlier MMA, incl. PV_t(j-1))
+  uint64_t* p_ready = s_full + 2;             // [2]  P_t(j) in smem, S_t(j) consumed, O_t rescaled
+  uint64_t* o_full = p_ready + 2;             // [2]  last PV_t of the item complete
+  uint64_t* o_empty = o_full + 2;             // [2]  epilogue has read O_t
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (p.Lk + TK - 1) / TK;
+
+  if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int i = 0; i < F2_ST; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_ready[t], 4); mbar_init(&o_full[t], 1); mbar_init(&o_empty[t], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t g = 0, it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int qb = item % n_qblk, h = (item / n_qblk) % p.H, b = item / (n_qblk * p.H);
+        const int q0 = qb * 2 * TQ;
+        const bool two = q0 + TQ < p.Lq;
+        mbar_wait(q_empty, (it & 1) ^ 1);
+        mbar_expect_tx(q_full, (two ? 2 : 1) * TQ * HD * 2);
+        tma_load_4d(smem + Fwd2Smem::Q_OFF, &tm_q, q_full, 0, h, q0, b);
+        if (two) tma_load_4d(smem + Fwd2Smem::Q_OFF + TQ * HD * 2, &tm_q, q_full, 0, h, q0 + TQ, b);
+        for (int j = 0; j < n_tiles; ++j, ++g) {
+          const int st = g % F2_ST;
+          mbar_wait(&kv_empty[st], ((g / F2_ST) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[st], 2 * TK * HD * 2);
+          tma_load_4d(smem + Fwd2Smem::K_OFF + st * TK * HD * 2, &tm_k, &kv_full[st], 0, h, j * TK, b);
+          tma_load_4d(smem + Fwd2Smem::V_OFF + st * TK * HD * 2, &tm_v, &kv_full[st], 0, h, j * TK, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, TK, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(TQ, HD, 0, 1);
+      uint32_t g = 0, it = 0, pr_cnt[2] = {0, 0}, o_cnt[2] = {0, 0};
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int qb = item % n_qblk;
+        const int nt = (qb * 2 * TQ + TQ < p.Lq) ? 2 : 1;
+        mbar_wait(q_full, it & 1);
+        {
+          const int st = g % F2_ST;
+          mbar_wait(&kv_full[st], (g / F2_ST) & 1);
+          tc_fence_after();
+          const uint32_t sk = smem_u32(smem + Fwd2Smem::K_OFF + st * TK * HD * 2);
+          for (int t = 0; t < nt; ++t) {
+            const uint32_t sq = smem_u32(smem + Fwd2Smem::Q_OFF + t * TQ * HD * 2);
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k)
+              umma_ss(tmem_base + t * TK, umma_desc(sq + k * 32, 16, 1024), umma_desc(sk + k * 32, 16, 1024), idesc_s, k > 0);
+            umma_commit(&s_full[t]);
+          }
+          if (n_tiles == 1) umma_commit(q_empty);
+        }
+        for (int j = 0; j < n_tiles; ++j) {
+          const int st = (g + j) % F2_ST;
+          const uint32_t sv = smem_u32(smem + Fwd2Smem::V_OFF + st * TK * HD * 2);
+          uint32_t sk_next = 0;
+          if (j + 1 < n_tiles) {
+            const int stn = (g + j + 1) % F2_ST;
+            mbar_wait(&kv_full[stn], ((g + j + 1) / F2_ST) & 1);
+            sk_next = smem_u32(smem + Fwd2Smem::K_OFF + stn * TK * HD * 2);
+          }
+          const int ksteps = (min(TK, p.Lk - j * TK) + 15) >> 4;   // P columns past ceil32(valid) are never written
+          for (int t = 0; t < nt; ++t) {
+            mbar_wait(&p_ready[t], pr_cnt[t] & 1);
+            ++pr_cnt[t];
+            if (j == 0) mbar_wait(&o_empty[t], (o_cnt[t] & 1) ^ 1);   // the previous item's epilogue has drained O_t
+            tc_fence_after();
+            const uint32_t sp = smem_u32(smem + Fwd2Smem::P_OFF + t * TQ * TK * 2);
+            const uint32_t t_o = tmem_base + 2 * TK + t * HD;
+            for (int k = 0; k < ksteps; ++k)
+              umma_ss(t_o, umma_desc(sp + (k >> 2) * (TQ * 128) + (k & 3) * 32, 16, 1024), umma_desc(sv + k * 2048, TK * 128, 1024), idesc_o,
+                      (j > 0 || k > 0) ? 1u : 0u);
+            if (j + 1 < n_tiles) {
+              const uint32_t sq = smem_u32(smem + Fwd2Smem::Q_OFF + t * TQ * HD * 2);
+#pragma unroll
+              for (int k = 0; k < HD / 16; ++k)
+                umma_ss(tmem_base + t * TK, umma_desc(sq + k * 32, 16, 1024), umma_desc(sk_next + k * 32, 16, 1024), idesc_s, k > 0);
+              umma_commit(&s_full[t]);
+            } else {
+              umma_commit(&o_full[t]);
+              ++o_cnt[t];
+            }
+          }
+          umma_commit(&kv_empty[st]);
+          if (j + 2 == n_tiles) umma_commit(q_empty);
+        }
+        g += n_tiles;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int t = (warp - 2) >> 2;                   // query tile / warpgroup
+    const int grp = warp & 3;                        // TMEM lane group this warp may touch
+    const int row = grp * 32 + lane;                 // row of the tile == TMEM lane
+    const uint32_t lane_addr = uint32_t(grp * 32) << 16;
+    const uint32_t t_s = tmem_base + t * TK, t_o = tmem_base + 2 * TK + t * HD;
+    const float c = p.scale * LOG2E;
+    const uint64_t c2 = f2_pack(c, c);
+    uint8_t* prow = smem + Fwd2Smem::P_OFF + t * TQ * TK * 2;
+    uint32_t sf_cnt = 0, o_cnt = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int qb = item % n_qblk, h = (item / n_qblk) % p.H, b = item / (n_qblk * p.H);
+      const int q0 = qb * 2 * TQ + t * TQ;
+      if (q0 >= p.Lq) continue;                      // this warpgroup's tile does not exist (the MMA warp skips it too)
+      float m = -INFINITY, l = 0.f;                  // m: reference max the stored P / O are scaled against (raw score units)
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(&s_full[t], sf_cnt & 1);           // also implies PV_t(j-1) retired: O_t and the P_t tile are ours again
+        ++sf_cnt;
+        tc_fence_after();
+        const int valid = min(TK, p.Lk - j * TK);    // keys beyond Lk were zero-filled by TMA: mask them
+        const int cols = (valid + 31) & ~31;
+        const bool ragged = valid < cols;
+        float tmax = -INFINITY, tmax_b = -INFINITY;
+#pragma unroll 1
+        for (int cc = 0; cc < cols; cc += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_s + lane_addr + cc, r);
+          tmem_ld_wait();
+          if (ragged && cc + 32 > valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (cc + i >= valid) r[i] = 0xff800000u;   // -inf
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            tmax = fmax3(tmax, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+            tmax_b = fmax3(tmax_b, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+          }
+        }
+        const float m_new = fmax3(m, tmax, tmax_b);
+        // lazy rescale: move the reference max only when it would grow by more than 2^8, so P <= 2^8 (exact after the final O / l)
+        const bool grow = (m_new - m) * c > 8.f;     // first tile: m = -inf -> true
+        const float m_use = grow ? m_new : m;
+        const float alpha = grow ? ex2_approx((m - m_use) * c) : 1.f;   // first tile: 0
+        const float nmc = -m_use * c;
+        const uint64_t nmc2 = f2_pack(nmc, nmc);
+        uint64_t lsum2 = 0ull;
+#pragma unroll 1
+        for (int cc = 0; cc < cols; cc += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_s + lane_addr + cc, r);
+          tmem_ld_wait();
+          if (ragged && cc + 32 > valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (cc + i >= valid) r[i] = 0xff800000u;   // ex2(-inf) = 0
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float x0, x1;
+            f2_unpack(f2_fma(f2_pack_u(r[i], r[i + 1]), c2, nmc2), x0, x1);
+            const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+            lsum2 = f2_add(lsum2, f2_pack(e0, e1));
+            pk[i >> 1] = pack_bf16(e0, e1);
+          }
+          uint8_t* half = prow + (cc >> 6) * (TQ * 128);   // 32 keys = four 16-byte chunks of this row inside the 64-key half
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const uint32_t chunk = ((cc & 63) >> 3) + q4;
+            *reinterpret_cast<uint4*>(half + sw128_offset(row, chunk)) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+          }
+        }
+        float ls0, ls1;
+        f2_unpack(lsum2, ls0, ls1);
+        l = l * alpha + (ls0 + ls1);
+        m = m_use;
+        if (j > 0 && __any_sync(0xffffffffu, grow)) {  // O was accumulated against the old reference max: rescale it in TMEM
+#pragma unroll
+          for (int cc = 0; cc < HD; cc += 16) {
+            uint32_t r[16];
+            tmem_ld16(t_o + lane_addr + cc, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st16(t_o + lane_addr + cc, r);
+          }
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();                      // P (generic-proxy stores) -> visible to the UMMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[t]);
+      }
+      mbar_wait(&o_full[t], o_cnt & 1);
+      ++o_cnt;
+      tc_fence_after();
+      const int qrow = q0 + row;
+      if (qrow < p.Lq) p.LSE[((long long)b * p.H + h) * p.Lq + qrow] = m * p.scale + logf(l);
+      // O / l -> bf16 -> this warp's 32 x 128 B slice of the (now free) P_t tile -> full 128-byte lines to global
+      store_rows64(t_o + lane_addr, prow + grp * (32 * 128), p.O + ((long long)b * p.Lq + q0 + grp * 32) * p.ldo + h * HD, p.ldo,
+                   p.Lq - (q0 + grp * 32), lane, 1.f / l);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[t]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 // 4-D view (d, head, token, batch) of a token-major [B, L, ld] tensor slice; box = 64 x 1 x rows x 1
 static int make_head_tmap(CUtensorMap* m, const void* base, long long ld, int B, int H, int L, int rows) {
   uint64_t dims[4] = {uint64_t(HD), uint64_t(H), uint64_t(L), uint64_t(B)};
@@ -281,11 +529,22 @@ int attn_fwd_tc(const b200f_attn_args& a, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
+    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::TOTAL));
     configured = true;
   }
-  dim3 grid((a.Lq + TQ - 1) / TQ, a.H, a.B);
-  attn_fwd_tc_kernel<<<grid, ATT_THREADS, FwdSmem::TOTAL, st>>>(tq, tk, tv, p);
-  return check_launch("attn_fwd_tc_kernel");
+  // a single 128-query tile per (batch, head) leaves the second softmax warpgroup of the two-tile kernel idle: use the
+  // one-tile-per-CTA kernel there (measured Lq=30, Lk=512: 0.094 ms vs 0.122 ms).  b200f_debug_set(4, 1|2) forces either.
+  if (g_attn_fwd_variant == 1 || (g_attn_fwd_variant == 0 && a.Lq <= TQ)) {
+    dim3 grid((a.Lq + TQ - 1) / TQ, a.H, a.B);
+    attn_fwd_tc_kernel<<<grid, ATT_THREADS, FwdSmem::TOTAL, st>>>(tq, tk, tv, p);
+    return check_launch("attn_fwd_tc_kernel");
+  }
+  const int n_qblk = (a.Lq + 2 * TQ - 1) / (2 * TQ);
+  const long long n_items = (long long)n_qblk * a.H * a.B;
+  B200F_REQUIRE(n_items < (1ll << 31), B200F_ERR_SHAPE, "attention(tcgen05): too many work items");
+  const int grid = int(n_items < num_sms() ? n_items : num_sms());
+  attn_fwd_tc2_kernel<<<grid, F2_THREADS, Fwd2Smem::TOTAL, st>>>(tq, tk, tv, p, n_qblk, int(n_items));
+  return check_launch("attn_fwd_tc2_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------

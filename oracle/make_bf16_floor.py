@@ -53,6 +53,8 @@ def rel(x, r):
 def main():
     floors = {}
     for cid, c in CASES.items():
+        if c.get("fp32_only"):
+            continue
         kind = c["kind"]
         cfgkw = dict(H=512, heads=8, graph_hidden=512, graph_layers=3)
         cfgkw.update(c["cfg"])

@@ -49,10 +49,33 @@ class AttnArgs(C.Structure):
 
 _lib = None
 
+# Optional live per-entry-point profile (tools/step_profile.py): when CALL_PROFILE is a list, every compute entry point is
+# bracketed by CUDA events on the launching stream and (name, start, stop) is appended.  Off (None) in normal use.
+CALL_PROFILE = None
+_NOT_KERNELS = ("b200f_last_error", "b200f_launch_count", "b200f_infonce_workspace_bytes", "b200f_version", "b200f_debug_set")
 
-def lib() -> C.CDLL:
+
+class _ProfiledLib:
+    def __getattr__(self, name):
+        fn = getattr(_lib, name)
+        if name in _NOT_KERNELS:
+            return fn
+
+        def call(*args):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            CALL_PROFILE.append((name, e0, e1))
+            return rc
+        return call
+
+
+def lib():
     """Load the shared library (once).  Raises if it has not been built."""
     global _lib
+    if _lib is not None:
+        return _lib if CALL_PROFILE is None else _ProfiledLib()
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise B200FusionError(
@@ -62,7 +85,7 @@ def lib() -> C.CDLL:
         _lib.b200f_last_error.restype = C.c_char_p
         _lib.b200f_launch_count.restype = C.c_ulonglong
         _lib.b200f_infonce_workspace_bytes.restype = C.c_size_t
-    return _lib
+    return _lib if CALL_PROFILE is None else _ProfiledLib()
 
 
 def check(rc: int, what: str) -> None:

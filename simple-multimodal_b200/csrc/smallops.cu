@@ -244,7 +244,10 @@ __global__ void __launch_bounds__(128) tok3_fwd_kernel(const T* __restrict__ qkv
   const int nvec = H / VN;
   float wsum[3][3] = {};
   for (int v0 = 0; v0 < nvec; v0 += 32) {
-    const int vi = v0 + lane;          // nvec is a multiple of 32 (checked on the host)
+    // lanes past the row (H/VN not a multiple of 32) idle through the loads/stores but still take part in the
+    // shuffles; head groups (LPH lanes) never straddle the boundary because nvec = heads * LPH
+    const bool live = v0 + lane < nvec;
+    const int vi = live ? v0 + lane : 0;
     const int head = vi / LPH;
     float q[3][VN], k[3][VN], vv[3][VN];
 #pragma unroll
@@ -269,13 +272,14 @@ __global__ void __launch_bounds__(128) tok3_fwd_kernel(const T* __restrict__ qkv
 #pragma unroll
       for (int j = 0; j < 3; ++j) { p[i][j] = expf(p[i][j] - mx); sum += p[i][j]; }
 #pragma unroll
-      for (int j = 0; j < 3; ++j) { p[i][j] /= sum; if (lane % LPH == 0) wsum[i][j] += p[i][j]; }
+      for (int j = 0; j < 3; ++j) { p[i][j] /= sum; if (live && lane % LPH == 0) wsum[i][j] += p[i][j]; }
       float o[VN];
 #pragma unroll
       for (int e = 0; e < VN; ++e) o[e] = p[i][0] * vv[0][e] + p[i][1] * vv[1][e] + p[i][2] * vv[2][e];
-      Vec16<T> ov; ov.pack(o); ov.store(ctx + (b * 3 + i) * H + vi * VN);
+      Vec16<T> ov; ov.pack(o);
+      if (live) ov.store(ctx + (b * 3 + i) * H + vi * VN);
     }
-    if (lane % LPH == 0) {
+    if (live && lane % LPH == 0) {
       float* po = probs + (b * heads + head) * 9;
 #pragma unroll
       for (int i = 0; i < 3; ++i)
@@ -304,7 +308,8 @@ __global__ void __launch_bounds__(128) tok3_bwd_kernel(const T* __restrict__ dct
   T* dbase = dqkv + b * 9LL * H;
   const int nvec = H / VN;
   for (int v0 = 0; v0 < nvec; v0 += 32) {
-    const int vi = v0 + lane;
+    const bool live = v0 + lane < nvec;
+    const int vi = live ? v0 + lane : 0;
     const int head = vi / LPH;
     float q[3][VN], k[3][VN], vv[3][VN], g[3][VN];
 #pragma unroll
@@ -341,7 +346,7 @@ __global__ void __launch_bounds__(128) tok3_bwd_kernel(const T* __restrict__ dct
         dv[e] = p[0][t] * g[0][e] + p[1][t] * g[1][e] + p[2][t] * g[2][e];
       }
       Vec16<T> a, c, d; a.pack(dq); c.pack(dk); d.pack(dv);
-      a.store(dbase + t * 3LL * H + vi * VN); c.store(dbase + t * 3LL * H + H + vi * VN); d.store(dbase + t * 3LL * H + 2 * H + vi * VN);
+      if (live) { a.store(dbase + t * 3LL * H + vi * VN); c.store(dbase + t * 3LL * H + H + vi * VN); d.store(dbase + t * 3LL * H + 2 * H + vi * VN); }
     }
   }
 }
@@ -523,7 +528,7 @@ int b200f_gat_bwd(const void* dout, const void* out, const void* xp, const float
   DISPATCH_DTYPE(dtype, T, {                                                                                          \
     constexpr int VN = Vec16<T>::N;                                                                                   \
     const int D = H / heads;                                                                                          \
-    B200F_REQUIRE(heads > 0 && H % heads == 0 && D % VN == 0 && (H / VN) % 32 == 0, B200F_ERR_SHAPE, "tok3: H=%d heads=%d", H, heads); \
+    B200F_REQUIRE(heads > 0 && H % heads == 0 && D % VN == 0, B200F_ERR_SHAPE, "tok3: H=%d heads=%d", H, heads); \
     const int lph = D / VN;                                                                                           \
     const unsigned grid = (unsigned)((B + 3) / 4);                                                                    \
     cudaStream_t st = static_cast<cudaStream_t>(stream);                                                              \

@@ -1,0 +1,171 @@
+"""Parity at BASELINE.json's full sizes, where the oracle cannot run the whole batch: size-independent properties plus
+oracle spot-checks of individual samples (every head but InfoNCE is per-sample independent, SURVEY 8e, so a row of the
+full-batch CUDA result must equal the oracle run on that sample alone).
+
+  * configs[1]  MulT, B=256, text 512 / audio 512 / video 30, H=512, bf16:
+      - rows {0, 101, 255} of the pooled / fused outputs against the fp64 oracle on those samples (rtol 2e-2),
+      - batch-permutation equivariance, chunk-size invariance (resident vs recomputed chunks), finite gradients,
+      - input-gradient rows of the spot samples against the oracle's (the objective is a per-sample mean).
+  * configs[2]  ContrastiveFusion + InfoNCE, B=4096, bf16: the fp64 oracle does finish at this size (the B x B logits are
+      16.8 M entries): losses within 1e-3, projections 2e-2; closed-form KATs at B=4096 (identical rows -> log B).
+  * configs[3] shape, 1 GPU: HierarchicalFusion B=4096 with modality dropout: masked modalities receive zero input
+      gradient, outputs finite, fused rows of spot samples against the oracle (fused features do not depend on InfoNCE)."""
+import math
+
+import pytest
+import torch
+
+from oracle import fusion_oracle as fo
+from parity_util import FL, Cfg, pkg, rel
+
+pytestmark = pytest.mark.gpu
+LENS = (512, 512, 30)
+H = 512
+
+
+def _bf16_exact(P):
+    return {k: v.to(torch.bfloat16).float() for k, v in P.items()}
+
+
+def _features(B, seed, device="cuda"):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return [torch.randn((B, L, H), generator=g).to(torch.bfloat16) for L in LENS]
+
+
+@pytest.fixture(scope="module")
+def mult_full():
+    B = 256
+    P = _bf16_exact(fo.init_params("mult", H=H, heads=8, seed=5))
+    host = _features(B, 77)
+    head = FL.MultimodalTransformer(Cfg()).cuda()
+    head.load_state_dict(P, strict=True)
+    head.train()
+    xs = [h.cuda().requires_grad_(True) for h in host]
+    out = head(*xs)
+    loss = (out["fused_features"].float() ** 2).sum() / (B * H)
+    loss.backward()
+    torch.cuda.synchronize()
+    return dict(B=B, P=P, host=host, head=head, out={k: v.detach() for k, v in out.items()}, dx=[x.grad for x in xs],
+                pg={k: p.grad.clone() for k, p in head.named_parameters()})
+
+
+def test_mult_b256_rows_match_oracle(mult_full):
+    m = mult_full
+    P64 = {k: v.double() for k, v in m["P"].items()}
+    for b in (0, 101, 255):
+        xs = [h[b:b + 1].double().requires_grad_(True) for h in m["host"]]
+        ref = fo.mult_fusion(*xs, P64, heads=8)
+        ((ref["fused_features"] ** 2).sum() / (m["B"] * H)).backward()
+        for k in ("fused_features", "text_features", "audio_features", "video_features"):
+            assert rel(m["out"][k][b:b + 1], ref[k]) <= 2e-2, (b, k)
+        for i, x in enumerate(xs):
+            assert rel(m["dx"][i][b:b + 1], x.grad) <= 4e-2, (b, i)       # bf16 gradient floor of MulT, see bf16_floor.json
+
+
+def test_mult_b256_gradients_finite_and_nonzero(mult_full):
+    for k, g in mult_full["pg"].items():
+        assert g is not None and torch.isfinite(g).all(), k
+        if not k.endswith("in_proj_bias"):
+            assert float(g.abs().max()) > 0, k
+    # softmax is shift-invariant in the key bias: d/d(k-bias) is exactly zero in the reference's math
+    Hh = H
+    kb = mult_full["pg"]["text_to_audio.attention.in_proj_bias"][Hh:2 * Hh]
+    vb = mult_full["pg"]["text_to_audio.attention.in_proj_bias"][2 * Hh:]
+    assert float(kb.abs().max()) <= 1e-3 * float(vb.abs().max())
+
+
+def test_mult_b256_permutation_and_chunk_invariance(mult_full):
+    m = mult_full
+    head = m["head"]
+    perm = torch.randperm(m["B"], generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        out_p = head(*[h[perm].cuda() for h in m["host"]])
+    # per-sample independence: permuting the batch permutes the rows -- bit-exact, every row runs the same instruction stream
+    assert torch.equal(out_p["fused_features"], m["out"]["fused_features"][perm.cuda()])
+    # chunking (64-sample chunks, only one resident -> the rest recomputed in backward) changes neither outputs nor gradients
+    head.chunk_size, head.stash_fraction = 64, 1e-9
+    try:
+        for p in head.parameters():
+            p.grad = None
+        xs = [h.cuda().requires_grad_(True) for h in m["host"]]
+        out = head(*xs)
+        ((out["fused_features"].float() ** 2).sum() / (m["B"] * H)).backward()
+        torch.cuda.synchronize()
+        assert torch.equal(out["fused_features"], m["out"]["fused_features"])
+        for i in range(3):
+            assert torch.equal(xs[i].grad, m["dx"][i]), i
+        for k, p in head.named_parameters():          # fp32 atomics / different split-K partitions: equal up to summation order
+            assert rel(p.grad, m["pg"][k]) <= 1e-3 or float(m["pg"][k].norm()) < 1e-6, k
+    finally:
+        head.chunk_size, head.stash_fraction = FL.MultimodalTransformer.chunk_size, FL.MultimodalTransformer.stash_fraction
+
+
+def test_contrastive_b4096_matches_oracle():
+    B = 4096
+    P = _bf16_exact(fo.init_params("contrastive", H=H, heads=8, seed=9))
+    feats = [f.to(torch.bfloat16).float() for f in fo.synthetic_features(B, (None, None, None), H=H, seed=31)]
+    head = FL.ContrastiveFusion(Cfg()).cuda()
+    head.load_state_dict(P, strict=True)
+    head.train()
+    xs = [f.cuda().to(torch.bfloat16).requires_grad_(True) for f in feats]
+    out = head(*xs, compute_contrastive_loss=True)
+    sum(out["contrastive_losses"].values()).backward()
+    torch.cuda.synchronize()
+    P64 = {k: v.double().requires_grad_(True) for k, v in P.items()}
+    x64 = [f.double().requires_grad_(True) for f in feats]
+    ref = fo.contrastive_fusion(*x64, P64, temperature=0.07, compute_contrastive_loss=True)
+    sum(ref["contrastive_losses"].values()).backward()
+    for k, v in ref["contrastive_losses"].items():
+        assert abs(float(out["contrastive_losses"][k].detach()) - float(v.detach())) <= 1e-3, k
+    for k in ("fused_features", "text_proj", "audio_proj", "video_proj"):
+        assert rel(out[k], ref[k]) <= 2e-2, k
+    for i in range(3):
+        assert rel(xs[i].grad, x64[i].grad) <= 5e-2, i       # InfoNCE gradient through bf16 logits at 1/tau = 14.3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_infonce_b4096_known_answers(dtype):
+    B, D = 4096, 256
+    ops = pkg.ops
+    z = (torch.ones(B, D) / math.sqrt(D)).to("cuda", dtype)            # 1/16: exact in bf16
+    l0, l1, l2 = ops.InfoNCE3Fn.apply(z, z, z, 0.07, None)
+    for l in (l0, l1, l2):
+        assert abs(float(l) - math.log(B)) <= (1e-5 if dtype == torch.float32 else 1e-3)
+    # one-hot rows repeating every D samples: S_ij = 1/tau when i == j (mod D), else 0
+    e = torch.eye(D).repeat(B // D, 1).to("cuda", dtype)
+    l0, _, _ = ops.InfoNCE3Fn.apply(e, e, e, 0.07, None)
+    r = B // D
+    expect = math.log(r * math.exp(1 / 0.07) + (B - r)) - 1 / 0.07
+    assert abs(float(l0) - expect) <= (1e-5 * max(1.0, expect) if dtype == torch.float32 else 1e-3)
+
+
+def test_hierarchical_b4096_mask_and_rows():
+    B = 4096
+    P = _bf16_exact(fo.init_params("hierarchical", H=H, heads=8, seed=3))
+    head = FL.HierarchicalFusion(Cfg()).cuda()
+    head.load_state_dict(P, strict=True)
+    head.train()
+    g = torch.Generator(device="cuda").manual_seed(123)
+    xs = [torch.randn((B, L, H), generator=g, device="cuda", dtype=torch.bfloat16).requires_grad_(True) for L in LENS]
+    mask = pkg.ModalityDropout(0.3, seed=99).sample_mask(B, "cuda")
+    assert mask.shape == (B, 3) and bool((mask.sum(1) >= 1).all())                # keep-at-least-one repair (encoders.py:308-314)
+    assert 0.6 < float(mask.float().mean()) < 0.8
+    out = head(*xs, compute_contrastive_loss=True, mask=mask)
+    loss = (out["fused_features"].float() ** 2).sum() / (B * H) + 0.1 * sum(out["contrastive_losses"].values())
+    loss.backward()
+    torch.cuda.synchronize()
+    for k, v in out.items():
+        if isinstance(v, torch.Tensor):
+            assert torch.isfinite(v).all(), k
+    for i in range(3):
+        dropped = mask[:, i] == 0
+        assert bool(dropped.any())
+        assert float(xs[i].grad[dropped].abs().max()) == 0.0                        # a dropped modality gets no gradient
+        assert float(xs[i].grad[~dropped].abs().max()) > 0.0
+    P64 = {k: v.double() for k, v in P.items()}
+    for b in (7, 4095):
+        row = [x[b:b + 1].detach().double().cpu() for x in xs]
+        row = fo.apply_modality_mask(*row, mask[b:b + 1].double().cpu())
+        ref = fo.hierarchical_fusion(*row, P64, heads=8, compute_contrastive_loss=False)
+        for k in ("fused_features", "mult_features", "early_features", "graph_features", "adaptive_features", "contrastive_features"):
+            assert rel(out[k][b:b + 1], ref[k]) <= 2e-2, (b, k)

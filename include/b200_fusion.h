@@ -77,6 +77,10 @@ typedef struct {
   int32_t flags;                        /* B200F_EPI_*                                           */
   int32_t dtype;                        /* b200f_dtype of A, B, residual, relu_mask (and C)      */
   int32_t split_k;                      /* >1 only with B200F_EPI_ACCUM; 0/1 = none              */
+  float* colsum;                        /* optional [N] fp32 accumulator: += column sums of the
+                                           stored C (the bias gradient of the Linear whose output
+                                           gradient C is, e.g. ffn.0.bias from the FFN2 input-gradient
+                                           GEMM); summed in the epilogue of the tcgen05 kernels      */
 } b200f_gemm_args;
 int b200f_gemm(const b200f_gemm_args* args, void* stream);
 
@@ -102,6 +106,10 @@ typedef struct {
   void* dK; int64_t lddk;
   void* dV; int64_t lddv;
   float* delta;                         /* [B,H,Lq] workspace: rowsum(dO * O)                    */
+  /* optional fp32 [H*D] accumulators (nullable): += column sums over (b, l) of dQ / dK / dV, i.e.
+   * the bias gradients of the projections that produced Q / K / V (in_proj_bias of
+   * nn.MultiheadAttention, torch nn/functional.py:5740-5760) -- fused into the backward epilogue */
+  float* dbq; float* dbk; float* dbv;
 } b200f_attn_args;
 int b200f_attn_fwd(const b200f_attn_args* args, void* stream);
 int b200f_attn_bwd(const b200f_attn_args* args, void* stream);

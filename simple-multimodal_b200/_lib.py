@@ -30,7 +30,8 @@ class GemmArgs(C.Structure):
                 ("bias", C.c_void_p),
                 ("residual", C.c_void_p), ("ldr", C.c_int64),
                 ("relu_mask", C.c_void_p), ("ldm", C.c_int64),
-                ("alpha", C.c_float), ("flags", C.c_int32), ("dtype", C.c_int32), ("split_k", C.c_int32)]
+                ("alpha", C.c_float), ("flags", C.c_int32), ("dtype", C.c_int32), ("split_k", C.c_int32),
+                ("colsum", C.c_void_p)]
 
 
 class AttnArgs(C.Structure):
@@ -44,7 +45,8 @@ class AttnArgs(C.Structure):
                 ("dQ", C.c_void_p), ("lddq", C.c_int64),
                 ("dK", C.c_void_p), ("lddk", C.c_int64),
                 ("dV", C.c_void_p), ("lddv", C.c_int64),
-                ("delta", C.c_void_p)]
+                ("delta", C.c_void_p),
+                ("dbq", C.c_void_p), ("dbk", C.c_void_p), ("dbv", C.c_void_p)]
 
 
 _lib = None

@@ -34,9 +34,11 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st);
 int gemm_f32_simt(const b200f_gemm_args& a, cudaStream_t st);
 int gemm_bf16_simt(const b200f_gemm_args& a, cudaStream_t st);
 bool gemm_tc_eligible(const b200f_gemm_args& a);
+bool gemm_tc_colsum_fused(const b200f_gemm_args& a);
 extern uint32_t g_dbg_mn_lbo, g_dbg_mn_sbo, g_dbg_mn_kadv;
 extern bool g_dbg_disable_pair;
 extern int g_attn_fwd_variant;
+extern int g_attn_bwd_variant;
 
 }  // namespace b200f
 
@@ -59,9 +61,18 @@ int b200f_device_supported(int device) {
 int b200f_gemm(const b200f_gemm_args* a, void* stream) {
   if (!a) return b200f::fail(B200F_ERR_SHAPE, "gemm: null args");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->dtype == B200F_BF16) return b200f::gemm_tc_eligible(*a) ? b200f::gemm_bf16_tc(*a, st) : b200f::gemm_bf16_simt(*a, st);
-  if (a->dtype == B200F_F32) return b200f::gemm_f32_simt(*a, st);
-  return b200f::fail(B200F_ERR_DTYPE, "gemm: unknown dtype %d", a->dtype);
+  if (a->colsum && (a->flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) && a->dtype == B200F_BF16)
+    return b200f::fail(B200F_ERR_UNSUPPORTED, "gemm: colsum needs the output in the operand dtype");
+  if (a->dtype == B200F_BF16 && b200f::gemm_tc_eligible(*a) && (!a->colsum || b200f::gemm_tc_colsum_fused(*a)))
+    return b200f::gemm_bf16_tc(*a, st);                       // column sums (if any) come out of the epilogue
+  b200f_gemm_args plain = *a;                                // other paths: GEMM, then one pass over the stored C
+  plain.colsum = nullptr;
+  int rc;
+  if (a->dtype == B200F_BF16) rc = b200f::gemm_tc_eligible(plain) ? b200f::gemm_bf16_tc(plain, st) : b200f::gemm_bf16_simt(plain, st);
+  else if (a->dtype == B200F_F32) rc = b200f::gemm_f32_simt(plain, st);
+  else return b200f::fail(B200F_ERR_DTYPE, "gemm: unknown dtype %d", a->dtype);
+  if (rc || !a->colsum) return rc;
+  return b200f_colsum_accum(a->C, a->ldc, a->colsum, a->M, a->N, a->dtype, stream);
 }
 
 // debug: override MN-major UMMA descriptor geometry (0 restores the default). Not part of the product API.
@@ -72,6 +83,7 @@ int b200f_debug_set(int key, unsigned value) {
     case 2: b200f::g_dbg_mn_kadv = value; break;
     case 3: b200f::g_dbg_disable_pair = value != 0; break;
     case 4: b200f::g_attn_fwd_variant = int(value); break;
+    case 5: b200f::g_attn_bwd_variant = int(value); break;
     default: return b200f::fail(B200F_ERR_UNSUPPORTED, "unknown debug key %d", key);
   }
   return B200F_OK;
@@ -109,8 +121,14 @@ int b200f_attn_bwd(const b200f_attn_args* a, void* stream) {
   int rc = b200f::attn_check(a);
   if (rc || a->B == 0) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->dtype == B200F_BF16 && a->D == 64 && !b200f::g_force_simt_attention) return b200f::attn_bwd_tc(*a, st);
-  return b200f::attn_bwd_simt_dispatch(*a, st);
+  const bool tc = a->dtype == B200F_BF16 && a->D == 64 && !b200f::g_force_simt_attention;
+  rc = tc ? b200f::attn_bwd_tc(*a, st) : b200f::attn_bwd_simt_dispatch(*a, st);
+  if (rc || (tc && b200f::g_attn_bwd_variant == 0)) return rc;      // the persistent tcgen05 kernels sum the bias gradients in their epilogue
+  const int64_t W = (int64_t)a->H * a->D;
+  if (a->dbq && (rc = b200f_colsum_accum(a->dQ, a->lddq, a->dbq, (int64_t)a->B * a->Lq, W, a->dtype, stream))) return rc;
+  if (a->dbk && (rc = b200f_colsum_accum(a->dK, a->lddk, a->dbk, (int64_t)a->B * a->Lk, W, a->dtype, stream))) return rc;
+  if (a->dbv && (rc = b200f_colsum_accum(a->dV, a->lddv, a->dbv, (int64_t)a->B * a->Lk, W, a->dtype, stream))) return rc;
+  return B200F_OK;
 }
 
 // debug: route bf16 attention through the CUDA-core kernels (for A/B comparison against the tcgen05 path)

@@ -38,12 +38,16 @@ struct AttnTcParams {
   bf16* dQ; long long lddq;
   bf16* dK; long long lddk;
   bf16* dV; long long lddv;
+  float* dbq; float* dbk; float* dbv;   // optional [H*64] fp32 accumulators: column sums of dQ / dK / dV (in-proj bias gradients)
 };
 
 // Epilogue helper: this warp's 32 accumulator rows x 64 fp32 columns in TMEM -> (x mul) -> bf16 -> a private [32 x 128 B]
 // swizzled smem tile -> global, 4 full 128-byte rows per store instruction (a thread owns a ROW in TMEM, so direct
 // stores would touch 32 different lines per instruction).  `gbase` points at (first row of this warp, first column).
-__device__ __forceinline__ void store_rows64(uint32_t taddr, uint8_t* stage, bf16* gbase, long long ld, int rows_valid, int lane, float mul) {
+// `colsum` (optional, 64 floats for this head): += the column sums of the rows stored (the bf16-rounded values, so it
+// equals a column sum over the stored tensor) -- the bias gradient of the projection that produced Q / K / V.
+__device__ __forceinline__ void store_rows64(uint32_t taddr, uint8_t* stage, bf16* gbase, long long ld, int rows_valid, int lane, float mul,
+                                             float* colsum = nullptr) {
 #pragma unroll
   for (int cc = 0; cc < HD; cc += 16) {
     uint32_t r[16];
@@ -63,6 +67,17 @@ __device__ __forceinline__ void store_rows64(uint32_t taddr, uint8_t* stage, bf1
     if (r < rows_valid)
       *reinterpret_cast<uint4*>(gbase + (long long)r * ld + cchunk * 8) = *reinterpret_cast<const uint4*>(stage + sw128_offset(r, cchunk));
   }
+  if (colsum) {                          // lane owns columns 2*lane, 2*lane+1: one conflict-free 4-byte word per row
+    float a0 = 0.f, a1 = 0.f;
+    const int nr = rows_valid < 32 ? rows_valid : 32;
+    for (int r = 0; r < nr; ++r) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(stage + sw128_offset(r, lane >> 2) + (lane & 3) * 4);
+      a0 += __uint_as_float(w << 16);
+      a1 += __uint_as_float(w & 0xFFFF0000u);
+    }
+    if (nr > 0) { atomicAdd(colsum + 2 * lane, a0); atomicAdd(colsum + 2 * lane + 1, a1); }
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -255,14 +270,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
 // ------------------------------------------------------------------------------------------------
 // forward v2 (default): persistent, one CTA per SM, TWO 128-query tiles in flight.
-//   warp 0      TMA producer : Q tiles of the next work item, 3-deep ring of {K,V} tiles
-//   warp 1      MMA issuer   : per key tile j and query tile t:  PV_t(j), then S_t(j+1) -- so while warpgroup t runs the
+//   warp 8      TMA producer : Q tiles of the next work item, 3-deep ring of {K,V} tiles
+//   warp 9      MMA issuer   : per key tile j and query tile t:  PV_t(j), then S_t(j+1) -- so while warpgroup t runs the
 //                              softmax of S_t(j+1) the tensor pipe works on the other tile, and the two warpgroups keep
 //                              the MUFU pipe (the real bound at head dim 64: one exp per 256 MMA FLOPs) continuously busy
-//   warps 2-5   softmax warpgroup 0 (query rows 0..127 of the item),  warps 6-9  warpgroup 1 (rows 128..255)
+//   warps 0-3   softmax warpgroup 0 (query rows 0..127 of the item),  warps 4-7  warpgroup 1 (rows 128..255); 224 registers
+//               each after setmaxnreg (a whole 128-score row stays in registers: the scores are read from TMEM once)
 // TMEM: S_0 [0,128) S_1 [128,256) O_0 [256,320) O_1 [320,384).  A work item = (batch, head, 256-query block).
 // ------------------------------------------------------------------------------------------------
-static constexpr int F2_THREADS = 320;
+static constexpr int F2_THREADS = 384;     // warps 0-3 softmax warpgroup 0, 4-7 warpgroup 1, 8 TMA, 9 MMA, 10-11 idle (complete the third warpgroup)
+static constexpr int SOFTMAX_REGS = 224, IO_REGS = 56;   // setmaxnreg: 256 x 224 + 128 x 56 = 384 x 168 (the launch allocation)
 static constexpr int F2_ST = 3;      // K/V ring depth
 struct Fwd2Smem {
   static constexpr int Q_OFF = 0;                              // 2 x [128 x 64] bf16, K-major SW128
@@ -291,7 +308,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.Lk + TK - 1) / TK;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
     mbar_init(q_full, 1); mbar_init(q_empty, 1);
@@ -299,13 +316,15 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_ready[t], 4); mbar_init(&o_full[t], 1); mbar_init(&o_empty[t], 4); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp >= 8) {
+  setmaxnreg_dec<IO_REGS>();
+  if (warp == 8) {
     if (lane == 0) {
       uint32_t g = 0, it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -326,7 +345,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, TK, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(TQ, HD, 0, 1);
@@ -387,8 +406,10 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
     }
     __syncwarp();
+  }
   } else {
-    const int t = (warp - 2) >> 2;                   // query tile / warpgroup
+    setmaxnreg_inc<SOFTMAX_REGS>();
+    const int t = warp >> 2;                         // query tile / warpgroup
     const int grp = warp & 3;                        // TMEM lane group this warp may touch
     const int row = grp * 32 + lane;                 // row of the tile == TMEM lane
     const uint32_t lane_addr = uint32_t(grp * 32) << 16;
@@ -409,21 +430,27 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const int valid = min(TK, p.Lk - j * TK);    // keys beyond Lk were zero-filled by TMA: mask them
         const int cols = (valid + 31) & ~31;
         const bool ragged = valid < cols;
+        // ONE pass over the scores: the whole row (up to 128 fp32) is loaded into registers with all tcgen05.ld in flight
+        // together (a load costs ~94 cycles per warp: serialising 8 of them per tile was a third of the softmax time)
+        uint32_t r[4][32];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q * 32 < cols) tmem_ld32(t_s + lane_addr + q * 32, r[q]);
+        tmem_ld_wait();
         float tmax = -INFINITY, tmax_b = -INFINITY;
-#pragma unroll 1
-        for (int cc = 0; cc < cols; cc += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_s + lane_addr + cc, r);
-          tmem_ld_wait();
-          if (ragged && cc + 32 > valid) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (cc + i >= valid) r[i] = 0xff800000u;   // -inf
-          }
+        for (int q = 0; q < 4; ++q) {
+          if (q * 32 < cols) {
+            if (ragged && q * 32 + 32 > valid) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            tmax = fmax3(tmax, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-            tmax_b = fmax3(tmax_b, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+              for (int i = 0; i < 32; ++i)
+                if (q * 32 + i >= valid) r[q][i] = 0xff800000u;   // -inf: ex2(-inf) = 0
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              tmax = fmax3(tmax, __uint_as_float(r[q][i]), __uint_as_float(r[q][i + 1]));
+              tmax_b = fmax3(tmax_b, __uint_as_float(r[q][i + 2]), __uint_as_float(r[q][i + 3]));
+            }
           }
         }
         const float m_new = fmax3(m, tmax, tmax_b);
@@ -434,30 +461,24 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const float nmc = -m_use * c;
         const uint64_t nmc2 = f2_pack(nmc, nmc);
         uint64_t lsum2 = 0ull;
-#pragma unroll 1
-        for (int cc = 0; cc < cols; cc += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_s + lane_addr + cc, r);
-          tmem_ld_wait();
-          if (ragged && cc + 32 > valid) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (cc + i >= valid) r[i] = 0xff800000u;   // ex2(-inf) = 0
-          }
-          uint32_t pk[16];
+        for (int q = 0; q < 4; ++q) {
+          if (q * 32 < cols) {
+            uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float x0, x1;
-            f2_unpack(f2_fma(f2_pack_u(r[i], r[i + 1]), c2, nmc2), x0, x1);
-            const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
-            lsum2 = f2_add(lsum2, f2_pack(e0, e1));
-            pk[i >> 1] = pack_bf16(e0, e1);
-          }
-          uint8_t* half = prow + (cc >> 6) * (TQ * 128);   // 32 keys = four 16-byte chunks of this row inside the 64-key half
+            for (int i = 0; i < 32; i += 2) {
+              float x0, x1;
+              f2_unpack(f2_fma(f2_pack_u(r[q][i], r[q][i + 1]), c2, nmc2), x0, x1);
+              const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+              lsum2 = f2_add(lsum2, f2_pack(e0, e1));
+              pk[i >> 1] = pack_bf16(e0, e1);
+            }
+            uint8_t* half = prow + (q >> 1) * (TQ * 128);   // 32 keys = four 16-byte chunks of this row inside the 64-key half
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const uint32_t chunk = ((cc & 63) >> 3) + q4;
-            *reinterpret_cast<uint4*>(half + sw128_offset(row, chunk)) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const uint32_t chunk = (q & 1) * 4 + q4;
+              *reinterpret_cast<uint4*>(half + sw128_offset(row, chunk)) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+            }
           }
         }
         float ls0, ls1;
@@ -497,7 +518,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
 }
 
 // 4-D view (d, head, token, batch) of a token-major [B, L, ld] tensor slice; box = 64 x 1 x rows x 1
@@ -860,6 +881,435 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   if (warp == 1) tmem_dealloc<256>(tmem_base);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// backward v2 (default): persistent kernels, one CTA per SM, TWO 128-row tiles in flight -- the forward v2 schedule.
+// While warpgroup t turns S_t / dP_t into dS_t (MUFU + FMA bound), the tensor pipe runs the other tile's MMAs, and the
+// next S / dP of a tile is issued right behind the accumulation MMA that consumed the previous dS; K/V (dQ kernel) or
+// Q/dO (dKdV kernel) tiles are shared by both tiles through a 3-deep TMA ring, and the next work item's resident
+// operands are fetched while the current item's last tile is still in the softmax warps.
+//   warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 warpgroup 0, warps 6-9 warpgroup 1.
+// ------------------------------------------------------------------------------------------------
+static constexpr int B2_THREADS = 384;     // warps 0-3 warpgroup 0, 4-7 warpgroup 1, 8 TMA, 9 MMA, 10-11 idle
+static constexpr int B2_ST = 3;
+
+struct Dq2Smem {
+  static constexpr int Q_OFF = 0;                              // 2 x [128 x 64]
+  static constexpr int DO_OFF = Q_OFF + 2 * TQ * HD * 2;       // 2 x [128 x 64]
+  static constexpr int K_OFF = DO_OFF + 2 * TQ * HD * 2;       // B2_ST x [64 keys x 64]
+  static constexpr int V_OFF = K_OFF + B2_ST * BT * HD * 2;    // B2_ST x [64 keys x 64]
+  static constexpr int DS_OFF = V_OFF + B2_ST * BT * HD * 2;   // 2 x [128 x 64 keys] bf16, K-major SW128
+  static constexpr int BAR_OFF = DS_OFF + 2 * TQ * BT * 2;
+  static constexpr int TOTAL = BAR_OFF + 256;
+};
+
+// work item = (batch, head, 256-query block); TMEM per tile t: S_t [192t, +64) dP_t [+64, +128) dQ_t [+128, +192)
+__global__ void __launch_bounds__(B2_THREADS, 1)
+attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                       const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p,
+                       const int n_qblk, const int n_items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Dq2Smem::BAR_OFF);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;               // [B2_ST]
+  uint64_t* kv_empty = kv_full + B2_ST;       // [B2_ST]
+  uint64_t* sdp_full = kv_empty + B2_ST;      // [2]  S_t(j), dP_t(j) complete (and every earlier MMA, incl. dQ_t(j-1))
+  uint64_t* ds_ready = sdp_full + 2;          // [2]  dS_t(j) in smem, S_t / dP_t consumed
+  uint64_t* dq_full = ds_ready + 2;           // [2]  last dQ_t MMA of the item complete
+  uint64_t* dq_empty = dq_full + 2;           // [2]  epilogue has read dQ_t
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (p.Lk + BT - 1) / BT;
+
+  if (warp == 8 && lane == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int i = 0; i < B2_ST; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(&sdp_full[t], 1); mbar_init(&ds_ready[t], 4); mbar_init(&dq_full[t], 1); mbar_init(&dq_empty[t], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 8) {
+  setmaxnreg_dec<IO_REGS>();
+  if (warp == 8) {
+    if (lane == 0) {
+      uint32_t g = 0, it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int qb = item % n_qblk, h = (item / n_qblk) % p.H, b = item / (n_qblk * p.H);
+        const int q0 = qb * 2 * TQ;
+        const bool two = q0 + TQ < p.Lq;
+        mbar_wait(q_empty, (it & 1) ^ 1);
+        mbar_expect_tx(q_full, (two ? 4 : 2) * TQ * HD * 2);
+        tma_load_4d(smem + Dq2Smem::Q_OFF, &tm_q, q_full, 0, h, q0, b);
+        tma_load_4d(smem + Dq2Smem::DO_OFF, &tm_do, q_full, 0, h, q0, b);
+        if (two) {
+          tma_load_4d(smem + Dq2Smem::Q_OFF + TQ * HD * 2, &tm_q, q_full, 0, h, q0 + TQ, b);
+          tma_load_4d(smem + Dq2Smem::DO_OFF + TQ * HD * 2, &tm_do, q_full, 0, h, q0 + TQ, b);
+        }
+        for (int j = 0; j < n_tiles; ++j, ++g) {
+          const int st = g % B2_ST;
+          mbar_wait(&kv_empty[st], ((g / B2_ST) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[st], 2 * BT * HD * 2);
+          tma_load_4d(smem + Dq2Smem::K_OFF + st * BT * HD * 2, &tm_k, &kv_full[st], 0, h, j * BT, b);
+          tma_load_4d(smem + Dq2Smem::V_OFF + st * BT * HD * 2, &tm_v, &kv_full[st], 0, h, j * BT, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, BT, 0, 0);     // S = Q K^T, dP = dO V^T   (N = 64 keys)
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(TQ, HD, 0, 1);    // dQ += dS K             (K MN-major, N = d)
+      uint32_t g = 0, it = 0, ds_cnt[2] = {0, 0}, dq_cnt[2] = {0, 0};
+      auto issue_sdp = [&](int t, uint32_t sk, uint32_t sv) {
+        const uint32_t sq = smem_u32(smem + Dq2Smem::Q_OFF + t * TQ * HD * 2), sdo = smem_u32(smem + Dq2Smem::DO_OFF + t * TQ * HD * 2);
+        const uint32_t t_s = tmem_base + t * 192, t_dp = t_s + 64;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_ss(t_s, umma_desc(sq + k * 32, 16, 1024), umma_desc(sk + k * 32, 16, 1024), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_ss(t_dp, umma_desc(sdo + k * 32, 16, 1024), umma_desc(sv + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(&sdp_full[t]);
+      };
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int qb = item % n_qblk;
+        const int nt = (qb * 2 * TQ + TQ < p.Lq) ? 2 : 1;
+        mbar_wait(q_full, it & 1);
+        {
+          const int st = g % B2_ST;
+          mbar_wait(&kv_full[st], (g / B2_ST) & 1);
+          tc_fence_after();
+          for (int t = 0; t < nt; ++t)
+            issue_sdp(t, smem_u32(smem + Dq2Smem::K_OFF + st * BT * HD * 2), smem_u32(smem + Dq2Smem::V_OFF + st * BT * HD * 2));
+          if (n_tiles == 1) umma_commit(q_empty);
+        }
+        for (int j = 0; j < n_tiles; ++j) {
+          const int st = (g + j) % B2_ST;
+          const uint32_t sk = smem_u32(smem + Dq2Smem::K_OFF + st * BT * HD * 2);
+          uint32_t sk_next = 0, sv_next = 0;
+          if (j + 1 < n_tiles) {
+            const int stn = (g + j + 1) % B2_ST;
+            mbar_wait(&kv_full[stn], ((g + j + 1) / B2_ST) & 1);
+            sk_next = smem_u32(smem + Dq2Smem::K_OFF + stn * BT * HD * 2);
+            sv_next = smem_u32(smem + Dq2Smem::V_OFF + stn * BT * HD * 2);
+          }
+          for (int t = 0; t < nt; ++t) {
+            mbar_wait(&ds_ready[t], ds_cnt[t] & 1);
+            ++ds_cnt[t];
+            if (j == 0) mbar_wait(&dq_empty[t], (dq_cnt[t] & 1) ^ 1);   // the previous item's epilogue has drained dQ_t
+            tc_fence_after();
+            const uint32_t sds = smem_u32(smem + Dq2Smem::DS_OFF + t * TQ * BT * 2);
+            const uint32_t t_dq = tmem_base + t * 192 + 128;
+#pragma unroll
+            for (int k = 0; k < BT / 16; ++k)
+              umma_ss(t_dq, umma_desc(sds + k * 32, 16, 1024), umma_desc(sk + k * 2048, BT * 128, 1024), idesc_dq, (j > 0 || k > 0) ? 1u : 0u);
+            if (j + 1 < n_tiles) {
+              issue_sdp(t, sk_next, sv_next);
+            } else {
+              umma_commit(&dq_full[t]);
+              ++dq_cnt[t];
+            }
+          }
+          umma_commit(&kv_empty[st]);
+          if (j + 2 == n_tiles) umma_commit(q_empty);
+        }
+        g += n_tiles;
+      }
+    }
+    __syncwarp();
+  }
+  } else {
+    setmaxnreg_inc<SOFTMAX_REGS>();
+    const int t = warp >> 2;
+    const int grp = warp & 3;
+    const int row = grp * 32 + lane;
+    const uint32_t lane_addr = uint32_t(grp * 32) << 16;
+    const uint32_t t_s = tmem_base + t * 192, t_dp = t_s + 64, t_dq = t_s + 128;
+    uint8_t* ds_tile = smem + Dq2Smem::DS_OFF + t * TQ * BT * 2;
+    const float c = p.scale * LOG2E;
+    const uint64_t c2 = f2_pack(c, c), sc2 = f2_pack(p.scale, p.scale);
+    uint32_t sf_cnt = 0, dq_cnt = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int qb = item % n_qblk, h = (item / n_qblk) % p.H, b = item / (n_qblk * p.H);
+      const int q0 = qb * 2 * TQ + t * TQ;
+      if (q0 >= p.Lq) continue;                      // this warpgroup's tile does not exist (the MMA warp skips it too)
+      const int qrow = q0 + row;
+      const long long ri = ((long long)b * p.H + h) * p.Lq + qrow;
+      const float nlse2 = -(qrow < p.Lq ? p.LSE[ri] : 0.f) * LOG2E;
+      const float ndl = -(qrow < p.Lq ? p.delta[ri] : 0.f) * p.scale;
+      const uint64_t nlse22 = f2_pack(nlse2, nlse2), ndl2 = f2_pack(ndl, ndl);
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(&sdp_full[t], sf_cnt & 1);         // also implies dQ_t(j-1) retired: the dS_t tile is ours again
+        ++sf_cnt;
+        tc_fence_after();
+        uint32_t rs[2][32], rp[2][32];               // the whole 64-key row of S and dP: four loads in flight, one wait
+        tmem_ld32(t_s + lane_addr, rs[0]);
+        tmem_ld32(t_dp + lane_addr, rp[0]);
+        tmem_ld32(t_s + lane_addr + 32, rs[1]);
+        tmem_ld32(t_dp + lane_addr + 32, rp[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {     // dS = P o (dP - delta) * scale, two elements per FFMA2 / FMUL2
+            float x0, x1, d0, d1;
+            f2_unpack(f2_fma(f2_pack_u(rs[hf][i], rs[hf][i + 1]), c2, nlse22), x0, x1);
+            const uint64_t t2 = f2_fma(f2_pack_u(rp[hf][i], rp[hf][i + 1]), sc2, ndl2);
+            f2_unpack(f2_mul(f2_pack(ex2_approx(x0), ex2_approx(x1)), t2), d0, d1);
+            pk[i >> 1] = pack_bf16(d0, d1);
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            *reinterpret_cast<uint4*>(ds_tile + sw128_offset(row, hf * 4 + q4)) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ds_ready[t]);
+      }
+      mbar_wait(&dq_full[t], dq_cnt & 1);
+      ++dq_cnt;
+      tc_fence_after();
+      // the dS_t tile is free once the last dQ_t MMA retired: stage dQ through this warp's 4 KB slice of it
+      store_rows64(t_dq + lane_addr, ds_tile + grp * (32 * 128), p.dQ + ((long long)b * p.Lq + q0 + grp * 32) * p.lddq + h * HD, p.lddq,
+                   p.Lq - (q0 + grp * 32), lane, 1.f, p.dbq ? p.dbq + h * HD : nullptr);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dq_empty[t]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
+}
+
+struct Dkv2Smem {
+  static constexpr int K_OFF = 0;                              // 2 x [128 keys x 64]
+  static constexpr int V_OFF = K_OFF + 2 * TK * HD * 2;        // 2 x [128 keys x 64]
+  static constexpr int Q_OFF = V_OFF + 2 * TK * HD * 2;        // B2_ST x [64 queries x 64]
+  static constexpr int DO_OFF = Q_OFF + B2_ST * BT * HD * 2;   // B2_ST x [64 queries x 64]
+  static constexpr int P_OFF = DO_OFF + B2_ST * BT * HD * 2;   // 2 x P^T  [128 keys x 64 queries] bf16
+  static constexpr int DS_OFF = P_OFF + 2 * TK * BT * 2;       // 2 x dS^T [128 keys x 64 queries] bf16
+  static constexpr int STAT_OFF = DS_OFF + 2 * TK * BT * 2;    // 2 warpgroups x 2 buffers x {lse2[64], delta[64]} fp32
+  static constexpr int BAR_OFF = STAT_OFF + 2 * 2 * 2 * BT * 4;
+  static constexpr int TOTAL = BAR_OFF + 256;
+};
+
+// work item = (batch, head, 256-key block); TMEM per tile t: S^T_t [256t, +64) dP^T_t [+64, +128) dV_t [+128, +192) dK_t [+192, +256)
+__global__ void __launch_bounds__(B2_THREADS, 1)
+attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                        const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p,
+                        const int n_kblk, const int n_items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Dkv2Smem::BAR_OFF);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* kv_empty = bars + 1;
+  uint64_t* q_full = bars + 2;                // [B2_ST]
+  uint64_t* q_empty = q_full + B2_ST;         // [B2_ST]
+  uint64_t* sdp_full = q_empty + B2_ST;       // [2]
+  uint64_t* ds_ready = sdp_full + 2;          // [2]
+  uint64_t* acc_full = ds_ready + 2;          // [2]
+  uint64_t* acc_empty = acc_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (p.Lq + BT - 1) / BT;
+
+  if (warp == 8 && lane == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+    mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
+    for (int i = 0; i < B2_ST; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(&sdp_full[t], 1); mbar_init(&ds_ready[t], 4); mbar_init(&acc_full[t], 1); mbar_init(&acc_empty[t], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 8) {
+  setmaxnreg_dec<IO_REGS>();
+  if (warp == 8) {
+    if (lane == 0) {
+      uint32_t g = 0, it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int kb = item % n_kblk, h = (item / n_kblk) % p.H, b = item / (n_kblk * p.H);
+        const int k0 = kb * 2 * TK;
+        const bool two = k0 + TK < p.Lk;
+        mbar_wait(kv_empty, (it & 1) ^ 1);
+        mbar_expect_tx(kv_full, (two ? 4 : 2) * TK * HD * 2);
+        tma_load_4d(smem + Dkv2Smem::K_OFF, &tm_k, kv_full, 0, h, k0, b);
+        tma_load_4d(smem + Dkv2Smem::V_OFF, &tm_v, kv_full, 0, h, k0, b);
+        if (two) {
+          tma_load_4d(smem + Dkv2Smem::K_OFF + TK * HD * 2, &tm_k, kv_full, 0, h, k0 + TK, b);
+          tma_load_4d(smem + Dkv2Smem::V_OFF + TK * HD * 2, &tm_v, kv_full, 0, h, k0 + TK, b);
+        }
+        for (int i = 0; i < n_tiles; ++i, ++g) {
+          const int st = g % B2_ST;
+          mbar_wait(&q_empty[st], ((g / B2_ST) & 1) ^ 1);
+          mbar_expect_tx(&q_full[st], 2 * BT * HD * 2);
+          tma_load_4d(smem + Dkv2Smem::Q_OFF + st * BT * HD * 2, &tm_q, &q_full[st], 0, h, i * BT, b);
+          tma_load_4d(smem + Dkv2Smem::DO_OFF + st * BT * HD * 2, &tm_do, &q_full[st], 0, h, i * BT, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(TK, BT, 0, 0);     // S^T = K Q^T, dP^T = V dO^T   (N = 64 queries)
+      constexpr uint32_t idesc_acc = umma_idesc_bf16(TK, HD, 0, 1);   // dV += P^T dO, dK += dS^T Q   (B MN-major, N = d)
+      uint32_t g = 0, it = 0, ds_cnt[2] = {0, 0}, acc_cnt[2] = {0, 0};
+      auto issue_sdp = [&](int t, uint32_t sq, uint32_t sdo) {
+        const uint32_t sk = smem_u32(smem + Dkv2Smem::K_OFF + t * TK * HD * 2), sv = smem_u32(smem + Dkv2Smem::V_OFF + t * TK * HD * 2);
+        const uint32_t t_s = tmem_base + t * 256, t_dp = t_s + 64;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_ss(t_s, umma_desc(sk + k * 32, 16, 1024), umma_desc(sq + k * 32, 16, 1024), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_ss(t_dp, umma_desc(sv + k * 32, 16, 1024), umma_desc(sdo + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(&sdp_full[t]);
+      };
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int kb = item % n_kblk;
+        const int nt = (kb * 2 * TK + TK < p.Lk) ? 2 : 1;
+        mbar_wait(kv_full, it & 1);
+        {
+          const int st = g % B2_ST;
+          mbar_wait(&q_full[st], (g / B2_ST) & 1);
+          tc_fence_after();
+          for (int t = 0; t < nt; ++t)
+            issue_sdp(t, smem_u32(smem + Dkv2Smem::Q_OFF + st * BT * HD * 2), smem_u32(smem + Dkv2Smem::DO_OFF + st * BT * HD * 2));
+          if (n_tiles == 1) umma_commit(kv_empty);
+        }
+        for (int i = 0; i < n_tiles; ++i) {
+          const int st = (g + i) % B2_ST;
+          const uint32_t sq = smem_u32(smem + Dkv2Smem::Q_OFF + st * BT * HD * 2), sdo = smem_u32(smem + Dkv2Smem::DO_OFF + st * BT * HD * 2);
+          uint32_t sq_next = 0, sdo_next = 0;
+          if (i + 1 < n_tiles) {
+            const int stn = (g + i + 1) % B2_ST;
+            mbar_wait(&q_full[stn], ((g + i + 1) / B2_ST) & 1);
+            sq_next = smem_u32(smem + Dkv2Smem::Q_OFF + stn * BT * HD * 2);
+            sdo_next = smem_u32(smem + Dkv2Smem::DO_OFF + stn * BT * HD * 2);
+          }
+          for (int t = 0; t < nt; ++t) {
+            mbar_wait(&ds_ready[t], ds_cnt[t] & 1);
+            ++ds_cnt[t];
+            if (i == 0) mbar_wait(&acc_empty[t], (acc_cnt[t] & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t sp = smem_u32(smem + Dkv2Smem::P_OFF + t * TK * BT * 2), sds = smem_u32(smem + Dkv2Smem::DS_OFF + t * TK * BT * 2);
+            const uint32_t t_dv = tmem_base + t * 256 + 128, t_dk = t_dv + 64;
+#pragma unroll
+            for (int k = 0; k < BT / 16; ++k)
+              umma_ss(t_dv, umma_desc(sp + k * 32, 16, 1024), umma_desc(sdo + k * 2048, BT * 128, 1024), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < BT / 16; ++k)
+              umma_ss(t_dk, umma_desc(sds + k * 32, 16, 1024), umma_desc(sq + k * 2048, BT * 128, 1024), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
+            if (i + 1 < n_tiles) {
+              issue_sdp(t, sq_next, sdo_next);
+            } else {
+              umma_commit(&acc_full[t]);
+              ++acc_cnt[t];
+            }
+          }
+          umma_commit(&q_empty[st]);
+          if (i + 2 == n_tiles) umma_commit(kv_empty);
+        }
+        g += n_tiles;
+      }
+    }
+    __syncwarp();
+  }
+  } else {
+    setmaxnreg_inc<SOFTMAX_REGS>();
+    const int t = warp >> 2;
+    const int grp = warp & 3;
+    const int row = grp * 32 + lane;                 // key row of the tile == TMEM lane
+    const int t128 = threadIdx.x - t * 128;          // 0..127 inside this warpgroup
+    const uint32_t lane_addr = uint32_t(grp * 32) << 16;
+    const uint32_t t_s = tmem_base + t * 256, t_dp = t_s + 64, t_dv = t_s + 128, t_dk = t_s + 192;
+    uint8_t* p_tile = smem + Dkv2Smem::P_OFF + t * TK * BT * 2;
+    uint8_t* ds_tile = smem + Dkv2Smem::DS_OFF + t * TK * BT * 2;
+    float* stats = reinterpret_cast<float*>(smem + Dkv2Smem::STAT_OFF) + t * (2 * 2 * BT);
+    const float c = p.scale * LOG2E;
+    const uint64_t c2 = f2_pack(c, c), sc2 = f2_pack(p.scale, p.scale);
+    uint32_t sf_cnt = 0, acc_cnt = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int kb = item % n_kblk, h = (item / n_kblk) % p.H, b = item / (n_kblk * p.H);
+      const int k0 = kb * 2 * TK + t * TK;
+      if (k0 >= p.Lk) continue;
+      const long long stat_base = ((long long)b * p.H + h) * p.Lq;
+      for (int i = 0; i < n_tiles; ++i) {
+        float* sl = stats + (sf_cnt & 1) * 2 * BT;   // [lse2[64] | delta[64]] of this tile's queries; parity runs across items
+        {
+          const int qi = i * BT + (t128 & 63);
+          float v = 0.f;                             // stored negated (and delta pre-scaled) so the inner loop is pure FFMA2
+          if (qi < p.Lq) v = t128 < 64 ? -p.LSE[stat_base + qi] * LOG2E : -p.delta[stat_base + qi] * p.scale;
+          sl[t128] = v;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
+        mbar_wait(&sdp_full[t], sf_cnt & 1);         // implies the previous tile's dV/dK MMAs (reading P^T/dS^T) retired
+        ++sf_cnt;
+        tc_fence_after();
+        uint32_t rs[2][32], rp[2][32];               // the whole 64-query row of S^T and dP^T: four loads in flight, one wait
+        tmem_ld32(t_s + lane_addr, rs[0]);
+        tmem_ld32(t_dp + lane_addr, rp[0]);
+        tmem_ld32(t_s + lane_addr + 32, rs[1]);
+        tmem_ld32(t_dp + lane_addr + 32, rp[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t pp[16], pd[16];
+          const uint64_t* nl2 = reinterpret_cast<const uint64_t*>(sl + hf * 32);         // -lse2 of the queries, pairs (warp-broadcast reads)
+          const uint64_t* nd2 = reinterpret_cast<const uint64_t*>(sl + BT + hf * 32);    // -delta*scale
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float x0, x1, d0, d1;
+            f2_unpack(f2_fma(f2_pack_u(rs[hf][e], rs[hf][e + 1]), c2, nl2[e >> 1]), x0, x1);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            const uint64_t t2 = f2_fma(f2_pack_u(rp[hf][e], rp[hf][e + 1]), sc2, nd2[e >> 1]);
+            f2_unpack(f2_mul(f2_pack(p0, p1), t2), d0, d1);
+            pp[e >> 1] = pack_bf16(p0, p1);
+            pd[e >> 1] = pack_bf16(d0, d1);
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const uint32_t off = sw128_offset(row, hf * 4 + q4);
+            *reinterpret_cast<uint4*>(p_tile + off) = make_uint4(pp[q4 * 4], pp[q4 * 4 + 1], pp[q4 * 4 + 2], pp[q4 * 4 + 3]);
+            *reinterpret_cast<uint4*>(ds_tile + off) = make_uint4(pd[q4 * 4], pd[q4 * 4 + 1], pd[q4 * 4 + 2], pd[q4 * 4 + 3]);
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ds_ready[t]);
+      }
+      mbar_wait(&acc_full[t], acc_cnt & 1);
+      ++acc_cnt;
+      tc_fence_after();
+      // P^T / dS^T tiles are free once the last accumulation MMA retired: stage dV / dK through this warp's slices of them
+      store_rows64(t_dv + lane_addr, p_tile + grp * (32 * 128), p.dV + ((long long)b * p.Lk + k0 + grp * 32) * p.lddv + h * HD, p.lddv,
+                   p.Lk - (k0 + grp * 32), lane, 1.f, p.dbv ? p.dbv + h * HD : nullptr);
+      store_rows64(t_dk + lane_addr, ds_tile + grp * (32 * 128), p.dK + ((long long)b * p.Lk + k0 + grp * 32) * p.lddk + h * HD, p.lddk,
+                   p.Lk - (k0 + grp * 32), lane, 1.f, p.dbk ? p.dbk + h * HD : nullptr);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[t]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
+}
+
+int g_attn_bwd_variant = 0;      // 0 = persistent two-tile kernels, 1 = one tile per CTA (debug / A-B; b200f_debug_set(5, v))
+
 int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st) {
   int rc = attn_tc_check(a);
   if (rc) return rc;
@@ -871,6 +1321,7 @@ int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st) {
   p.dQ = static_cast<bf16*>(a.dQ); p.lddq = a.lddq;
   p.dK = static_cast<bf16*>(a.dK); p.lddk = a.lddk;
   p.dV = static_cast<bf16*>(a.dV); p.lddv = a.lddv;
+  p.dbq = a.dbq; p.dbk = a.dbk; p.dbv = a.dbv;
   const long long rows = (long long)a.B * a.H * a.Lq;
   attn_delta_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(static_cast<const bf16*>(a.dO), a.lddo, static_cast<const bf16*>(a.O), a.ldo, a.delta, a.B, a.H, a.Lq);
   if ((rc = check_launch("attn_delta_kernel"))) return rc;
@@ -878,9 +1329,38 @@ int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st) {
   if (!configured) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::TOTAL));
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem::TOTAL));
+    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Dq2Smem::TOTAL));
+    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Dkv2Smem::TOTAL));
     configured = true;
   }
   CUtensorMap tq, tdo, tk, tv;
+  if (g_attn_bwd_variant == 0) {
+    {  // dQ: 128-row Q/dO boxes, 64-row K/V boxes; item = (batch, head, 256-query block)
+      if ((rc = make_head_tmap(&tq, a.Q, a.ldq, a.B, a.H, a.Lq, TQ))) return rc;
+      if ((rc = make_head_tmap(&tdo, a.dO, a.lddo, a.B, a.H, a.Lq, TQ))) return rc;
+      if ((rc = make_head_tmap(&tk, a.K, a.ldk, a.B, a.H, a.Lk, BT))) return rc;
+      if ((rc = make_head_tmap(&tv, a.V, a.ldv, a.B, a.H, a.Lk, BT))) return rc;
+      const int n_qblk = (a.Lq + 2 * TQ - 1) / (2 * TQ);
+      const long long n_items = (long long)n_qblk * a.H * a.B;
+      B200F_REQUIRE(n_items < (1ll << 31), B200F_ERR_SHAPE, "attention(tcgen05): too many work items");
+      const int grid = int(n_items < num_sms() ? n_items : num_sms());
+      attn_bwd_dq_tc2_kernel<<<grid, B2_THREADS, Dq2Smem::TOTAL, st>>>(tq, tdo, tk, tv, p, n_qblk, int(n_items));
+      if ((rc = check_launch("attn_bwd_dq_tc2_kernel"))) return rc;
+    }
+    {  // dKdV: 128-row K/V boxes, 64-row Q/dO boxes; item = (batch, head, 256-key block)
+      if ((rc = make_head_tmap(&tq, a.Q, a.ldq, a.B, a.H, a.Lq, BT))) return rc;
+      if ((rc = make_head_tmap(&tdo, a.dO, a.lddo, a.B, a.H, a.Lq, BT))) return rc;
+      if ((rc = make_head_tmap(&tk, a.K, a.ldk, a.B, a.H, a.Lk, TK))) return rc;
+      if ((rc = make_head_tmap(&tv, a.V, a.ldv, a.B, a.H, a.Lk, TK))) return rc;
+      const int n_kblk = (a.Lk + 2 * TK - 1) / (2 * TK);
+      const long long n_items = (long long)n_kblk * a.H * a.B;
+      B200F_REQUIRE(n_items < (1ll << 31), B200F_ERR_SHAPE, "attention(tcgen05): too many work items");
+      const int grid = int(n_items < num_sms() ? n_items : num_sms());
+      attn_bwd_dkv_tc2_kernel<<<grid, B2_THREADS, Dkv2Smem::TOTAL, st>>>(tq, tdo, tk, tv, p, n_kblk, int(n_items));
+      if ((rc = check_launch("attn_bwd_dkv_tc2_kernel"))) return rc;
+    }
+    return B200F_OK;
+  }
   {  // dQ kernel: 128-row Q/dO boxes, 64-row K/V boxes
     if ((rc = make_head_tmap(&tq, a.Q, a.ldq, a.B, a.H, a.Lq, TQ))) return rc;
     if ((rc = make_head_tmap(&tdo, a.dO, a.lddo, a.B, a.H, a.Lq, TQ))) return rc;

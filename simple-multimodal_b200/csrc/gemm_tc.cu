@@ -35,6 +35,7 @@ struct GemmTcParams {
   // UMMA descriptor geometry (bytes), filled by the host so it can be probed without recompiling
   uint32_t a_lbo, a_sbo, a_kadv, b_lbo, b_sbo, b_kadv;
   int vec_ok;  // C / residual / mask rows are 16-byte aligned -> 128-bit epilogue accesses
+  float* colsum;  // optional [N]: += column sums of the stored bf16 C (N % 64 == 0; staged bf16 epilogue only)
 };
 
 template <int BN, int STAGES>
@@ -233,6 +234,19 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, uint8_
     for (int it = 0; it < 8; ++it) {
       const int rr = it * 4 + crow;
       if (row0 + rr < p.M) *reinterpret_cast<uint4*>(cbase + (long long)rr * p.ldc) = *reinterpret_cast<const uint4*>(st + sw128_offset(rr, cchunk));
+    }
+    if (p.colsum) {
+      // bias gradient: column sums of the 32 x 64 block just staged (the rounded values that were stored).  A lane owns
+      // columns 2*lane, 2*lane+1 (one conflict-free word per row); even lanes collect 4 columns and issue one vector RED.
+      float a0 = 0.f, a1 = 0.f;
+      const int nr = p.M - row0 < 32 ? int(p.M - row0) : 32;
+      for (int rr = 0; rr < nr; ++rr) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(st + sw128_offset(rr, lane >> 2) + (lane & 3) * 4);
+        a0 += __uint_as_float(w << 16);
+        a1 += __uint_as_float(w & 0xFFFF0000u);
+      }
+      const float b0 = __shfl_down_sync(0xffffffffu, a0, 1), b1 = __shfl_down_sync(0xffffffffu, a1, 1);
+      if (!(lane & 1)) red_add_v4(p.colsum + col0 + 2 * lane, make_float4(a0, a1, b0, b1));
     }
     __syncwarp();
   }
@@ -659,6 +673,14 @@ bool gemm_tc_eligible(const b200f_gemm_args& a) {
   return a.lda % 8 == 0 && a.ldb % 8 == 0 && aligned16(a.A) && aligned16(a.B) && a.N >= 8 && a.K >= 8 && a.M >= 1;
 }
 
+// The column-sum epilogue lives in the staged bf16 path only: full 64-column blocks, vector accesses, 16-byte aligned accumulator.
+bool gemm_tc_colsum_fused(const b200f_gemm_args& a) {
+  const bool out_f32 = (a.flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) != 0;
+  const bool vec_ok = aligned16(a.C) && a.ldc % 8 == 0 && (!a.residual || (a.ldr % 8 == 0 && aligned16(a.residual))) &&
+                      (!a.relu_mask || (a.ldm % 8 == 0 && aligned16(a.relu_mask))) && (!a.bias || aligned16(a.bias));
+  return gemm_tc_eligible(a) && !out_f32 && vec_ok && a.N % 64 == 0 && aligned16(a.colsum);
+}
+
 int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
   B200F_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, B200F_ERR_SHAPE, "gemm: empty shape M=%lld N=%lld K=%lld", (long long)a.M, (long long)a.N, (long long)a.K);
   B200F_REQUIRE(gemm_tc_eligible(a), B200F_ERR_ALIGN, "gemm(bf16/tcgen05): lda/ldb must be multiples of 8 elements and A/B 16-byte aligned");
@@ -699,6 +721,9 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
   p.mask = static_cast<const bf16*>(a.relu_mask); p.ldm = a.ldm;
   p.alpha = a.alpha; p.flags = a.flags;
   p.vec_ok = vec_ok ? 1 : 0;
+  p.colsum = a.colsum;
+  if (a.colsum)
+    B200F_REQUIRE(gemm_tc_colsum_fused(a), B200F_ERR_UNSUPPORTED, "gemm(tcgen05): fused colsum needs bf16 output, N %% 64 == 0 and aligned rows");
   // K-major SW128: rows of 128 B, 8-row groups 1024 B apart, +32 B per K=16 step inside the swizzle row.
   // MN-major SW128: 64-element (128 B) MN chunks, k rows 128 B apart, 8-k-row groups 1024 B apart (SBO),
   //                 MN chunks BK*128 B apart (LBO), +16 k rows = 2048 B per K=16 step.

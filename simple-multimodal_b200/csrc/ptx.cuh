@@ -210,6 +210,12 @@ __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
 }
 
 
+// ---------------------------------------------------------------- register reallocation between warpgroups
+// All four warps of a warpgroup (warps 4g..4g+3) must execute the same one.  The softmax warpgroups of the attention kernels
+// keep a whole score row (128 fp32) in registers and need room to batch MUFU/FFMA2 work; the TMA / MMA warps need ~32.
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ---------------------------------------------------------------- CTA pairs (cta_group::2)
 // In the shared::cluster window the address of rank r's copy of a shared variable is (cta address | r << 24) for the two CTAs
 // of an MMA pair; clearing bit 24 therefore names the LEADER (even) CTA's copy from either CTA.

@@ -7,10 +7,21 @@
 namespace b200f {
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm forward: one warp per row; the row lives in registers between the two statistics passes.
+// LayerNorm forward: one warp per row, R rows per warp iteration.  All 16-byte loads of the R rows (x and the optional
+// residual post-adds) are issued before the first reduction, so each lane keeps R*NV*(1..3) loads in flight -- the
+// kernel is HBM-bound and a single row per warp (1 KB in flight) left the memory pipe mostly idle.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int NV>
-__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+template <int VN>
+__device__ __forceinline__ void load_param(const float* __restrict__ p, float (&f)[VN]) {
+#pragma unroll
+  for (int j = 0; j < VN; j += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p + j));
+    f[j] = t.x; f[j + 1] = t.y; f[j + 2] = t.z; f[j + 3] = t.w;
+  }
+}
+
+template <typename T, int NV, int R>
+__global__ void __launch_bounds__(256, (NV <= 2 ? 2 : 1)) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, const T* __restrict__ post1,
                                                             const T* __restrict__ post2, T* __restrict__ y,
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out,
@@ -20,55 +31,89 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int nvec = H / VN;
-  for (long long row = warp0; row < rows; row += nwarps) {
-    const T* xr = x + row * H;
-    float v[NV][VN];
-    float s = 0.f;
+  const float inv_h = 1.f / H;
+  for (long long row0 = warp0 * R; row0 < rows; row0 += nwarps * R) {
+    Vec16<T> raw[R][NV], p1[R][NV], p2[R][NV];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = lane + i * 32;
+        if (row0 + r < rows && vi < nvec) {
+          const long long off = (row0 + r) * H + vi * VN;
+          raw[r][i].load(x + off);
+          if (post1) p1[r][i].load(post1 + off);
+          if (post2) p2[r][i].load(post2 + off);
+        }
+      }
+    float v[R][NV][VN], mean[R], rstd[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (row0 + r < rows && lane + i * 32 < nvec) {
+          raw[r][i].unpack(v[r][i]);
+#pragma unroll
+          for (int j = 0; j < VN; ++j) s += v[r][i][j];
+        }
+      mean[r] = s;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) mean[r] = warp_sum(mean[r]) * inv_h;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (row0 + r < rows && lane + i * 32 < nvec) {
+#pragma unroll
+          for (int j = 0; j < VN; ++j) { const float d = v[r][i][j] - mean[r]; q += d * d; }
+        }
+      rstd[r] = q;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(warp_sum(rstd[r]) * inv_h + eps);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
-        Vec16<T> t; t.load(xr + vi * VN); t.unpack(v[i]);
+        float gm[VN], bt[VN];
+        load_param<VN>(gamma + vi * VN, gm);
+        load_param<VN>(beta + vi * VN, bt);
 #pragma unroll
-        for (int j = 0; j < VN; ++j) s += v[i][j];
+        for (int r = 0; r < R; ++r)
+          if (row0 + r < rows) {
+            float o[VN];
+#pragma unroll
+            for (int j = 0; j < VN; ++j) o[j] = (v[r][i][j] - mean[r]) * rstd[r] * gm[j] + bt[j];
+            if (post1) {
+              float f[VN]; p1[r][i].unpack(f);
+#pragma unroll
+              for (int j = 0; j < VN; ++j) o[j] += f[j];
+            }
+            if (post2) {
+              float f[VN]; p2[r][i].unpack(f);
+#pragma unroll
+              for (int j = 0; j < VN; ++j) o[j] += f[j];
+            }
+            Vec16<T> t; t.pack(o); t.store(y + (row0 + r) * H + vi * VN);
+          }
       }
     }
-    const float mean = warp_sum(s) / H;
-    float q = 0.f;
+    if (lane < R && row0 + lane < rows) {
+      float m = mean[0], s = rstd[0];
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-      if (lane + i * 32 < nvec) {
-#pragma unroll
-        for (int j = 0; j < VN; ++j) { const float d = v[i][j] - mean; q += d * d; }
-      }
-    const float rstd = rsqrtf(warp_sum(q) / H + eps);
-    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = lane + i * 32;
-      if (vi < nvec) {
-        float o[VN];
-#pragma unroll
-        for (int j = 0; j < VN; ++j) o[j] = (v[i][j] - mean) * rstd * gamma[vi * VN + j] + beta[vi * VN + j];
-        if (post1) {
-          Vec16<T> t; t.load(post1 + row * H + vi * VN); float f[VN]; t.unpack(f);
-#pragma unroll
-          for (int j = 0; j < VN; ++j) o[j] += f[j];
-        }
-        if (post2) {
-          Vec16<T> t; t.load(post2 + row * H + vi * VN); float f[VN]; t.unpack(f);
-#pragma unroll
-          for (int j = 0; j < VN; ++j) o[j] += f[j];
-        }
-        Vec16<T> t; t.pack(o); t.store(y + row * H + vi * VN);
-      }
+      for (int r = 1; r < R; ++r) if (lane == r) { m = mean[r]; s = rstd[r]; }
+      mean_out[row0 + lane] = m; rstd_out[row0 + lane] = s;
     }
   }
 }
 
 // LayerNorm backward: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma  (+ dres);
 // dgamma/dbeta: per-lane register partials over the warp's rows -> shared atomics -> global atomics.
-template <typename T, int NV>
+// R rows per warp iteration with every load issued up front, as in the forward kernel.
+template <typename T, int NV, int R>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                             const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                             const float* __restrict__ gamma, const T* __restrict__ dres,
@@ -82,55 +127,78 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int nvec = H / VN;
+  const float inv_h = 1.f / H;
   float pg[NV][VN], pb[NV][VN], gm[NV][VN], px[NV][VN];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
 #pragma unroll
-    for (int j = 0; j < VN; ++j) { pg[i][j] = 0.f; pb[i][j] = 0.f; px[i][j] = 0.f; gm[i][j] = vi < nvec ? gamma[vi * VN + j] : 0.f; }
+    for (int j = 0; j < VN; ++j) { pg[i][j] = 0.f; pb[i][j] = 0.f; px[i][j] = 0.f; gm[i][j] = 0.f; }
+    if (vi < nvec) load_param<VN>(gamma + vi * VN, gm[i]);
   }
-  for (long long row = warp0; row < rows; row += nwarps) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[NV][VN], g[NV][VN];
-    float s1 = 0.f, s2 = 0.f;
+  for (long long row0 = warp0 * R; row0 < rows; row0 += nwarps * R) {
+    Vec16<T> rdy[R][NV], rx[R][NV], rres[R][NV];
+    float mean[R], rstd[R];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = lane + i * 32;
-      if (vi < nvec) {
-        Vec16<T> a, b; a.load(dy + row * H + vi * VN); b.load(x + row * H + vi * VN);
-        float d[VN], xv[VN]; a.unpack(d); b.unpack(xv);
+    for (int r = 0; r < R; ++r) {
+      const bool ok = row0 + r < rows;
+      mean[r] = ok ? mean_in[row0 + r] : 0.f;
+      rstd[r] = ok ? rstd_in[row0 + r] : 0.f;
 #pragma unroll
-        for (int j = 0; j < VN; ++j) {
-          xh[i][j] = (xv[j] - mean) * rstd;
-          g[i][j] = d[j] * gm[i][j];
-          s1 += g[i][j];
-          s2 += g[i][j] * xh[i][j];
-          pg[i][j] += d[j] * xh[i][j];
-          pb[i][j] += d[j];
+      for (int i = 0; i < NV; ++i) {
+        const int vi = lane + i * 32;
+        if (ok && vi < nvec) {
+          const long long off = (row0 + r) * H + vi * VN;
+          rdy[r][i].load(dy + off);
+          rx[r][i].load(x + off);
+          if (dres) rres[r][i].load(dres + off);
         }
       }
     }
-    const float c1 = warp_sum(s1) / H, c2 = warp_sum(s2) / H;
+    float xh[R][NV][VN], g[R][NV][VN], c1[R], c2[R];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = lane + i * 32;
-      if (vi < nvec) {
-        float o[VN];
+    for (int r = 0; r < R; ++r) {
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < VN; ++j) o[j] = rstd * (g[i][j] - c1 - xh[i][j] * c2);
-        if (dres) {
-          Vec16<T> t; t.load(dres + row * H + vi * VN); float f[VN]; t.unpack(f);
+      for (int i = 0; i < NV; ++i)
+        if (row0 + r < rows && lane + i * 32 < nvec) {
+          float d[VN], xv[VN]; rdy[r][i].unpack(d); rx[r][i].unpack(xv);
 #pragma unroll
-          for (int j = 0; j < VN; ++j) o[j] += f[j];
+          for (int j = 0; j < VN; ++j) {
+            xh[r][i][j] = (xv[j] - mean[r]) * rstd[r];
+            g[r][i][j] = d[j] * gm[i][j];
+            s1 += g[r][i][j];
+            s2 += g[r][i][j] * xh[r][i][j];
+            pg[i][j] += d[j] * xh[r][i][j];
+            pb[i][j] += d[j];
+          }
         }
-        Vec16<T> t; t.pack(o); t.store(dx + row * H + vi * VN);
-        if (dxsum) {            // sum what was stored (rounded to T), so it equals a column sum over the dx tensor
-          float q[VN]; t.unpack(q);
+      c1[r] = s1; c2[r] = s2;
+    }
 #pragma unroll
-          for (int j = 0; j < VN; ++j) px[i][j] += q[j];
+    for (int r = 0; r < R; ++r) { c1[r] = warp_sum(c1[r]) * inv_h; c2[r] = warp_sum(c2[r]) * inv_h; }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = lane + i * 32;
+        if (row0 + r < rows && vi < nvec) {
+          float o[VN];
+#pragma unroll
+          for (int j = 0; j < VN; ++j) o[j] = rstd[r] * (g[r][i][j] - c1[r] - xh[r][i][j] * c2[r]);
+          if (dres) {
+            float f[VN]; rres[r][i].unpack(f);
+#pragma unroll
+            for (int j = 0; j < VN; ++j) o[j] += f[j];
+          }
+          Vec16<T> t; t.pack(o); t.store(dx + (row0 + r) * H + vi * VN);
+          if (dxsum) {            // sum what was stored (rounded to T), so it equals a column sum over the dx tensor
+            float q[VN]; t.unpack(q);
+#pragma unroll
+            for (int j = 0; j < VN; ++j) px[i][j] += q[j];
+          }
         }
       }
-    }
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -450,10 +518,11 @@ int b200f_layernorm_fwd(const void* x, const float* gamma, const float* beta, co
     B200F_REQUIRE(H % VN == 0 && H > 0, B200F_ERR_SHAPE, "layernorm: H=%d must be a multiple of %d", H, VN);
     B200F_REQUIRE(aligned16(x) && aligned16(y) && aligned16(post1) && aligned16(post2), B200F_ERR_ALIGN, "layernorm: 16-byte alignment");
     const int need = (H / VN + 31) / 32;
-    const long long blocks = (rows + 7) / 8;
-    const int grid = int(blocks < (long long)num_sms() * 8 ? blocks : (long long)num_sms() * 8);
     DISPATCH_NV(need, NV, {
-      layernorm_fwd_kernel<T, NV><<<grid, 256, 0, st>>>(static_cast<const T*>(x), gamma, beta, static_cast<const T*>(post1),
+      constexpr int R = NV <= 2 ? 2 : 1;
+      const long long blocks = (rows + 8 * R - 1) / (8 * R);
+      const int grid = int(blocks < (long long)num_sms() * 8 ? blocks : (long long)num_sms() * 8);
+      layernorm_fwd_kernel<T, NV, R><<<grid, 256, 0, st>>>(static_cast<const T*>(x), gamma, beta, static_cast<const T*>(post1),
                                                          static_cast<const T*>(post2), static_cast<T*>(y), mean, rstd, rows, H, eps);
     })
   })
@@ -469,10 +538,11 @@ int b200f_layernorm_bwd(const void* dy, const void* x, const float* mean, const 
     B200F_REQUIRE(H % VN == 0 && H > 0, B200F_ERR_SHAPE, "layernorm: H=%d must be a multiple of %d", H, VN);
     B200F_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(dres), B200F_ERR_ALIGN, "layernorm: 16-byte alignment");
     const int need = (H / VN + 31) / 32;
-    const long long blocks = (rows + 7) / 8;
-    const int grid = int(blocks < (long long)num_sms() * 4 ? blocks : (long long)num_sms() * 4);
     DISPATCH_NV(need, NV, {
-      layernorm_bwd_kernel<T, NV><<<grid, 256, 3 * H * sizeof(float), st>>>(static_cast<const T*>(dy), static_cast<const T*>(x), mean, rstd, gamma,
+      constexpr int R = NV <= 2 ? 2 : 1;
+      const long long blocks = (rows + 8 * R - 1) / (8 * R);
+      const int grid = int(blocks < (long long)num_sms() * 4 ? blocks : (long long)num_sms() * 4);
+      layernorm_bwd_kernel<T, NV, R><<<grid, 256, 3 * H * sizeof(float), st>>>(static_cast<const T*>(dy), static_cast<const T*>(x), mean, rstd, gamma,
                                                                             static_cast<const T*>(dres), static_cast<T*>(dx), dgamma, dbeta, dxsum, rows, H);
     })
   })

@@ -46,7 +46,7 @@ GEMM_PROFILE = None          # None, or a list collecting (start_event, stop_eve
 def gemm(a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_layout: int = 0, b_layout: int = 0,
          out: Optional[Tensor] = None, bias: Optional[Tensor] = None, residual: Optional[Tensor] = None,
          relu_mask: Optional[Tensor] = None, relu: bool = False, alpha: float = 1.0, accumulate: bool = False,
-         out_f32: bool = False, split_k: int = 1) -> Tensor:
+         out_f32: bool = False, split_k: int = 1, colsum: Optional[Tensor] = None) -> Tensor:
     """C[M,N] = epi(alpha * sum_k A(m,k) B(n,k)); see b200f_gemm in include/b200_fusion.h.
     `a`/`b` are 2-D views (row stride = leading dimension)."""
     require_cuda(a, b, out, bias, residual, relu_mask)
@@ -71,6 +71,8 @@ def gemm(a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_layout: int = 0, b_l
         flags |= L.EPI_OUT_F32
     if bias is not None and bias.dtype != torch.float32:
         raise B200FusionError("gemm: bias must be float32")
+    if colsum is not None and (colsum.dtype != torch.float32 or not colsum.is_contiguous() or colsum.numel() != N or want_f32 and dt != torch.float32):
+        raise B200FusionError("gemm: colsum must be a contiguous float32 [N] accumulator and the output must be in the operand dtype")
     for name, t in (("residual", residual), ("relu_mask", relu_mask)):
         if t is not None and t.dtype != dt:
             raise B200FusionError(f"gemm: {name} dtype must match the operands")
@@ -82,7 +84,8 @@ def gemm(a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_layout: int = 0, b_l
                       ldr=0 if residual is None else residual.stride(0),
                       relu_mask=None if relu_mask is None else relu_mask.data_ptr(),
                       ldm=0 if relu_mask is None else relu_mask.stride(0),
-                      alpha=alpha, flags=flags, dtype=dtype_code(dt), split_k=split_k)
+                      alpha=alpha, flags=flags, dtype=dtype_code(dt), split_k=split_k,
+                      colsum=None if colsum is None else colsum.data_ptr())
     if GEMM_PROFILE is None:
         check(lib().b200f_gemm(C.byref(args), stream_ptr()), "b200f_gemm")
         return out
@@ -107,10 +110,11 @@ def linear_fwd(x2: Tensor, w: Tensor, bias: Optional[Tensor], *, relu=False, res
     return gemm(x2, w, M=M, N=w.size(0), K=K, out=out, bias=bias, residual=residual, relu=relu)
 
 
-def linear_dgrad(dy2: Tensor, w: Tensor, *, relu_mask=None, residual=None, out=None) -> Tensor:
-    """dx[M,K] = dy2[M,N] w[N,K]  (B operand N-contiguous: no transposed weight copy)."""
+def linear_dgrad(dy2: Tensor, w: Tensor, *, relu_mask=None, residual=None, out=None, colsum=None) -> Tensor:
+    """dx[M,K] = dy2[M,N] w[N,K]  (B operand N-contiguous: no transposed weight copy).
+    `colsum` [K] fp32 += column sums of dx: the bias gradient of the Linear that produced this GEMM's input activation."""
     M, N = dy2.shape
-    return gemm(dy2, w, M=M, N=w.size(1), K=N, a_layout=0, b_layout=1, out=out, relu_mask=relu_mask, residual=residual)
+    return gemm(dy2, w, M=M, N=w.size(1), K=N, a_layout=0, b_layout=1, out=out, relu_mask=relu_mask, residual=residual, colsum=colsum)
 
 
 def linear_wgrad(dy2: Tensor, x2: Tensor, dw: Tensor) -> Tensor:
@@ -255,7 +259,13 @@ def attn_fwd(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float, out: Opt
 
 
 def attn_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor, heads: int, scale: float,
-             dq: Tensor, dk: Tensor, dv: Tensor) -> None:
+             dq: Tensor, dk: Tensor, dv: Tensor, dbq: Optional[Tensor] = None, dbk: Optional[Tensor] = None,
+             dbv: Optional[Tensor] = None) -> None:
+    """dq/dk/dv <- attention backward.  dbq/dbk/dbv (optional fp32 [H*D] views, contiguous) are INCREMENTED by the column sums
+    of dq/dk/dv over all tokens: the bias gradients of the producing projections, summed in the kernels' epilogue."""
+    for t in (dbq, dbk, dbv):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != q.size(2)):
+            raise B200FusionError("attn_bwd: bias-gradient accumulators must be contiguous float32 [H*D]")
     B, Lq, W = q.shape
     Lk = k.size(1)
     D = W // heads
@@ -264,7 +274,9 @@ def attn_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor
     (gp, ldg), (dqp, lddq), (dkp, lddk), (dvp, lddv) = _tokens(do), _tokens(dq), _tokens(dk), _tokens(dv)
     args = L.AttnArgs(B=B, H=heads, Lq=Lq, Lk=Lk, D=D, Q=qp, ldq=ldq, K=kp, ldk=ldk, V=vp, ldv=ldv, O=op, ldo=ldo,
                       LSE=lse.data_ptr(), scale=scale, dtype=dtype_code(q.dtype), dO=gp, lddo=ldg, dQ=dqp, lddq=lddq,
-                      dK=dkp, lddk=lddk, dV=dvp, lddv=lddv, delta=delta.data_ptr())
+                      dK=dkp, lddk=lddk, dV=dvp, lddv=lddv, delta=delta.data_ptr(),
+                      dbq=None if dbq is None else dbq.data_ptr(), dbk=None if dbk is None else dbk.data_ptr(),
+                      dbv=None if dbv is None else dbv.data_ptr())
     check(lib().b200f_attn_bwd(C.byref(args), stream_ptr()), "b200f_attn_bwd")
 
 

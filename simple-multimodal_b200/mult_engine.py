@@ -144,11 +144,11 @@ def _chunk_backward(st, W: _Weights, H: int, heads: int, dpooled: Tensor, G: Dic
         d_att = K.meanpool_bwd(d_pc, Ls[m])
         dqkv = torch.empty_like(s["qkv"])
         qkv = s["qkv"]
-        K.attn_bwd(d_att, qkv[:, :, :H], qkv[:, :, H:2 * H], qkv[:, :, 2 * H:], s["att"], s["lse"], heads, scale,
-                   dqkv[:, :, :H], dqkv[:, :, H:2 * H], dqkv[:, :, 2 * H:])
+        db = G[pre + "in_proj_bias"]        # Q / V bias gradients are summed in the attention-backward epilogue; the K-bias
+        K.attn_bwd(d_att, qkv[:, :, :H], qkv[:, :, H:2 * H], qkv[:, :, 2 * H:], s["att"], s["lse"], heads, scale,   # gradient is
+                   dqkv[:, :, :H], dqkv[:, :, H:2 * H], dqkv[:, :, 2 * H:], dbq=db[:H], dbv=db[2 * H:])            # identically 0 (softmax shift invariance)
         dqkv2 = dqkv.view(-1, 3 * H)
         K.linear_wgrad(dqkv2, s["enh"], G[pre + "in_proj_weight"])
-        K.colsum_accum(dqkv2, G[pre + "in_proj_bias"])
         d_enh[m] = K.linear_dgrad(dqkv2, W.w(pre + "in_proj_weight"))
     dproj = [torch.empty_like(p) for p in proj]
     d_s1 = {}
@@ -158,9 +158,9 @@ def _chunk_backward(st, W: _Weights, H: int, heads: int, dpooled: Tensor, G: Dic
         ds2 = K.layernorm_bwd(d_enh[qm], s["s2"], s["mean2"], s["rstd2"], W.f32(f"{name}.norm2.weight"),
                               G[f"{name}.norm2.weight"], G[f"{name}.norm2.bias"], dxsum=G[f"{name}.ffn.3.bias"])   # + bias grad of FFN2
         K.linear_wgrad(ds2, s["hid"], G[f"{name}.ffn.3.weight"])
-        dhid = K.linear_dgrad(ds2, W.w(f"{name}.ffn.3.weight"), relu_mask=s["hid"])        # ReLU' fused in the epilogue
+        dhid = K.linear_dgrad(ds2, W.w(f"{name}.ffn.3.weight"), relu_mask=s["hid"],       # ReLU' and the FFN1 bias gradient
+                              colsum=G[f"{name}.ffn.0.bias"])                                # (column sums) fused in the epilogue
         K.linear_wgrad(dhid, s["x1"], G[f"{name}.ffn.0.weight"])
-        K.colsum_accum(dhid, G[f"{name}.ffn.0.bias"])
         dx1 = K.linear_dgrad(dhid, W.w(f"{name}.ffn.0.weight"), residual=ds2)             # + residual path x1 -> s2
         ds1 = K.layernorm_bwd(dx1, s["s1"], s["mean1"], s["rstd1"], W.f32(f"{name}.norm1.weight"),
                               G[f"{name}.norm1.weight"], G[f"{name}.norm1.bias"], dxsum=G[f"{name}.attention.out_proj.bias"])
@@ -170,12 +170,12 @@ def _chunk_backward(st, W: _Weights, H: int, heads: int, dpooled: Tensor, G: Dic
         dctx = K.linear_dgrad(ds1, W.w(f"{name}.attention.out_proj.weight")).view(Bc, Ls[qm], H)
         qo, ko = W.q_slot[name], W.kv_slot[name]
         K.attn_bwd(dctx, proj[qm][:, :, qo:qo + H], proj[km][:, :, ko:ko + H], proj[km][:, :, ko + H:ko + 2 * H], s["ctx"], s["lse"],
-                   heads, scale, dproj[qm][:, :, qo:qo + H], dproj[km][:, :, ko:ko + H], dproj[km][:, :, ko + H:ko + 2 * H])
+                   heads, scale, dproj[qm][:, :, qo:qo + H], dproj[km][:, :, ko:ko + H], dproj[km][:, :, ko + H:ko + 2 * H],
+                   dbq=dstack_b[qm][qo:qo + H], dbv=dstack_b[km][ko + H:ko + 2 * H])
     dxs = []
     for m in range(3):
         dp2 = dproj[m].view(-1, 6 * H)
         K.linear_wgrad(dp2, x2[m], dstack_w[m])
-        K.colsum_accum(dp2, dstack_b[m])
         if need_dx:
             a_name, b_name = [n for n, qm, _ in BLOCKS if qm == m]
             direct = K.add(d_enh[m], d_s1[a_name], d_s1[b_name])      # residual paths into the input

@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
 pkg = importlib.import_module("simple-multimodal_b200")
 K = pkg.kernels
 
-SHAPES = [(2, 8, 512, 512), (3, 8, 512, 30), (3, 8, 30, 512), (2, 8, 100, 200), (1, 8, 128, 128), (2, 8, 1, 1), (1, 8, 257, 129)]
+SHAPES = [(2, 8, 512, 512), (3, 8, 512, 30), (3, 8, 30, 512), (2, 8, 100, 200), (1, 8, 128, 128), (2, 8, 1, 1), (1, 8, 257, 129),
+          (40, 8, 512, 512), (150, 8, 30, 30), (2, 8, 640, 384)]      # > 148 work items per kernel: several items per persistent CTA
 
 
 def reference(q, k, v, heads, scale):
@@ -38,10 +39,23 @@ def packed(B, L, width, dtype, seed):
     return torch.randn(B, L, width, device="cuda", generator=g).to(dtype)
 
 
+@pytest.fixture(params=[0, 1], ids=["persistent", "tile-per-cta"])
+def tc_variant(request):
+    """both generations of the tcgen05 kernels: b200f_debug_set(4 / 5, v) selects the forward / backward variant"""
+    lib = pkg._lib.lib()
+    lib.b200f_debug_set(4, 2 if request.param == 0 else 1)
+    lib.b200f_debug_set(5, request.param)
+    yield request.param
+    lib.b200f_debug_set(4, 0)
+    lib.b200f_debug_set(5, 0)
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
 @pytest.mark.parametrize("shape", SHAPES)
-def test_attention_forward_backward(shape, dtype):
+def test_attention_forward_backward(shape, dtype, tc_variant):
     B, heads, Lq, Lk = shape
+    if dtype == torch.float32 and (tc_variant == 1 or B > 3):
+        pytest.skip("the CUDA-core fp32 path has one variant; large batches are covered in bf16")
     W = heads * 64
     scale = 1 / math.sqrt(64)
     pq = packed(B, Lq, 2 * W, dtype, 1)                     # Q lives in columns [W, 2W) of a wider projection
@@ -57,13 +71,18 @@ def test_attention_forward_backward(shape, dtype):
     do = packed(B, Lq, W, dtype, 3)
     (o_ref * do.double()).sum().backward()
     dpq, dpkv = torch.zeros_like(pq), torch.zeros_like(pkv)
-    K.attn_bwd(do, q, k, v, o, lse, heads, scale, dpq[:, :, W:], dpkv[:, :, :W], dpkv[:, :, 2 * W:])
+    db = torch.ones(3, W, device="cuda", dtype=torch.float32)          # accumulators: the kernels ADD the column sums
+    K.attn_bwd(do, q, k, v, o, lse, heads, scale, dpq[:, :, W:], dpkv[:, :, :W], dpkv[:, :, 2 * W:], dbq=db[0], dbk=db[1], dbv=db[2])
     torch.cuda.synchronize()
     gt = 1e-5 if dtype == torch.float32 else 2e-2
     assert rel(dpq[:, :, W:], qd.grad) < gt, f"dQ {rel(dpq[:, :, W:], qd.grad)}"
     assert rel(dpkv[:, :, :W], kd.grad) < gt, f"dK {rel(dpkv[:, :, :W], kd.grad)}"
     assert rel(dpkv[:, :, 2 * W:], vd.grad) < gt, f"dV {rel(dpkv[:, :, 2 * W:], vd.grad)}"
     assert float(dpq[:, :, :W].abs().max()) == 0 and float(dpkv[:, :, W:2 * W].abs().max()) == 0     # untouched slices
+    # fused bias gradients == column sums of the stored gradients (fp32 accumulation of the rounded values)
+    for acc, grad in ((db[0], dpq[:, :, W:]), (db[1], dpkv[:, :, :W]), (db[2], dpkv[:, :, 2 * W:])):
+        want = grad.double().sum(dim=(0, 1)) + 1.0
+        assert float((acc.double() - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max())) + 1e-3 * float(grad.float().abs().max())
 
 
 def test_attention_tc_matches_cuda_core_path():

@@ -101,6 +101,24 @@ def test_gemm_weight_grad_accumulate_split_k(dtype):
     assert rel_err(acc - 1.0, ref) < 1e-5
 
 
+@pytest.mark.parametrize("dtype,shape", [(torch.bfloat16, (1000, 512, 256)), (torch.bfloat16, (4133, 2048, 512)), (torch.bfloat16, (300, 264, 192)),
+                                         (torch.bfloat16, (77, 128, 64)), (torch.float32, (300, 264, 192))])
+def test_gemm_fused_column_sums(dtype, shape):
+    """colsum[n] += sum_m C[m,n] of the STORED output (bias gradient fused in the epilogue; N % 64 != 0 and fp32 take
+    the GEMM + column-sum-kernel route inside the library).  With the ReLU-mask epilogue, as the FFN2 input-gradient GEMM uses it."""
+    K = importlib.import_module("simple-multimodal_b200.kernels")
+    M, N, Kd = shape
+    A, B, ref = make_operands(M, N, Kd, 0, 1, dtype, seed=6)
+    mask = torch.randn(M, N, device="cuda").to(dtype)
+    acc = torch.full((N,), 2.0, device="cuda")
+    out = K.gemm(A, B, M=M, N=N, K=Kd, a_layout=0, b_layout=1, relu_mask=mask, colsum=acc)
+    torch.cuda.synchronize()
+    want = ref * (mask.float() > 0)
+    assert rel_err(out, want) < (2e-6 if dtype == torch.float32 else 5e-3)
+    sums = out.double().sum(0) + 2.0
+    assert float((acc.double() - sums).abs().max()) <= 1e-5 * float(out.float().abs().sum(0).max()) + 1e-4
+
+
 def test_gemm_ragged_bf16_uses_cuda_cores():
     """Leading dimensions that are not 16-byte multiples (7-class logits, 3 gate logits) cannot go through TMA."""
     M, N, K = 130, 7, 512

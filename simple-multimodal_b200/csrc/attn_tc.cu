@@ -279,7 +279,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 // TMEM: S_0 [0,128) S_1 [128,256) O_0 [256,320) O_1 [320,384).  A work item = (batch, head, 256-query block).
 // ------------------------------------------------------------------------------------------------
 static constexpr int F2_THREADS = 384;     // warps 0-3 softmax warpgroup 0, 4-7 warpgroup 1, 8 TMA, 9 MMA, 10-11 idle (complete the third warpgroup)
-static constexpr int SOFTMAX_REGS = 224, IO_REGS = 56;   // setmaxnreg: 256 x 224 + 128 x 56 = 384 x 168 (the launch allocation)
+static constexpr int SOFTMAX_REGS = 216, IO_REGS = 72;   // setmaxnreg: 256 x 216 + 128 x 72 = 384 x 168 (the launch allocation)
 static constexpr int F2_ST = 3;      // K/V ring depth
 struct Fwd2Smem {
   static constexpr int Q_OFF = 0;                              // 2 x [128 x 64] bf16, K-major SW128
@@ -299,9 +299,11 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint64_t* q_empty = bars + 1;
   uint64_t* kv_full = bars + 2;               // [F2_ST]
   uint64_t* kv_empty = kv_full + F2_ST;       // [F2_ST]
-  uint64_t* s_full = kv_empty + F2_ST;        // [2]  S_t(j) complete (and every earlier MMA, incl. PV_t(j-1))
-  uint64_t* p_ready = s_full + 2;             // [2]  P_t(j) in smem, S_t(j) consumed, O_t rescaled
-  uint64_t* o_full = p_ready + 2;             // [2]  last PV_t of the item complete
+  uint64_t* s_full = kv_empty + F2_ST;        // [2]  S_t(j) complete
+  uint64_t* s_free = s_full + 2;              // [2]  S_t(j) is in the softmax warps' registers: the MMA warp may overwrite it with S_t(j+1)
+  uint64_t* p_ready = s_free + 2;             // [2]  P_t(j) in smem, O_t rescaled
+  uint64_t* pv_done = p_ready + 2;            // [2]  PV_t(j) retired (j < last): O_t and the P_t tile belong to the softmax warps again
+  uint64_t* o_full = pv_done + 2;             // [2]  last PV_t of the item complete
   uint64_t* o_empty = o_full + 2;             // [2]  epilogue has read O_t
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
 
@@ -313,7 +315,10 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
     mbar_init(q_full, 1); mbar_init(q_empty, 1);
     for (int i = 0; i < F2_ST; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_ready[t], 4); mbar_init(&o_full[t], 1); mbar_init(&o_empty[t], 4); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 4); mbar_init(&p_ready[t], 4); mbar_init(&pv_done[t], 1);
+      mbar_init(&o_full[t], 1); mbar_init(&o_empty[t], 4);
+    }
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc<512>(tmem_slot);
@@ -349,7 +354,21 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, TK, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(TQ, HD, 0, 1);
-      uint32_t g = 0, it = 0, pr_cnt[2] = {0, 0}, o_cnt[2] = {0, 0};
+      uint32_t g = 0, it = 0, pr_cnt[2] = {0, 0}, o_cnt[2] = {0, 0}, s_cnt[2] = {0, 0};
+      // S_t(j+1) is issued as soon as the softmax warps hold S_t(j) in registers (s_free), i.e. it runs under their exp work;
+      // PV_t(j) follows when P_t(j) is in smem.  Order on the tensor pipe per key tile: S_0(j+1) S_1(j+1) PV_0(j) PV_1(j).
+      // low descriptor words of the resident operands (see umma_lo): K-major tiles step 32 B (2 units) per K=16, the
+      // MN-major V tile steps 16 key rows = 2048 B (128 units); stages / tiles are (bytes >> 4) apart
+      const uint32_t q_lo = umma_lo(smem_u32(smem + Fwd2Smem::Q_OFF), 16), k_lo = umma_lo(smem_u32(smem + Fwd2Smem::K_OFF), 16);
+      const uint32_t v_lo = umma_lo(smem_u32(smem + Fwd2Smem::V_OFF), TK * 128), p_lo = umma_lo(smem_u32(smem + Fwd2Smem::P_OFF), 16);
+      constexpr uint32_t TILE16 = TQ * HD * 2 / 16, PT16 = TQ * TK * 2 / 16;
+      auto issue_s = [&](int t, int st) {
+        mbar_wait(&s_free[t], (s_cnt[t] & 1) ^ 1);     // first use passes immediately
+        ++s_cnt[t];
+        tc_fence_after();
+        umma_chain<HD / 16>(tmem_base + t * TK, q_lo + t * TILE16, 2, k_lo + st * TILE16, 2, idesc_s, 0);
+        umma_commit(&s_full[t]);
+      };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int qb = item % n_qblk;
         const int nt = (qb * 2 * TQ + TQ < p.Lq) ? 2 : 1;
@@ -358,24 +377,17 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           const int st = g % F2_ST;
           mbar_wait(&kv_full[st], (g / F2_ST) & 1);
           tc_fence_after();
-          const uint32_t sk = smem_u32(smem + Fwd2Smem::K_OFF + st * TK * HD * 2);
-          for (int t = 0; t < nt; ++t) {
-            const uint32_t sq = smem_u32(smem + Fwd2Smem::Q_OFF + t * TQ * HD * 2);
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k)
-              umma_ss(tmem_base + t * TK, umma_desc(sq + k * 32, 16, 1024), umma_desc(sk + k * 32, 16, 1024), idesc_s, k > 0);
-            umma_commit(&s_full[t]);
-          }
+          for (int t = 0; t < nt; ++t) issue_s(t, st);
           if (n_tiles == 1) umma_commit(q_empty);
         }
         for (int j = 0; j < n_tiles; ++j) {
           const int st = (g + j) % F2_ST;
-          const uint32_t sv = smem_u32(smem + Fwd2Smem::V_OFF + st * TK * HD * 2);
-          uint32_t sk_next = 0;
           if (j + 1 < n_tiles) {
             const int stn = (g + j + 1) % F2_ST;
             mbar_wait(&kv_full[stn], ((g + j + 1) / F2_ST) & 1);
-            sk_next = smem_u32(smem + Fwd2Smem::K_OFF + stn * TK * HD * 2);
+            tc_fence_after();
+            for (int t = 0; t < nt; ++t) issue_s(t, stn);
+            if (j + 2 == n_tiles) umma_commit(q_empty);
           }
           const int ksteps = (min(TK, p.Lk - j * TK) + 15) >> 4;   // P columns past ceil32(valid) are never written
           for (int t = 0; t < nt; ++t) {
@@ -383,24 +395,23 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             ++pr_cnt[t];
             if (j == 0) mbar_wait(&o_empty[t], (o_cnt[t] & 1) ^ 1);   // the previous item's epilogue has drained O_t
             tc_fence_after();
-            const uint32_t sp = smem_u32(smem + Fwd2Smem::P_OFF + t * TQ * TK * 2);
             const uint32_t t_o = tmem_base + 2 * TK + t * HD;
-            for (int k = 0; k < ksteps; ++k)
-              umma_ss(t_o, umma_desc(sp + (k >> 2) * (TQ * 128) + (k & 3) * 32, 16, 1024), umma_desc(sv + k * 2048, TK * 128, 1024), idesc_o,
-                      (j > 0 || k > 0) ? 1u : 0u);
+            const uint32_t pa = p_lo + t * PT16, vb = v_lo + st * TILE16;     // P: two K-major halves of 64 keys, (TQ * 128) B apart
+            if (ksteps == 8) {
+              umma_chain<4>(t_o, pa, 2, vb, 128, idesc_o, j > 0);
+              umma_chain<4>(t_o, pa + TQ * 128 / 16, 2, vb + 4 * 128, 128, idesc_o, 1);
+            } else {
+              for (int k = 0; k < ksteps; ++k)
+                umma_ss(t_o, umma_desc_lo(pa + (k >> 2) * (TQ * 128 / 16) + (k & 3) * 2), umma_desc_lo(vb + k * 128), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+            }
             if (j + 1 < n_tiles) {
-              const uint32_t sq = smem_u32(smem + Fwd2Smem::Q_OFF + t * TQ * HD * 2);
-#pragma unroll
-              for (int k = 0; k < HD / 16; ++k)
-                umma_ss(tmem_base + t * TK, umma_desc(sq + k * 32, 16, 1024), umma_desc(sk_next + k * 32, 16, 1024), idesc_s, k > 0);
-              umma_commit(&s_full[t]);
+              umma_commit(&pv_done[t]);
             } else {
               umma_commit(&o_full[t]);
               ++o_cnt[t];
             }
           }
           umma_commit(&kv_empty[st]);
-          if (j + 2 == n_tiles) umma_commit(q_empty);
         }
         g += n_tiles;
       }
@@ -417,14 +428,14 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const float c = p.scale * LOG2E;
     const uint64_t c2 = f2_pack(c, c);
     uint8_t* prow = smem + Fwd2Smem::P_OFF + t * TQ * TK * 2;
-    uint32_t sf_cnt = 0, o_cnt = 0;
+    uint32_t sf_cnt = 0, o_cnt = 0, pv_cnt = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int qb = item % n_qblk, h = (item / n_qblk) % p.H, b = item / (n_qblk * p.H);
       const int q0 = qb * 2 * TQ + t * TQ;
       if (q0 >= p.Lq) continue;                      // this warpgroup's tile does not exist (the MMA warp skips it too)
       float m = -INFINITY, l = 0.f;                  // m: reference max the stored P / O are scaled against (raw score units)
       for (int j = 0; j < n_tiles; ++j) {
-        mbar_wait(&s_full[t], sf_cnt & 1);           // also implies PV_t(j-1) retired: O_t and the P_t tile are ours again
+        mbar_wait(&s_full[t], sf_cnt & 1);
         ++sf_cnt;
         tc_fence_after();
         const int valid = min(TK, p.Lk - j * TK);    // keys beyond Lk were zero-filled by TMA: mask them
@@ -437,6 +448,9 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         for (int q = 0; q < 4; ++q)
           if (q * 32 < cols) tmem_ld32(t_s + lane_addr + q * 32, r[q]);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);        // S_t is in registers: the next S_t may be computed under this tile's softmax
         float tmax = -INFINITY, tmax_b = -INFINITY;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -461,6 +475,11 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const float nmc = -m_use * c;
         const uint64_t nmc2 = f2_pack(nmc, nmc);
         uint64_t lsum2 = 0ull;
+        if (j > 0) {                                   // PV_t(j-1) must have retired before P_t is overwritten / O_t rescaled
+          mbar_wait(&pv_done[t], pv_cnt & 1);
+          ++pv_cnt;
+          tc_fence_after();
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           if (q * 32 < cols) {
@@ -892,6 +911,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 // ------------------------------------------------------------------------------------------------
 static constexpr int B2_THREADS = 384;     // warps 0-3 warpgroup 0, 4-7 warpgroup 1, 8 TMA, 9 MMA, 10-11 idle
 static constexpr int B2_ST = 3;
+static constexpr int B2_SOFTMAX_REGS = 200, B2_IO_REGS = 104;   // 256 x 200 + 128 x 104 = 384 x 168: the MMA issuer must not spill
 
 struct Dq2Smem {
   static constexpr int Q_OFF = 0;                              // 2 x [128 x 64]
@@ -914,10 +934,11 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   uint64_t* q_empty = bars + 1;
   uint64_t* kv_full = bars + 2;               // [B2_ST]
   uint64_t* kv_empty = kv_full + B2_ST;       // [B2_ST]
-  uint64_t* sdp_full = kv_empty + B2_ST;      // [2]  S_t(j), dP_t(j) complete (and every earlier MMA, incl. dQ_t(j-1))
-  uint64_t* ds_ready = sdp_full + 2;          // [2]  dS_t(j) in smem, S_t / dP_t consumed
-  uint64_t* dq_full = ds_ready + 2;           // [2]  last dQ_t MMA of the item complete
-  uint64_t* dq_empty = dq_full + 2;           // [2]  epilogue has read dQ_t
+  uint64_t* sdp_full = kv_empty + B2_ST;      // [2]  S_t(j), dP_t(j) complete
+  uint64_t* sdp_free = sdp_full + 2;          // [2]  S_t(j), dP_t(j) are in the softmax warps' registers: the MMA warp may overwrite them
+  uint64_t* ds_ready = sdp_free + 2;          // [2]  dS_t(j) in smem
+  uint64_t* ds_free = ds_ready + 2;           // [2]  dQ_t(j) MMAs retired: the dS_t tile may be rewritten; the last one of an item = dQ_t complete
+  uint64_t* dq_empty = ds_free + 2;           // [2]  epilogue has read dQ_t
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.Lk + BT - 1) / BT;
@@ -927,7 +948,9 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
     mbar_init(q_full, 1); mbar_init(q_empty, 1);
     for (int i = 0; i < B2_ST; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(&sdp_full[t], 1); mbar_init(&ds_ready[t], 4); mbar_init(&dq_full[t], 1); mbar_init(&dq_empty[t], 4); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&sdp_full[t], 1); mbar_init(&sdp_free[t], 4); mbar_init(&ds_ready[t], 4); mbar_init(&ds_free[t], 1); mbar_init(&dq_empty[t], 4);
+    }
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc<512>(tmem_slot);
@@ -937,7 +960,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 8) {
-  setmaxnreg_dec<IO_REGS>();
+  setmaxnreg_dec<B2_IO_REGS>();
   if (warp == 8) {
     if (lane == 0) {
       uint32_t g = 0, it = 0;
@@ -967,14 +990,22 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, BT, 0, 0);     // S = Q K^T, dP = dO V^T   (N = 64 keys)
       constexpr uint32_t idesc_dq = umma_idesc_bf16(TQ, HD, 0, 1);    // dQ += dS K             (K MN-major, N = d)
-      uint32_t g = 0, it = 0, ds_cnt[2] = {0, 0}, dq_cnt[2] = {0, 0};
-      auto issue_sdp = [&](int t, uint32_t sk, uint32_t sv) {
-        const uint32_t sq = smem_u32(smem + Dq2Smem::Q_OFF + t * TQ * HD * 2), sdo = smem_u32(smem + Dq2Smem::DO_OFF + t * TQ * HD * 2);
-        const uint32_t t_s = tmem_base + t * 192, t_dp = t_s + 64;
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_ss(t_s, umma_desc(sq + k * 32, 16, 1024), umma_desc(sk + k * 32, 16, 1024), idesc_s, k > 0);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_ss(t_dp, umma_desc(sdo + k * 32, 16, 1024), umma_desc(sv + k * 32, 16, 1024), idesc_s, k > 0);
+      uint32_t g = 0, it = 0, ds_cnt[2] = {0, 0}, dq_cnt[2] = {0, 0}, sdp_cnt[2] = {0, 0};
+      // S_t / dP_t of key tile j+1 are issued as soon as tile j sits in the softmax warps' registers (sdp_free) and run under
+      // their exp work; dQ_t(j) follows when dS_t(j) is in smem.
+      // low descriptor words (umma_lo): K-major operands step 2 units (32 B) per K=16; K as the MN-major B operand of the dQ
+      // MMA steps 16 key rows = 2048 B = 128 units
+      const uint32_t q_lo = umma_lo(smem_u32(smem + Dq2Smem::Q_OFF), 16), do_lo = umma_lo(smem_u32(smem + Dq2Smem::DO_OFF), 16);
+      const uint32_t k_lo = umma_lo(smem_u32(smem + Dq2Smem::K_OFF), 16), v_lo = umma_lo(smem_u32(smem + Dq2Smem::V_OFF), 16);
+      const uint32_t kmn_lo = umma_lo(smem_u32(smem + Dq2Smem::K_OFF), BT * 128), ds_lo = umma_lo(smem_u32(smem + Dq2Smem::DS_OFF), 16);
+      constexpr uint32_t QT16 = TQ * HD * 2 / 16, KT16 = BT * HD * 2 / 16, DST16 = TQ * BT * 2 / 16;
+      auto issue_sdp = [&](int t, int st) {
+        mbar_wait(&sdp_free[t], (sdp_cnt[t] & 1) ^ 1);   // first use passes immediately
+        ++sdp_cnt[t];
+        tc_fence_after();
+        const uint32_t t_s = tmem_base + t * 192;
+        umma_chain<HD / 16>(t_s, q_lo + t * QT16, 2, k_lo + st * KT16, 2, idesc_s, 0);
+        umma_chain<HD / 16>(t_s + 64, do_lo + t * QT16, 2, v_lo + st * KT16, 2, idesc_s, 0);
         umma_commit(&sdp_full[t]);
       };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -985,39 +1016,27 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           const int st = g % B2_ST;
           mbar_wait(&kv_full[st], (g / B2_ST) & 1);
           tc_fence_after();
-          for (int t = 0; t < nt; ++t)
-            issue_sdp(t, smem_u32(smem + Dq2Smem::K_OFF + st * BT * HD * 2), smem_u32(smem + Dq2Smem::V_OFF + st * BT * HD * 2));
+          for (int t = 0; t < nt; ++t) issue_sdp(t, st);
           if (n_tiles == 1) umma_commit(q_empty);
         }
         for (int j = 0; j < n_tiles; ++j) {
           const int st = (g + j) % B2_ST;
-          const uint32_t sk = smem_u32(smem + Dq2Smem::K_OFF + st * BT * HD * 2);
-          uint32_t sk_next = 0, sv_next = 0;
           if (j + 1 < n_tiles) {
             const int stn = (g + j + 1) % B2_ST;
             mbar_wait(&kv_full[stn], ((g + j + 1) / B2_ST) & 1);
-            sk_next = smem_u32(smem + Dq2Smem::K_OFF + stn * BT * HD * 2);
-            sv_next = smem_u32(smem + Dq2Smem::V_OFF + stn * BT * HD * 2);
+            tc_fence_after();
+            for (int t = 0; t < nt; ++t) issue_sdp(t, stn);
+            if (j + 2 == n_tiles) umma_commit(q_empty);
           }
           for (int t = 0; t < nt; ++t) {
             mbar_wait(&ds_ready[t], ds_cnt[t] & 1);
             ++ds_cnt[t];
-            if (j == 0) mbar_wait(&dq_empty[t], (dq_cnt[t] & 1) ^ 1);   // the previous item's epilogue has drained dQ_t
+            if (j == 0) { mbar_wait(&dq_empty[t], (dq_cnt[t] & 1) ^ 1); ++dq_cnt[t]; }   // the previous item's epilogue has drained dQ_t
             tc_fence_after();
-            const uint32_t sds = smem_u32(smem + Dq2Smem::DS_OFF + t * TQ * BT * 2);
-            const uint32_t t_dq = tmem_base + t * 192 + 128;
-#pragma unroll
-            for (int k = 0; k < BT / 16; ++k)
-              umma_ss(t_dq, umma_desc(sds + k * 32, 16, 1024), umma_desc(sk + k * 2048, BT * 128, 1024), idesc_dq, (j > 0 || k > 0) ? 1u : 0u);
-            if (j + 1 < n_tiles) {
-              issue_sdp(t, sk_next, sv_next);
-            } else {
-              umma_commit(&dq_full[t]);
-              ++dq_cnt[t];
-            }
+            umma_chain<BT / 16>(tmem_base + t * 192 + 128, ds_lo + t * DST16, 2, kmn_lo + st * KT16, 128, idesc_dq, j > 0);
+            umma_commit(&ds_free[t]);
           }
           umma_commit(&kv_empty[st]);
-          if (j + 2 == n_tiles) umma_commit(q_empty);
         }
         g += n_tiles;
       }
@@ -1025,7 +1044,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     __syncwarp();
   }
   } else {
-    setmaxnreg_inc<SOFTMAX_REGS>();
+    setmaxnreg_inc<B2_SOFTMAX_REGS>();
     const int t = warp >> 2;
     const int grp = warp & 3;
     const int row = grp * 32 + lane;
@@ -1034,7 +1053,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     uint8_t* ds_tile = smem + Dq2Smem::DS_OFF + t * TQ * BT * 2;
     const float c = p.scale * LOG2E;
     const uint64_t c2 = f2_pack(c, c), sc2 = f2_pack(p.scale, p.scale);
-    uint32_t sf_cnt = 0, dq_cnt = 0;
+    uint32_t sf_cnt = 0, dsf_cnt = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int qb = item % n_qblk, h = (item / n_qblk) % p.H, b = item / (n_qblk * p.H);
       const int q0 = qb * 2 * TQ + t * TQ;
@@ -1045,7 +1064,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       const float ndl = -(qrow < p.Lq ? p.delta[ri] : 0.f) * p.scale;
       const uint64_t nlse22 = f2_pack(nlse2, nlse2), ndl2 = f2_pack(ndl, ndl);
       for (int j = 0; j < n_tiles; ++j) {
-        mbar_wait(&sdp_full[t], sf_cnt & 1);         // also implies dQ_t(j-1) retired: the dS_t tile is ours again
+        mbar_wait(&sdp_full[t], sf_cnt & 1);
         ++sf_cnt;
         tc_fence_after();
         uint32_t rs[2][32], rp[2][32];               // the whole 64-key row of S and dP: four loads in flight, one wait
@@ -1054,6 +1073,13 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         tmem_ld32(t_s + lane_addr + 32, rs[1]);
         tmem_ld32(t_dp + lane_addr + 32, rp[1]);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sdp_free[t]);      // the next S_t / dP_t may be computed under this tile's exp work
+        if (j > 0) {                                   // dQ_t(j-1) must have retired before the dS_t tile is rewritten
+          mbar_wait(&ds_free[t], dsf_cnt & 1);
+          ++dsf_cnt;
+        }
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           uint32_t pk[16];
@@ -1074,8 +1100,8 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(&ds_ready[t]);
       }
-      mbar_wait(&dq_full[t], dq_cnt & 1);
-      ++dq_cnt;
+      mbar_wait(&ds_free[t], dsf_cnt & 1);           // the item's last dQ_t MMA
+      ++dsf_cnt;
       tc_fence_after();
       // the dS_t tile is free once the last dQ_t MMA retired: stage dQ through this warp's 4 KB slice of it
       store_rows64(t_dq + lane_addr, ds_tile + grp * (32 * 128), p.dQ + ((long long)b * p.Lq + q0 + grp * 32) * p.lddq + h * HD, p.lddq,
@@ -1113,10 +1139,11 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint64_t* kv_empty = bars + 1;
   uint64_t* q_full = bars + 2;                // [B2_ST]
   uint64_t* q_empty = q_full + B2_ST;         // [B2_ST]
-  uint64_t* sdp_full = q_empty + B2_ST;       // [2]
-  uint64_t* ds_ready = sdp_full + 2;          // [2]
-  uint64_t* acc_full = ds_ready + 2;          // [2]
-  uint64_t* acc_empty = acc_full + 2;         // [2]
+  uint64_t* sdp_full = q_empty + B2_ST;       // [2]  S^T_t(i), dP^T_t(i) complete
+  uint64_t* sdp_free = sdp_full + 2;          // [2]  ... and in the softmax warps' registers: may be overwritten
+  uint64_t* ds_ready = sdp_free + 2;          // [2]  P^T_t(i), dS^T_t(i) in smem
+  uint64_t* ds_free = ds_ready + 2;           // [2]  dV_t / dK_t MMAs of tile i retired (the last one of an item = accumulators complete)
+  uint64_t* acc_empty = ds_free + 2;          // [2]  epilogue has read dV_t / dK_t
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.Lq + BT - 1) / BT;
@@ -1126,7 +1153,9 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
     mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
     for (int i = 0; i < B2_ST; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(&sdp_full[t], 1); mbar_init(&ds_ready[t], 4); mbar_init(&acc_full[t], 1); mbar_init(&acc_empty[t], 4); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&sdp_full[t], 1); mbar_init(&sdp_free[t], 4); mbar_init(&ds_ready[t], 4); mbar_init(&ds_free[t], 1); mbar_init(&acc_empty[t], 4);
+    }
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc<512>(tmem_slot);
@@ -1136,7 +1165,7 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 8) {
-  setmaxnreg_dec<IO_REGS>();
+  setmaxnreg_dec<B2_IO_REGS>();
   if (warp == 8) {
     if (lane == 0) {
       uint32_t g = 0, it = 0;
@@ -1166,14 +1195,21 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(TK, BT, 0, 0);     // S^T = K Q^T, dP^T = V dO^T   (N = 64 queries)
       constexpr uint32_t idesc_acc = umma_idesc_bf16(TK, HD, 0, 1);   // dV += P^T dO, dK += dS^T Q   (B MN-major, N = d)
-      uint32_t g = 0, it = 0, ds_cnt[2] = {0, 0}, acc_cnt[2] = {0, 0};
-      auto issue_sdp = [&](int t, uint32_t sq, uint32_t sdo) {
-        const uint32_t sk = smem_u32(smem + Dkv2Smem::K_OFF + t * TK * HD * 2), sv = smem_u32(smem + Dkv2Smem::V_OFF + t * TK * HD * 2);
-        const uint32_t t_s = tmem_base + t * 256, t_dp = t_s + 64;
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_ss(t_s, umma_desc(sk + k * 32, 16, 1024), umma_desc(sq + k * 32, 16, 1024), idesc_s, k > 0);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_ss(t_dp, umma_desc(sv + k * 32, 16, 1024), umma_desc(sdo + k * 32, 16, 1024), idesc_s, k > 0);
+      uint32_t g = 0, it = 0, ds_cnt[2] = {0, 0}, acc_cnt[2] = {0, 0}, sdp_cnt[2] = {0, 0};
+      // low descriptor words (umma_lo): K-major operands step 2 units (32 B) per K=16; Q / dO as MN-major B operands of the
+      // accumulation MMAs step 16 query rows = 2048 B = 128 units
+      const uint32_t k_lo = umma_lo(smem_u32(smem + Dkv2Smem::K_OFF), 16), v_lo = umma_lo(smem_u32(smem + Dkv2Smem::V_OFF), 16);
+      const uint32_t q_lo = umma_lo(smem_u32(smem + Dkv2Smem::Q_OFF), 16), do_lo = umma_lo(smem_u32(smem + Dkv2Smem::DO_OFF), 16);
+      const uint32_t qmn_lo = umma_lo(smem_u32(smem + Dkv2Smem::Q_OFF), BT * 128), domn_lo = umma_lo(smem_u32(smem + Dkv2Smem::DO_OFF), BT * 128);
+      const uint32_t p_lo = umma_lo(smem_u32(smem + Dkv2Smem::P_OFF), 16), ds_lo = umma_lo(smem_u32(smem + Dkv2Smem::DS_OFF), 16);
+      constexpr uint32_t KT16 = TK * HD * 2 / 16, QT16 = BT * HD * 2 / 16, PT16 = TK * BT * 2 / 16;
+      auto issue_sdp = [&](int t, int st) {
+        mbar_wait(&sdp_free[t], (sdp_cnt[t] & 1) ^ 1);   // first use passes immediately
+        ++sdp_cnt[t];
+        tc_fence_after();
+        const uint32_t t_s = tmem_base + t * 256;
+        umma_chain<HD / 16>(t_s, k_lo + t * KT16, 2, q_lo + st * QT16, 2, idesc_s, 0);
+        umma_chain<HD / 16>(t_s + 64, v_lo + t * KT16, 2, do_lo + st * QT16, 2, idesc_s, 0);
         umma_commit(&sdp_full[t]);
       };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -1184,42 +1220,29 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const int st = g % B2_ST;
           mbar_wait(&q_full[st], (g / B2_ST) & 1);
           tc_fence_after();
-          for (int t = 0; t < nt; ++t)
-            issue_sdp(t, smem_u32(smem + Dkv2Smem::Q_OFF + st * BT * HD * 2), smem_u32(smem + Dkv2Smem::DO_OFF + st * BT * HD * 2));
+          for (int t = 0; t < nt; ++t) issue_sdp(t, st);
           if (n_tiles == 1) umma_commit(kv_empty);
         }
         for (int i = 0; i < n_tiles; ++i) {
           const int st = (g + i) % B2_ST;
-          const uint32_t sq = smem_u32(smem + Dkv2Smem::Q_OFF + st * BT * HD * 2), sdo = smem_u32(smem + Dkv2Smem::DO_OFF + st * BT * HD * 2);
-          uint32_t sq_next = 0, sdo_next = 0;
-          if (i + 1 < n_tiles) {
+          if (i + 1 < n_tiles) {                       // run ahead: next query tile's S^T / dP^T under this tile's exp work
             const int stn = (g + i + 1) % B2_ST;
             mbar_wait(&q_full[stn], ((g + i + 1) / B2_ST) & 1);
-            sq_next = smem_u32(smem + Dkv2Smem::Q_OFF + stn * BT * HD * 2);
-            sdo_next = smem_u32(smem + Dkv2Smem::DO_OFF + stn * BT * HD * 2);
+            tc_fence_after();
+            for (int t = 0; t < nt; ++t) issue_sdp(t, stn);
+            if (i + 2 == n_tiles) umma_commit(kv_empty);
           }
           for (int t = 0; t < nt; ++t) {
             mbar_wait(&ds_ready[t], ds_cnt[t] & 1);
             ++ds_cnt[t];
-            if (i == 0) mbar_wait(&acc_empty[t], (acc_cnt[t] & 1) ^ 1);
+            if (i == 0) { mbar_wait(&acc_empty[t], (acc_cnt[t] & 1) ^ 1); ++acc_cnt[t]; }
             tc_fence_after();
-            const uint32_t sp = smem_u32(smem + Dkv2Smem::P_OFF + t * TK * BT * 2), sds = smem_u32(smem + Dkv2Smem::DS_OFF + t * TK * BT * 2);
-            const uint32_t t_dv = tmem_base + t * 256 + 128, t_dk = t_dv + 64;
-#pragma unroll
-            for (int k = 0; k < BT / 16; ++k)
-              umma_ss(t_dv, umma_desc(sp + k * 32, 16, 1024), umma_desc(sdo + k * 2048, BT * 128, 1024), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-            for (int k = 0; k < BT / 16; ++k)
-              umma_ss(t_dk, umma_desc(sds + k * 32, 16, 1024), umma_desc(sq + k * 2048, BT * 128, 1024), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
-            if (i + 1 < n_tiles) {
-              issue_sdp(t, sq_next, sdo_next);
-            } else {
-              umma_commit(&acc_full[t]);
-              ++acc_cnt[t];
-            }
+            const uint32_t t_dv = tmem_base + t * 256 + 128;
+            umma_chain<BT / 16>(t_dv, p_lo + t * PT16, 2, domn_lo + st * QT16, 128, idesc_acc, i > 0);
+            umma_chain<BT / 16>(t_dv + 64, ds_lo + t * PT16, 2, qmn_lo + st * QT16, 128, idesc_acc, i > 0);
+            umma_commit(&ds_free[t]);
           }
           umma_commit(&q_empty[st]);
-          if (i + 2 == n_tiles) umma_commit(kv_empty);
         }
         g += n_tiles;
       }
@@ -1227,7 +1250,7 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     __syncwarp();
   }
   } else {
-    setmaxnreg_inc<SOFTMAX_REGS>();
+    setmaxnreg_inc<B2_SOFTMAX_REGS>();
     const int t = warp >> 2;
     const int grp = warp & 3;
     const int row = grp * 32 + lane;                 // key row of the tile == TMEM lane
@@ -1239,7 +1262,7 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     float* stats = reinterpret_cast<float*>(smem + Dkv2Smem::STAT_OFF) + t * (2 * 2 * BT);
     const float c = p.scale * LOG2E;
     const uint64_t c2 = f2_pack(c, c), sc2 = f2_pack(p.scale, p.scale);
-    uint32_t sf_cnt = 0, acc_cnt = 0;
+    uint32_t sf_cnt = 0, dsf_cnt = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int kb = item % n_kblk, h = (item / n_kblk) % p.H, b = item / (n_kblk * p.H);
       const int k0 = kb * 2 * TK + t * TK;
@@ -1254,7 +1277,7 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           sl[t128] = v;
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
-        mbar_wait(&sdp_full[t], sf_cnt & 1);         // implies the previous tile's dV/dK MMAs (reading P^T/dS^T) retired
+        mbar_wait(&sdp_full[t], sf_cnt & 1);
         ++sf_cnt;
         tc_fence_after();
         uint32_t rs[2][32], rp[2][32];               // the whole 64-query row of S^T and dP^T: four loads in flight, one wait
@@ -1263,6 +1286,13 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         tmem_ld32(t_s + lane_addr + 32, rs[1]);
         tmem_ld32(t_dp + lane_addr + 32, rp[1]);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sdp_free[t]);      // the next S^T_t / dP^T_t may be computed under this tile's exp work
+        if (i > 0) {                                   // dV_t / dK_t MMAs of the previous tile must have retired before P^T / dS^T are rewritten
+          mbar_wait(&ds_free[t], dsf_cnt & 1);
+          ++dsf_cnt;
+        }
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           uint32_t pp[16], pd[16];
@@ -1290,8 +1320,8 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(&ds_ready[t]);
       }
-      mbar_wait(&acc_full[t], acc_cnt & 1);
-      ++acc_cnt;
+      mbar_wait(&ds_free[t], dsf_cnt & 1);           // the item's last accumulation MMAs
+      ++dsf_cnt;
       tc_fence_after();
       // P^T / dS^T tiles are free once the last accumulation MMA retired: stage dV / dK through this warp's slices of them
       store_rows64(t_dv + lane_addr, p_tile + grp * (32 * 128), p.dV + ((long long)b * p.Lk + k0 + grp * 32) * p.lddv + h * HD, p.lddv,

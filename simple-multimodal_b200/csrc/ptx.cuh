@@ -117,6 +117,36 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Cheap descriptor arithmetic for issue loops that are bound by the single issuing thread (attention: N = 64 MMAs retire in
+// 32 cycles, so ~40 integer instructions per MMA to rebuild two descriptors starve the tensor pipe).  The high word of a
+// SW128 descriptor with SBO = 1024 is a constant; the low word is (addr >> 4) | (LBO >> 4) << 16, so advancing an operand
+// by `bytes` is one integer add of bytes >> 4 on the low word.
+constexpr uint32_t kDescHiSw128Sbo1024 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ uint64_t umma_desc_lo(uint32_t lo) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(kDescHiSw128Sbo1024));
+  return r;
+}
+// D[tmem] += A * B (always accumulates: no predicate set-up)
+__device__ __forceinline__ void umma_ss_acc(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc)
+      : "memory");
+}
+// NSTEP K=16 steps of one accumulation: operand low words advance by a_step / b_step (in 16-byte units) per step; the first
+// step overwrites the accumulator unless `acc_first`.
+template <int NSTEP>
+__device__ __forceinline__ void umma_chain(uint32_t d_tmem, uint32_t a_lo, uint32_t a_step, uint32_t b_lo, uint32_t b_step, uint32_t idesc,
+                                           uint32_t acc_first) {
+  umma_ss(d_tmem, umma_desc_lo(a_lo), umma_desc_lo(b_lo), idesc, acc_first);
+#pragma unroll
+  for (int k = 1; k < NSTEP; ++k) umma_ss_acc(d_tmem, umma_desc_lo(a_lo + k * a_step), umma_desc_lo(b_lo + k * b_step), idesc);
+}
+
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

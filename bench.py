@@ -62,6 +62,12 @@ class Cfg:
     contrastive_temperature = 0.07
 
 
+def gemm_traffic():
+    """DRAM bytes of one launch of the dominant kernel, from the committed `ncu --set full` capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -295,6 +301,7 @@ def main():
 
     if rank == 0:
         pk = peaks()
+        traffic = gemm_traffic()
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         gflop = algorithmic_gflop_per_sample(kind, lens, b_global)
         line = {
@@ -312,7 +319,10 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all layouts)", "achieved": achieved, "peak": pk["tflops"],
-                         "unit": "TFLOP/s", "frac": achieved / pk["tflops"] if pk["tflops"] else None, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / pk["tflops"] if pk["tflops"] else None,
+                         "traffic": (traffic or {}).get("traffic_bytes_per_launch"),
+                         "traffic_launch": None if traffic is None else f'{traffic["kernel"]}: {traffic["launch"]}; algorithmic bytes '
+                                                                          f'{traffic["algorithmic_bytes_per_launch"]} ({traffic["source"]})',
                          "peak_source": pk["src"], "launches_per_step": n_gemm, "kernel_ms_per_step": gemm_ms,
                          "share_of_step": gemm_ms / ms if ms else None},
         }

@@ -10,6 +10,7 @@ from ._lib import B200FusionError, LIB_PATH                              # noqa:
 from .fusion_layers import (AdaptiveFusion, ContrastiveFusion, CrossModalTransformer, EarlyFusion, GraphFusion,   # noqa: F401
                             HierarchicalFusion, LateFusion, ModalityDropout, MultimodalTransformer)
 from .ops import allreduce_gradients, manual_seed                        # noqa: F401
+from .staging import FeaturePrefetcher                                   # noqa: F401
 
 __all__ = ["EarlyFusion", "LateFusion", "MultimodalTransformer", "CrossModalTransformer", "GraphFusion", "ContrastiveFusion",
-           "AdaptiveFusion", "HierarchicalFusion", "ModalityDropout", "allreduce_gradients", "manual_seed", "B200FusionError"]
+           "AdaptiveFusion", "HierarchicalFusion", "ModalityDropout", "allreduce_gradients", "manual_seed", "FeaturePrefetcher", "B200FusionError"]

@@ -179,7 +179,7 @@ class MultimodalTransformer(_FusionBase):
     """reference models/fusion_layers.py:93-179, executed by mult_engine.MulTFn (chunked, fused schedule)."""
 
     chunk_size = 256            # samples per MulT chunk (~7.4 GB of bf16 activations at L=512/512/30, H=512)
-    stash_fraction = 0.55       # share of the currently free device memory that forward may keep resident for backward
+    stash_fraction = 0.72       # share of the currently free device memory that forward may keep resident for backward
 
     def __init__(self, config):
         super().__init__()
@@ -203,7 +203,9 @@ class MultimodalTransformer(_FusionBase):
                                   "use fusion_dropout=0 or eval() (no silent fallback)")
         params = dict(self.named_parameters())
         H, heads = self.config.fusion_hidden_size, self.config.fusion_num_heads
+        # memory the stash may use: what the driver reports free plus what torch's caching allocator holds but has not handed out
         free_bytes, _ = torch.cuda.mem_get_info(t.device)
+        free_bytes += torch.cuda.memory_reserved(t.device) - torch.cuda.memory_allocated(t.device)
         budget = int(self.stash_fraction * free_bytes) if torch.is_grad_enabled() else 0
         return mult_engine.MulTFn.apply(t, a, v, H, heads, int(self.chunk_size), budget, self._names, *[params[n] for n in self._names])
 

@@ -77,6 +77,9 @@ typedef struct {
   int32_t flags;                        /* B200F_EPI_*                                           */
   int32_t dtype;                        /* b200f_dtype of A, B, residual, relu_mask (and C)      */
   int32_t split_k;                      /* >1 only with B200F_EPI_ACCUM; 0/1 = none              */
+  /* inverted dropout on the output after bias/residual/ReLU (nn.Dropout behind a Linear+ReLU, fusion_layers.py:197-199):
+   * element (m, n) kept iff the counter-based hash of (seed, m, n) passes, kept values scaled by 1/(1-p); 0 = off */
+  float dropout_p; uint32_t drop_seed_lo, drop_seed_hi;
   float* colsum;                        /* optional [N] fp32 accumulator: += column sums of the
                                            stored C (the bias gradient of the Linear whose output
                                            gradient C is, e.g. ffn.0.bias from the FFN2 input-gradient
@@ -110,6 +113,11 @@ typedef struct {
    * the bias gradients of the projections that produced Q / K / V (in_proj_bias of
    * nn.MultiheadAttention, torch nn/functional.py:5740-5760) -- fused into the backward epilogue */
   float* dbq; float* dbk; float* dbv;
+  /* dropout on the attention probabilities (nn.MultiheadAttention(dropout=p) in training mode, torch nn/functional.py
+   * 6647-6650): kept entries are scaled by 1/(1-p); the mask is regenerated from (drop_seed_lo, drop_seed_hi) by forward
+   * and backward (counter-based hash of (b, head, query, key), see csrc/common.cuh) -- pass the same values to both.
+   * dropout_p = 0 disables it.  LSE is the log-sum-exp of the UNdropped scores. */
+  float dropout_p; uint32_t drop_seed_lo, drop_seed_hi;
 } b200f_attn_args;
 int b200f_attn_fwd(const b200f_attn_args* args, void* stream);
 int b200f_attn_bwd(const b200f_attn_args* args, void* stream);
@@ -181,19 +189,25 @@ int b200f_infonce_grad(const void* x, const void* y, const float* lse_x, const f
 /* GATConv core on dense 3-node graphs (fusion_layers.py:267-282 + PyG GATConv semantics,
  * SURVEY 8c): xp [B,3,heads*C] (the `lin` projection), att_src/att_dst [heads*C], bias [C]
  *   out[b,i,:] = relu( mean_h sum_j softmax_j(leaky_relu(a_src[j,h]+a_dst[i,h])) xp[b,j,h,:] + bias )
- * alpha [B,3(i),heads,3(j)] fp32 is saved for backward. */
+ * alpha [B,3(i),heads,3(j)] fp32 (the softmax output) is saved for backward.  dropout_p > 0: GATConv(dropout=p) in training
+ * mode drops the attention coefficients before aggregation (kept / (1-p)); the mask is regenerated from the seed pair. */
 int b200f_gat_fwd(const void* xp, const float* att_src, const float* att_dst, const float* bias, void* out,
-                  float* alpha, int64_t B, int32_t heads, int32_t C, float slope, int32_t dtype, void* stream);
+                  float* alpha, int64_t B, int32_t heads, int32_t C, float slope, float dropout_p, uint32_t seed_lo,
+                  uint32_t seed_hi, int32_t dtype, void* stream);
 int b200f_gat_bwd(const void* dout, const void* out, const void* xp, const float* alpha, const float* att_src,
                   const float* att_dst, void* dxp, float* datt_src, float* datt_dst, float* dbias, int64_t B,
-                  int32_t heads, int32_t C, float slope, int32_t dtype, void* stream);
+                  int32_t heads, int32_t C, float slope, float dropout_p, uint32_t seed_lo, uint32_t seed_hi, int32_t dtype,
+                  void* stream);
 /* Attention over the 3 modality tokens (AdaptiveFusion, fusion_layers.py:432-434): qkv [B,3,3H]
  * packed projections -> ctx [B,3,H], probs [B,heads,3,3] fp32 (saved), head-averaged weights
- * avgw [B,3,3] fp32 (returned to the caller, torch/nn/functional.py:6657-6659). */
+ * avgw [B,3,3] fp32 (returned to the caller, torch/nn/functional.py:6657-6659).  dropout_p > 0: the weights are dropped
+ * (kept / (1-p)) before P V and before the head average, as nn.MultiheadAttention(dropout=p) does in training mode;
+ * probs stays the softmax output and the mask is regenerated from the seed pair in backward. */
 int b200f_tok3_attn_fwd(const void* qkv, void* ctx, float* probs, float* avgw, int64_t B, int32_t heads, int32_t H,
-                        float scale, int32_t dtype, void* stream);
+                        float scale, float dropout_p, uint32_t seed_lo, uint32_t seed_hi, int32_t dtype, void* stream);
 int b200f_tok3_attn_bwd(const void* dctx, const float* davgw, const void* qkv, const float* probs, void* dqkv,
-                        int64_t B, int32_t heads, int32_t H, float scale, int32_t dtype, void* stream);
+                        int64_t B, int32_t heads, int32_t H, float scale, float dropout_p, uint32_t seed_lo,
+                        uint32_t seed_hi, int32_t dtype, void* stream);
 /* Gated mix (fusion_layers.py:437-443): gate = softmax(logits[B,3]); mixed = sum_m att[b,m,:]*gate[b,m]. */
 int b200f_gate_mix_fwd(const void* att, const void* logits, float* gate, void* mixed, int64_t B, int32_t H,
                        int32_t dtype, void* stream);
@@ -211,6 +225,10 @@ int b200f_modality_mask(float* mask, int64_t B, float rate, uint64_t seed, uint6
 /* Inverted dropout with a counter-based RNG (nn.Dropout on the path): y = x * keep / (1-p);
  * the same (seed, offset) regenerates the mask in backward. */
 int b200f_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset, int32_t dtype, void* stream);
+/* In-place inverted dropout of an [M, N] activation (row stride ldx) with the mask b200f_gemm's dropout epilogue generates:
+ * element (m, n) kept iff the counter-based hash of (seed_lo, seed_hi, m, n) passes (csrc/common.cuh). */
+int b200f_dropout_rowcol(void* x, int64_t ldx, int64_t M, int64_t N, float p, uint32_t seed_lo, uint32_t seed_hi, int32_t dtype,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -31,6 +31,7 @@ class GemmArgs(C.Structure):
                 ("residual", C.c_void_p), ("ldr", C.c_int64),
                 ("relu_mask", C.c_void_p), ("ldm", C.c_int64),
                 ("alpha", C.c_float), ("flags", C.c_int32), ("dtype", C.c_int32), ("split_k", C.c_int32),
+                ("dropout_p", C.c_float), ("drop_seed_lo", C.c_uint32), ("drop_seed_hi", C.c_uint32),
                 ("colsum", C.c_void_p)]
 
 
@@ -46,7 +47,8 @@ class AttnArgs(C.Structure):
                 ("dK", C.c_void_p), ("lddk", C.c_int64),
                 ("dV", C.c_void_p), ("lddv", C.c_int64),
                 ("delta", C.c_void_p),
-                ("dbq", C.c_void_p), ("dbk", C.c_void_p), ("dbv", C.c_void_p)]
+                ("dbq", C.c_void_p), ("dbk", C.c_void_p), ("dbv", C.c_void_p),
+                ("dropout_p", C.c_float), ("drop_seed_lo", C.c_uint32), ("drop_seed_hi", C.c_uint32)]
 
 
 _lib = None

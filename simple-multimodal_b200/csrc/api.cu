@@ -63,15 +63,22 @@ int b200f_gemm(const b200f_gemm_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a->colsum && (a->flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) && a->dtype == B200F_BF16)
     return b200f::fail(B200F_ERR_UNSUPPORTED, "gemm: colsum needs the output in the operand dtype");
-  if (a->dtype == B200F_BF16 && b200f::gemm_tc_eligible(*a) && (!a->colsum || b200f::gemm_tc_colsum_fused(*a)))
-    return b200f::gemm_bf16_tc(*a, st);                       // column sums (if any) come out of the epilogue
-  b200f_gemm_args plain = *a;                                // other paths: GEMM, then one pass over the stored C
+  if (!(a->dropout_p >= 0.f && a->dropout_p < 1.f)) return b200f::fail(B200F_ERR_SHAPE, "gemm: dropout_p=%f not in [0,1)", a->dropout_p);
+  const bool extras = a->colsum || a->dropout_p > 0.f;
+  if (a->dropout_p > 0.f && (a->flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) && a->dtype == B200F_BF16)
+    return b200f::fail(B200F_ERR_UNSUPPORTED, "gemm: dropout needs the output in the operand dtype");
+  if (a->dtype == B200F_BF16 && b200f::gemm_tc_eligible(*a) && (!extras || b200f::gemm_tc_colsum_fused(*a)))
+    return b200f::gemm_bf16_tc(*a, st);                       // dropout / column sums (if any) come out of the epilogue
+  b200f_gemm_args plain = *a;                                // other paths: GEMM, then one pass each over the stored C
   plain.colsum = nullptr;
+  plain.dropout_p = 0.f;
   int rc;
   if (a->dtype == B200F_BF16) rc = b200f::gemm_tc_eligible(plain) ? b200f::gemm_bf16_tc(plain, st) : b200f::gemm_bf16_simt(plain, st);
   else if (a->dtype == B200F_F32) rc = b200f::gemm_f32_simt(plain, st);
   else return b200f::fail(B200F_ERR_DTYPE, "gemm: unknown dtype %d", a->dtype);
-  if (rc || !a->colsum) return rc;
+  if (rc) return rc;
+  if (a->dropout_p > 0.f && (rc = b200f_dropout_rowcol(a->C, a->ldc, a->M, a->N, a->dropout_p, a->drop_seed_lo, a->drop_seed_hi, a->dtype, stream))) return rc;
+  if (!a->colsum) return B200F_OK;
   return b200f_colsum_accum(a->C, a->ldc, a->colsum, a->M, a->N, a->dtype, stream);
 }
 
@@ -103,6 +110,7 @@ static int attn_check(const b200f_attn_args* a) {
   B200F_REQUIRE(a->B >= 0 && a->H > 0 && a->Lq > 0 && a->Lk > 0 && a->D > 0, B200F_ERR_SHAPE, "attention: bad shape B=%d H=%d Lq=%d Lk=%d D=%d", a->B,
                 a->H, a->Lq, a->Lk, a->D);
   B200F_REQUIRE(a->dtype == B200F_F32 || a->dtype == B200F_BF16, B200F_ERR_DTYPE, "attention: unknown dtype %d", a->dtype);
+  B200F_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, B200F_ERR_SHAPE, "attention: dropout_p=%f not in [0,1)", a->dropout_p);
   return B200F_OK;
 }
 }  // namespace b200f

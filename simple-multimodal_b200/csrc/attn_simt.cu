@@ -18,6 +18,8 @@ struct AttnP {
   float* LSE;
   float* delta;
   float scale;
+  uint32_t drop_thr, drop_seed_lo, drop_seed_hi;   // attention-probability dropout (0 = off), same mask as the tcgen05 kernels
+  float inv_keep;
 };
 
 template <typename T>
@@ -58,6 +60,10 @@ __global__ void __launch_bounds__(128) attn_fwd_simt(const AttnP p) {
     sum += e;
   }
   sum = warp_sum(sum);
+  if (p.drop_thr) {                                  // mask what multiplies V; the row sum stays that of the undropped scores
+    const uint32_t rk = drop_row_key(p.drop_seed_lo, p.drop_seed_hi, uint32_t(gw));
+    for (int j = lane; j < p.Lk; j += 32) sc[j] = drop_keep(rk, uint32_t(j), p.drop_thr) ? sc[j] * p.inv_keep : 0.f;
+  }
   __syncwarp();
   const float inv = 1.f / sum;
   T* o = tokw<T>(p.O, p.ldo, p.Lq, b, i, h, p.D);
@@ -102,6 +108,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_simt(const AttnP p) {
       s = fmaf(qs[d], to_f32(k[d]), s);
       dp = fmaf(gs[d], to_f32(v[d]), dp);
     }
+    if (p.drop_thr) dp = drop_keep(drop_row_key(p.drop_seed_lo, p.drop_seed_hi, uint32_t(gw)), uint32_t(j), p.drop_thr) ? dp * p.inv_keep : 0.f;
     ds[j] = expf(s - lse) * (dp - dl);
   }
   __syncwarp();
@@ -139,11 +146,17 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_simt(const AttnP p) {
     }
     const long long ri = ((long long)b * p.H + h) * p.Lq + i;
     const float pij = expf(s * p.scale - p.LSE[ri]);
+    float pd = pij;                                  // dropped + rescaled probability (multiplies dO in dV)
+    if (p.drop_thr) {
+      const bool keep = drop_keep(drop_row_key(p.drop_seed_lo, p.drop_seed_hi, uint32_t(ri)), uint32_t(j), p.drop_thr);
+      dp = keep ? dp * p.inv_keep : 0.f;
+      pd = keep ? pij * p.inv_keep : 0.f;
+    }
     const float dsij = pij * (dp - p.delta[ri]) * p.scale;
 #pragma unroll
     for (int d = 0; d < MAXD; ++d)
       if (d < p.D) {
-        dv[d] = fmaf(pij, to_f32(g[d]), dv[d]);
+        dv[d] = fmaf(pd, to_f32(g[d]), dv[d]);
         dk[d] = fmaf(dsij, to_f32(q[d]), dk[d]);
       }
   }
@@ -163,6 +176,8 @@ static AttnP make_params(const b200f_attn_args& a) {
   p.Q = a.Q; p.K = a.K; p.V = a.V; p.dO = a.dO; p.O = a.O; p.dQ = a.dQ; p.dK = a.dK; p.dV = a.dV;
   p.ldq = a.ldq; p.ldk = a.ldk; p.ldv = a.ldv; p.ldo = a.ldo; p.lddo = a.lddo; p.lddq = a.lddq; p.lddk = a.lddk; p.lddv = a.lddv;
   p.LSE = a.LSE; p.delta = a.delta; p.scale = a.scale;
+  p.drop_thr = drop_threshold(a.dropout_p); p.drop_seed_lo = a.drop_seed_lo; p.drop_seed_hi = a.drop_seed_hi;
+  p.inv_keep = 1.f / (1.f - a.dropout_p);
   return p;
 }
 

@@ -39,6 +39,9 @@ struct AttnTcParams {
   bf16* dK; long long lddk;
   bf16* dV; long long lddv;
   float* dbq; float* dbk; float* dbv;   // optional [H*64] fp32 accumulators: column sums of dQ / dK / dV (in-proj bias gradients)
+  // attention-probability dropout (persistent kernels, DROP = true instantiation): keep iff hash >= drop_thr, kept scaled by inv_keep
+  uint32_t drop_thr, drop_seed_lo, drop_seed_hi;
+  float inv_keep;
 };
 
 // Epilogue helper: this warp's 32 accumulator rows x 64 fp32 columns in TMEM -> (x mul) -> bf16 -> a private [32 x 128 B]
@@ -290,6 +293,7 @@ struct Fwd2Smem {
   static constexpr int TOTAL = BAR_OFF + 256;
 };
 
+template <bool DROP>
 __global__ void __launch_bounds__(F2_THREADS, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p, const int n_qblk, const int n_items) {
@@ -434,6 +438,8 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const int q0 = qb * 2 * TQ + t * TQ;
       if (q0 >= p.Lq) continue;                      // this warpgroup's tile does not exist (the MMA warp skips it too)
       float m = -INFINITY, l = 0.f;                  // m: reference max the stored P / O are scaled against (raw score units)
+      // dropout: P (what multiplies V) is masked, the row sum l is not; the 1/(1-p) scale rides on the final 1/l
+      const uint32_t rk = DROP ? drop_row_key(p.drop_seed_lo, p.drop_seed_hi, uint32_t((b * p.H + h) * p.Lq + q0 + row)) : 0u;
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(&s_full[t], sf_cnt & 1);
         ++sf_cnt;
@@ -488,8 +494,13 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             for (int i = 0; i < 32; i += 2) {
               float x0, x1;
               f2_unpack(f2_fma(f2_pack_u(r[q][i], r[q][i + 1]), c2, nmc2), x0, x1);
-              const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+              float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
               lsum2 = f2_add(lsum2, f2_pack(e0, e1));
+              if (DROP) {
+                const uint32_t cc = uint32_t(j * TK + q * 32 + i) * kDropColMul;
+                e0 = drop_keep_c(rk, cc, p.drop_thr) ? e0 : 0.f;
+                e1 = drop_keep_c(rk, cc + kDropColMul, p.drop_thr) ? e1 : 0.f;
+              }
               pk[i >> 1] = pack_bf16(e0, e1);
             }
             uint8_t* half = prow + (q >> 1) * (TQ * 128);   // 32 keys = four 16-byte chunks of this row inside the 64-key half
@@ -528,7 +539,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       if (qrow < p.Lq) p.LSE[((long long)b * p.H + h) * p.Lq + qrow] = m * p.scale + logf(l);
       // O / l -> bf16 -> this warp's 32 x 128 B slice of the (now free) P_t tile -> full 128-byte lines to global
       store_rows64(t_o + lane_addr, prow + grp * (32 * 128), p.O + ((long long)b * p.Lq + q0 + grp * 32) * p.ldo + h * HD, p.ldo,
-                   p.Lq - (q0 + grp * 32), lane, 1.f / l);
+                   p.Lq - (q0 + grp * 32), lane, (DROP ? p.inv_keep : 1.f) / l);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[t]);
@@ -569,12 +580,17 @@ int attn_fwd_tc(const b200f_attn_args& a, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
-    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::TOTAL));
+    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::TOTAL));
+    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::TOTAL));
     configured = true;
   }
   // a single 128-query tile per (batch, head) leaves the second softmax warpgroup of the two-tile kernel idle: use the
   // one-tile-per-CTA kernel there (measured Lq=30, Lk=512: 0.094 ms vs 0.122 ms).  b200f_debug_set(4, 1|2) forces either.
-  if (g_attn_fwd_variant == 1 || (g_attn_fwd_variant == 0 && a.Lq <= TQ)) {
+  p.drop_thr = drop_threshold(a.dropout_p); p.drop_seed_lo = a.drop_seed_lo; p.drop_seed_hi = a.drop_seed_hi;
+  p.inv_keep = 1.f / (1.f - a.dropout_p);
+  const bool drop = p.drop_thr != 0;
+  B200F_REQUIRE(!drop || g_attn_fwd_variant != 1, B200F_ERR_UNSUPPORTED, "attention(tcgen05): dropout needs the persistent kernel");
+  if (!drop && (g_attn_fwd_variant == 1 || (g_attn_fwd_variant == 0 && a.Lq <= TQ))) {
     dim3 grid((a.Lq + TQ - 1) / TQ, a.H, a.B);
     attn_fwd_tc_kernel<<<grid, ATT_THREADS, FwdSmem::TOTAL, st>>>(tq, tk, tv, p);
     return check_launch("attn_fwd_tc_kernel");
@@ -583,7 +599,8 @@ int attn_fwd_tc(const b200f_attn_args& a, cudaStream_t st) {
   const long long n_items = (long long)n_qblk * a.H * a.B;
   B200F_REQUIRE(n_items < (1ll << 31), B200F_ERR_SHAPE, "attention(tcgen05): too many work items");
   const int grid = int(n_items < num_sms() ? n_items : num_sms());
-  attn_fwd_tc2_kernel<<<grid, F2_THREADS, Fwd2Smem::TOTAL, st>>>(tq, tk, tv, p, n_qblk, int(n_items));
+  if (drop) attn_fwd_tc2_kernel<true><<<grid, F2_THREADS, Fwd2Smem::TOTAL, st>>>(tq, tk, tv, p, n_qblk, int(n_items));
+  else attn_fwd_tc2_kernel<false><<<grid, F2_THREADS, Fwd2Smem::TOTAL, st>>>(tq, tk, tv, p, n_qblk, int(n_items));
   return check_launch("attn_fwd_tc2_kernel");
 }
 
@@ -924,6 +941,7 @@ struct Dq2Smem {
 };
 
 // work item = (batch, head, 256-query block); TMEM per tile t: S_t [192t, +64) dP_t [+64, +128) dQ_t [+128, +192)
+template <bool DROP>
 __global__ void __launch_bounds__(B2_THREADS, 1)
 attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                        const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p,
@@ -1063,6 +1081,9 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       const float nlse2 = -(qrow < p.Lq ? p.LSE[ri] : 0.f) * LOG2E;
       const float ndl = -(qrow < p.Lq ? p.delta[ri] : 0.f) * p.scale;
       const uint64_t nlse22 = f2_pack(nlse2, nlse2), ndl2 = f2_pack(ndl, ndl);
+      // dropout: dP = keep/(1-p) * (dO V^T), so the mask and the scale ride on the multiplier of dP
+      const uint32_t rk = DROP ? drop_row_key(p.drop_seed_lo, p.drop_seed_hi, uint32_t((b * p.H + h) * p.Lq + qrow)) : 0u;
+      const float sck = p.scale * p.inv_keep;
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(&sdp_full[t], sf_cnt & 1);
         ++sf_cnt;
@@ -1087,7 +1108,12 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           for (int i = 0; i < 32; i += 2) {     // dS = P o (dP - delta) * scale, two elements per FFMA2 / FMUL2
             float x0, x1, d0, d1;
             f2_unpack(f2_fma(f2_pack_u(rs[hf][i], rs[hf][i + 1]), c2, nlse22), x0, x1);
-            const uint64_t t2 = f2_fma(f2_pack_u(rp[hf][i], rp[hf][i + 1]), sc2, ndl2);
+            uint64_t m2 = sc2;
+            if (DROP) {
+              const uint32_t cc = uint32_t(j * BT + hf * 32 + i) * kDropColMul;
+              m2 = f2_pack(drop_keep_c(rk, cc, p.drop_thr) ? sck : 0.f, drop_keep_c(rk, cc + kDropColMul, p.drop_thr) ? sck : 0.f);
+            }
+            const uint64_t t2 = f2_fma(f2_pack_u(rp[hf][i], rp[hf][i + 1]), m2, ndl2);
             f2_unpack(f2_mul(f2_pack(ex2_approx(x0), ex2_approx(x1)), t2), d0, d1);
             pk[i >> 1] = pack_bf16(d0, d1);
           }
@@ -1123,12 +1149,13 @@ struct Dkv2Smem {
   static constexpr int DO_OFF = Q_OFF + B2_ST * BT * HD * 2;   // B2_ST x [64 queries x 64]
   static constexpr int P_OFF = DO_OFF + B2_ST * BT * HD * 2;   // 2 x P^T  [128 keys x 64 queries] bf16
   static constexpr int DS_OFF = P_OFF + 2 * TK * BT * 2;       // 2 x dS^T [128 keys x 64 queries] bf16
-  static constexpr int STAT_OFF = DS_OFF + 2 * TK * BT * 2;    // 2 warpgroups x 2 buffers x {lse2[64], delta[64]} fp32
-  static constexpr int BAR_OFF = STAT_OFF + 2 * 2 * 2 * BT * 4;
+  static constexpr int STAT_OFF = DS_OFF + 2 * TK * BT * 2;    // 2 warpgroups x 2 buffers x {lse2[64], delta[64], dropout row key[64]}
+  static constexpr int BAR_OFF = STAT_OFF + 2 * 2 * 3 * BT * 4;
   static constexpr int TOTAL = BAR_OFF + 256;
 };
 
 // work item = (batch, head, 256-key block); TMEM per tile t: S^T_t [256t, +64) dP^T_t [+64, +128) dV_t [+128, +192) dK_t [+192, +256)
+template <bool DROP>
 __global__ void __launch_bounds__(B2_THREADS, 1)
 attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                         const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p,
@@ -1259,7 +1286,7 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     const uint32_t t_s = tmem_base + t * 256, t_dp = t_s + 64, t_dv = t_s + 128, t_dk = t_s + 192;
     uint8_t* p_tile = smem + Dkv2Smem::P_OFF + t * TK * BT * 2;
     uint8_t* ds_tile = smem + Dkv2Smem::DS_OFF + t * TK * BT * 2;
-    float* stats = reinterpret_cast<float*>(smem + Dkv2Smem::STAT_OFF) + t * (2 * 2 * BT);
+    float* stats = reinterpret_cast<float*>(smem + Dkv2Smem::STAT_OFF) + t * (2 * 3 * BT);
     const float c = p.scale * LOG2E;
     const uint64_t c2 = f2_pack(c, c), sc2 = f2_pack(p.scale, p.scale);
     uint32_t sf_cnt = 0, dsf_cnt = 0;
@@ -1268,13 +1295,16 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       const int k0 = kb * 2 * TK + t * TK;
       if (k0 >= p.Lk) continue;
       const long long stat_base = ((long long)b * p.H + h) * p.Lq;
+      const uint32_t jc = uint32_t(k0 + row) * kDropColMul;       // dropout: this thread's key column
+      const float sck = p.scale * p.inv_keep;
       for (int i = 0; i < n_tiles; ++i) {
-        float* sl = stats + (sf_cnt & 1) * 2 * BT;   // [lse2[64] | delta[64]] of this tile's queries; parity runs across items
+        float* sl = stats + (sf_cnt & 1) * 3 * BT;   // [lse2[64] | delta[64] | row key[64]] of this tile's queries; parity runs across items
         {
           const int qi = i * BT + (t128 & 63);
           float v = 0.f;                             // stored negated (and delta pre-scaled) so the inner loop is pure FFMA2
           if (qi < p.Lq) v = t128 < 64 ? -p.LSE[stat_base + qi] * LOG2E : -p.delta[stat_base + qi] * p.scale;
           sl[t128] = v;
+          if (DROP && t128 < 64) reinterpret_cast<uint32_t*>(sl)[2 * BT + t128] = drop_row_key(p.drop_seed_lo, p.drop_seed_hi, uint32_t(stat_base + qi));
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
         mbar_wait(&sdp_full[t], sf_cnt & 1);
@@ -1303,9 +1333,18 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             float x0, x1, d0, d1;
             f2_unpack(f2_fma(f2_pack_u(rs[hf][e], rs[hf][e + 1]), c2, nl2[e >> 1]), x0, x1);
             const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-            const uint64_t t2 = f2_fma(f2_pack_u(rp[hf][e], rp[hf][e + 1]), sc2, nd2[e >> 1]);
+            uint64_t m2 = sc2;
+            float pd0 = p0, pd1 = p1;                // what multiplies dO in dV: the dropped, rescaled probabilities
+            if (DROP) {
+              const uint32_t* rk = reinterpret_cast<const uint32_t*>(sl) + 2 * BT + hf * 32 + e;
+              const bool k0_ = drop_keep_c(rk[0], jc, p.drop_thr), k1_ = drop_keep_c(rk[1], jc, p.drop_thr);
+              m2 = f2_pack(k0_ ? sck : 0.f, k1_ ? sck : 0.f);
+              pd0 = k0_ ? p0 * p.inv_keep : 0.f;
+              pd1 = k1_ ? p1 * p.inv_keep : 0.f;
+            }
+            const uint64_t t2 = f2_fma(f2_pack_u(rp[hf][e], rp[hf][e + 1]), m2, nd2[e >> 1]);
             f2_unpack(f2_mul(f2_pack(p0, p1), t2), d0, d1);
-            pp[e >> 1] = pack_bf16(p0, p1);
+            pp[e >> 1] = pack_bf16(pd0, pd1);
             pd[e >> 1] = pack_bf16(d0, d1);
           }
 #pragma unroll
@@ -1352,6 +1391,10 @@ int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st) {
   p.dK = static_cast<bf16*>(a.dK); p.lddk = a.lddk;
   p.dV = static_cast<bf16*>(a.dV); p.lddv = a.lddv;
   p.dbq = a.dbq; p.dbk = a.dbk; p.dbv = a.dbv;
+  p.drop_thr = drop_threshold(a.dropout_p); p.drop_seed_lo = a.drop_seed_lo; p.drop_seed_hi = a.drop_seed_hi;
+  p.inv_keep = 1.f / (1.f - a.dropout_p);
+  const bool drop = p.drop_thr != 0;
+  B200F_REQUIRE(!drop || g_attn_bwd_variant == 0, B200F_ERR_UNSUPPORTED, "attention(tcgen05): dropout needs the persistent kernels");
   const long long rows = (long long)a.B * a.H * a.Lq;
   attn_delta_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(static_cast<const bf16*>(a.dO), a.lddo, static_cast<const bf16*>(a.O), a.ldo, a.delta, a.B, a.H, a.Lq);
   if ((rc = check_launch("attn_delta_kernel"))) return rc;
@@ -1359,8 +1402,10 @@ int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st) {
   if (!configured) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::TOTAL));
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem::TOTAL));
-    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Dq2Smem::TOTAL));
-    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Dkv2Smem::TOTAL));
+    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dq2Smem::TOTAL));
+    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dkv2Smem::TOTAL));
+    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dq2Smem::TOTAL));
+    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dkv2Smem::TOTAL));
     configured = true;
   }
   CUtensorMap tq, tdo, tk, tv;
@@ -1374,7 +1419,8 @@ int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st) {
       const long long n_items = (long long)n_qblk * a.H * a.B;
       B200F_REQUIRE(n_items < (1ll << 31), B200F_ERR_SHAPE, "attention(tcgen05): too many work items");
       const int grid = int(n_items < num_sms() ? n_items : num_sms());
-      attn_bwd_dq_tc2_kernel<<<grid, B2_THREADS, Dq2Smem::TOTAL, st>>>(tq, tdo, tk, tv, p, n_qblk, int(n_items));
+      if (drop) attn_bwd_dq_tc2_kernel<true><<<grid, B2_THREADS, Dq2Smem::TOTAL, st>>>(tq, tdo, tk, tv, p, n_qblk, int(n_items));
+      else attn_bwd_dq_tc2_kernel<false><<<grid, B2_THREADS, Dq2Smem::TOTAL, st>>>(tq, tdo, tk, tv, p, n_qblk, int(n_items));
       if ((rc = check_launch("attn_bwd_dq_tc2_kernel"))) return rc;
     }
     {  // dKdV: 128-row K/V boxes, 64-row Q/dO boxes; item = (batch, head, 256-key block)
@@ -1386,7 +1432,8 @@ int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st) {
       const long long n_items = (long long)n_kblk * a.H * a.B;
       B200F_REQUIRE(n_items < (1ll << 31), B200F_ERR_SHAPE, "attention(tcgen05): too many work items");
       const int grid = int(n_items < num_sms() ? n_items : num_sms());
-      attn_bwd_dkv_tc2_kernel<<<grid, B2_THREADS, Dkv2Smem::TOTAL, st>>>(tq, tdo, tk, tv, p, n_kblk, int(n_items));
+      if (drop) attn_bwd_dkv_tc2_kernel<true><<<grid, B2_THREADS, Dkv2Smem::TOTAL, st>>>(tq, tdo, tk, tv, p, n_kblk, int(n_items));
+      else attn_bwd_dkv_tc2_kernel<false><<<grid, B2_THREADS, Dkv2Smem::TOTAL, st>>>(tq, tdo, tk, tv, p, n_kblk, int(n_items));
       if ((rc = check_launch("attn_bwd_dkv_tc2_kernel"))) return rc;
     }
     return B200F_OK;

@@ -102,4 +102,29 @@ __host__ __device__ __forceinline__ float rng_uniform(uint64_t seed, uint64_t id
   return float(z >> 40) * (1.0f / 16777216.0f);
 }
 
+// ---- dropout masks generated inside the kernels (no mask tensor in memory) -------------------------------------------
+// An element is addressed by (row, col) of the matrix the dropout acts on -- attention probabilities: row = (b*H + h)*Lq + i,
+// col = key j; an activation [M, N]: row m, col n -- and kept iff a 32-bit multiplicative hash of (row key, col) is >= thr32 =
+// p * 2^32.  The row key is a full avalanche hash of (seed, row), computed once per row; the per-element part is 3 integer
+// instructions, cheap enough for the MUFU-bound softmax loops.  Forward, backward and recomputation regenerate the same mask
+// from (seed_lo, seed_hi).  tests/test_dropout.py restates this in numpy and checks rate / independence.
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t drop_row_key(uint32_t seed_lo, uint32_t seed_hi, uint32_t row) {
+  return hash32(seed_lo + hash32(seed_hi ^ row));
+}
+constexpr uint32_t kDropColMul = 0x9E3779B1u, kDropMix = 0x85EBCA6Bu;
+__host__ __device__ __forceinline__ bool drop_keep_c(uint32_t row_key, uint32_t col_times_mul, uint32_t thr32) {
+  return ((row_key ^ col_times_mul) * kDropMix) >= thr32;
+}
+__host__ __device__ __forceinline__ bool drop_keep(uint32_t row_key, uint32_t col, uint32_t thr32) {
+  return drop_keep_c(row_key, col * kDropColMul, thr32);
+}
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
+  const double t = double(p) * 4294967296.0;
+  return t <= 0.0 ? 0u : (t >= 4294967295.0 ? 4294967295u : uint32_t(t));
+}
+
 }  // namespace b200f

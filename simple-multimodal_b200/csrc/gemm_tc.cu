@@ -36,6 +36,8 @@ struct GemmTcParams {
   uint32_t a_lbo, a_sbo, a_kadv, b_lbo, b_sbo, b_kadv;
   int vec_ok;  // C / residual / mask rows are 16-byte aligned -> 128-bit epilogue accesses
   float* colsum;  // optional [N]: += column sums of the stored bf16 C (N % 64 == 0; staged bf16 epilogue only)
+  uint32_t drop_thr, drop_seed_lo, drop_seed_hi;   // inverted dropout on the output (staged bf16 epilogue only); 0 = off
+  float inv_keep;
 };
 
 template <int BN, int STAGES>
@@ -172,6 +174,7 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, uint8_
   const long long row = row0 + lane;
   const int crow = lane >> 3, cchunk = lane & 7;             // coalesced phase: 4 rows x 8 chunks per instruction
   const bool has_aux = p.residual || p.mask;
+  const uint32_t rk = p.drop_thr ? drop_row_key(p.drop_seed_lo, p.drop_seed_hi, uint32_t(row)) : 0u;
 #pragma unroll 1
   for (int blk = 0; blk < NBLK; ++blk) {
     const int c0 = c_begin + blk * 64;
@@ -216,6 +219,11 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, uint8_
         if (relu) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.drop_thr) {                                    // nn.Dropout behind Linear(+ReLU): mask from (seed, row, column)
+          const uint32_t cc = uint32_t(col0 + h * 32 + g * 8) * kDropColMul;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = drop_keep_c(rk, cc + uint32_t(j) * kDropColMul, p.drop_thr) ? v[j] * p.inv_keep : 0.f;
         }
         if (p.mask) {
           if (p.residual) {                                  // both present: the mask comes straight from global
@@ -678,7 +686,7 @@ bool gemm_tc_colsum_fused(const b200f_gemm_args& a) {
   const bool out_f32 = (a.flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) != 0;
   const bool vec_ok = aligned16(a.C) && a.ldc % 8 == 0 && (!a.residual || (a.ldr % 8 == 0 && aligned16(a.residual))) &&
                       (!a.relu_mask || (a.ldm % 8 == 0 && aligned16(a.relu_mask))) && (!a.bias || aligned16(a.bias));
-  return gemm_tc_eligible(a) && !out_f32 && vec_ok && a.N % 64 == 0 && aligned16(a.colsum);
+  return gemm_tc_eligible(a) && !out_f32 && vec_ok && a.N % 64 == 0 && (!a.colsum || aligned16(a.colsum));
 }
 
 int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
@@ -722,8 +730,10 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
   p.alpha = a.alpha; p.flags = a.flags;
   p.vec_ok = vec_ok ? 1 : 0;
   p.colsum = a.colsum;
-  if (a.colsum)
-    B200F_REQUIRE(gemm_tc_colsum_fused(a), B200F_ERR_UNSUPPORTED, "gemm(tcgen05): fused colsum needs bf16 output, N %% 64 == 0 and aligned rows");
+  p.drop_thr = drop_threshold(a.dropout_p); p.drop_seed_lo = a.drop_seed_lo; p.drop_seed_hi = a.drop_seed_hi;
+  p.inv_keep = 1.f / (1.f - a.dropout_p);
+  if (a.colsum || p.drop_thr)
+    B200F_REQUIRE(gemm_tc_colsum_fused(a), B200F_ERR_UNSUPPORTED, "gemm(tcgen05): fused colsum / dropout need bf16 output, N %% 64 == 0 and aligned rows");
   // K-major SW128: rows of 128 B, 8-row groups 1024 B apart, +32 B per K=16 step inside the swizzle row.
   // MN-major SW128: 64-element (128 B) MN chunks, k rows 128 B apart, 8-k-row groups 1024 B apart (SBO),
   //                 MN chunks BK*128 B apart (LBO), +16 k rows = 2048 B per K=16 step.

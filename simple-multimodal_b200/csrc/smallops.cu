@@ -45,7 +45,7 @@ __device__ __forceinline__ void gat_scores(const T* __restrict__ xp, const float
 template <typename T>
 __global__ void __launch_bounds__(128) gat_fwd_kernel(const T* __restrict__ xp, const float* __restrict__ att_src, const float* __restrict__ att_dst,
                                                       const float* __restrict__ bias, T* __restrict__ out, float* __restrict__ alpha_out,
-                                                      long long B, int heads, int C, float slope) {
+                                                      long long B, int heads, int C, float slope, uint32_t drop_thr, uint32_t seed_lo, uint32_t seed_hi, float inv_keep) {
   constexpr int VN = Vec16<T>::N;
   const int lane = threadIdx.x & 31;
   const long long b = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -71,7 +71,17 @@ __global__ void __launch_bounds__(128) gat_fwd_kernel(const T* __restrict__ xp, 
     float* ao = alpha_out + b * 3LL * heads * 3;
     for (int i = 0; i < 3; ++i)
       for (int h = 0; h < heads; ++h)
-        for (int j = 0; j < 3; ++j) ao[(i * heads + h) * 3 + j] = al[i][h][j];
+        for (int j = 0; j < 3; ++j) ao[(i * heads + h) * 3 + j] = al[i][h][j];   // the softmax output; dropout is regenerated in backward
+  }
+  if (drop_thr) {            // GATConv(dropout=p): F.dropout on the attention coefficients before aggregation (training mode)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int h = 0; h < GH; ++h) {
+        const uint32_t rk = drop_row_key(seed_lo, seed_hi, uint32_t((b * heads + h) * 3 + i));
+#pragma unroll
+        for (int j = 0; j < 3; ++j) al[i][h][j] = drop_keep(rk, uint32_t(j), drop_thr) ? al[i][h][j] * inv_keep : 0.f;
+      }
   }
   const int nvec = C / VN;
   const float invh = 1.f / heads;
@@ -110,7 +120,7 @@ __global__ void __launch_bounds__(128) gat_bwd_kernel(const T* __restrict__ dout
                                                       const float* __restrict__ alpha_in, const float* __restrict__ att_src,
                                                       const float* __restrict__ att_dst, T* __restrict__ dxp, float* __restrict__ datt_src,
                                                       float* __restrict__ datt_dst, float* __restrict__ dbias, long long B, int heads, int C,
-                                                      float slope) {
+                                                      float slope, uint32_t drop_thr, uint32_t seed_lo, uint32_t seed_hi, float inv_keep) {
   constexpr int VN = Vec16<T>::N;
   extern __shared__ float sm[];
   const int HC = heads * C;
@@ -169,13 +179,22 @@ __global__ void __launch_bounds__(128) gat_bwd_kernel(const T* __restrict__ dout
     for (int j = 0; j < 3; ++j)
 #pragma unroll
       for (int h = 0; h < GH; ++h) { da_src[j][h] = 0.f; da_dst[j][h] = 0.f; }
+    float mk[3][GH][3];      // dropout multiplier of each coefficient (1 without dropout): keep / (1 - p)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int h = 0; h < GH; ++h) {
+        const uint32_t rk = drop_thr ? drop_row_key(seed_lo, seed_hi, uint32_t((b * heads + h) * 3 + i)) : 0u;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) mk[i][h][j] = !drop_thr ? 1.f : (drop_keep(rk, uint32_t(j), drop_thr) ? inv_keep : 0.f);
+      }
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int h = 0; h < GH; ++h) {
         float dot = 0.f;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) { dal[i][h][j] = warp_sum(dal[i][h][j]) * invh; dot += al[i][h][j] * dal[i][h][j]; }
+        for (int j = 0; j < 3; ++j) { dal[i][h][j] = warp_sum(dal[i][h][j]) * invh * mk[i][h][j]; dot += al[i][h][j] * dal[i][h][j]; }
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           const float pre = a_src[j][h] + a_dst[i][h];
@@ -207,7 +226,8 @@ __global__ void __launch_bounds__(128) gat_bwd_kernel(const T* __restrict__ dout
           float f[VN], o[VN]; t.unpack(f);
 #pragma unroll
           for (int e = 0; e < VN; ++e) {
-            o[e] = invh * (al[0][hh][j] * g[0][e] + al[1][hh][j] * g[1][e] + al[2][hh][j] * g[2][e]) + da_src[j][hh] * ws[e] + da_dst[j][hh] * wd[e];
+            o[e] = invh * (al[0][hh][j] * mk[0][hh][j] * g[0][e] + al[1][hh][j] * mk[1][hh][j] * g[1][e] + al[2][hh][j] * mk[2][hh][j] * g[2][e]) +
+                   da_src[j][hh] * ws[e] + da_dst[j][hh] * wd[e];
             ps[e] += da_src[j][hh] * f[e];
             pd[e] += da_dst[j][hh] * f[e];
           }
@@ -235,7 +255,7 @@ __device__ __forceinline__ float group_sum(float v) {
 
 template <typename T, int LPH>  // LPH = lanes per head = D / VN (power of two <= 32)
 __global__ void __launch_bounds__(128) tok3_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ ctx, float* __restrict__ probs,
-                                                       float* __restrict__ avgw, long long B, int heads, int H, float scale) {
+                                                       float* __restrict__ avgw, long long B, int heads, int H, float scale, uint32_t drop_thr, uint32_t seed_lo, uint32_t seed_hi, float inv_keep) {
   constexpr int VN = Vec16<T>::N;
   const int lane = threadIdx.x & 31;
   const long long b = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -272,10 +292,18 @@ __global__ void __launch_bounds__(128) tok3_fwd_kernel(const T* __restrict__ qkv
 #pragma unroll
       for (int j = 0; j < 3; ++j) { p[i][j] = expf(p[i][j] - mx); sum += p[i][j]; }
 #pragma unroll
-      for (int j = 0; j < 3; ++j) { p[i][j] /= sum; if (live && lane % LPH == 0) wsum[i][j] += p[i][j]; }
+      for (int j = 0; j < 3; ++j) p[i][j] /= sum;
+      float pd[3] = {p[i][0], p[i][1], p[i][2]};     // nn.MultiheadAttention(dropout=p): the weights are dropped before P V, and the
+      if (drop_thr) {                                // returned (head-averaged) weights are the dropped ones (torch functional.py:6647-6665)
+        const uint32_t rk = drop_row_key(seed_lo, seed_hi, uint32_t((b * heads + head) * 3 + i));
+#pragma unroll
+        for (int j = 0; j < 3; ++j) pd[j] = drop_keep(rk, uint32_t(j), drop_thr) ? pd[j] * inv_keep : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) if (live && lane % LPH == 0) wsum[i][j] += pd[j];
       float o[VN];
 #pragma unroll
-      for (int e = 0; e < VN; ++e) o[e] = p[i][0] * vv[0][e] + p[i][1] * vv[1][e] + p[i][2] * vv[2][e];
+      for (int e = 0; e < VN; ++e) o[e] = pd[0] * vv[0][e] + pd[1] * vv[1][e] + pd[2] * vv[2][e];
       Vec16<T> ov; ov.pack(o);
       if (live) ov.store(ctx + (b * 3 + i) * H + vi * VN);
     }
@@ -299,7 +327,7 @@ __global__ void __launch_bounds__(128) tok3_fwd_kernel(const T* __restrict__ qkv
 template <typename T, int LPH>
 __global__ void __launch_bounds__(128) tok3_bwd_kernel(const T* __restrict__ dctx, const float* __restrict__ davgw, const T* __restrict__ qkv,
                                                        const float* __restrict__ probs, T* __restrict__ dqkv, long long B, int heads, int H,
-                                                       float scale) {
+                                                       float scale, uint32_t drop_thr, uint32_t seed_lo, uint32_t seed_hi, float inv_keep) {
   constexpr int VN = Vec16<T>::N;
   const int lane = threadIdx.x & 31;
   const long long b = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -320,17 +348,19 @@ __global__ void __launch_bounds__(128) tok3_bwd_kernel(const T* __restrict__ dct
       a.unpack(q[t]); c.unpack(k[t]); d.unpack(vv[t]); e.unpack(g[t]);
     }
     const float* pi = probs + (b * heads + head) * 9;
-    float p[3][3], ds[3][3];
+    float p[3][3], ds[3][3], mk[3][3];               // mk: dropout multiplier keep / (1 - p) of each weight (1 without dropout)
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       float dot = 0.f;
+      const uint32_t rk = drop_thr ? drop_row_key(seed_lo, seed_hi, uint32_t((b * heads + head) * 3 + i)) : 0u;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         p[i][j] = pi[i * 3 + j];
+        mk[i][j] = !drop_thr ? 1.f : (drop_keep(rk, uint32_t(j), drop_thr) ? inv_keep : 0.f);
         float s = 0.f;
 #pragma unroll
         for (int e = 0; e < VN; ++e) s += g[i][e] * vv[j][e];
-        ds[i][j] = group_sum<LPH>(s) + (davgw ? davgw[b * 9 + i * 3 + j] / heads : 0.f);
+        ds[i][j] = (group_sum<LPH>(s) + (davgw ? davgw[b * 9 + i * 3 + j] / heads : 0.f)) * mk[i][j];
         dot += p[i][j] * ds[i][j];
       }
 #pragma unroll
@@ -343,7 +373,7 @@ __global__ void __launch_bounds__(128) tok3_bwd_kernel(const T* __restrict__ dct
       for (int e = 0; e < VN; ++e) {
         dq[e] = ds[t][0] * k[0][e] + ds[t][1] * k[1][e] + ds[t][2] * k[2][e];
         dk[e] = ds[0][t] * q[0][e] + ds[1][t] * q[1][e] + ds[2][t] * q[2][e];
-        dv[e] = p[0][t] * g[0][e] + p[1][t] * g[1][e] + p[2][t] * g[2][e];
+        dv[e] = p[0][t] * mk[0][t] * g[0][e] + p[1][t] * mk[1][t] * g[1][e] + p[2][t] * mk[2][t] * g[2][e];
       }
       Vec16<T> a, c, d; a.pack(dq); c.pack(dk); d.pack(dv);
       if (live) { a.store(dbase + t * 3LL * H + vi * VN); c.store(dbase + t * 3LL * H + H + vi * VN); d.store(dbase + t * 3LL * H + 2 * H + vi * VN); }
@@ -463,6 +493,19 @@ __global__ void modality_mask_kernel(float* mask, long long B, float rate, uint6
   for (int m = 0; m < 3; ++m) mask[b * 3 + m] = k[m];
 }
 
+// in-place inverted dropout of an [M, N] activation with the (seed, row, column) mask the GEMM epilogue generates
+// (the route for outputs the tcgen05 epilogue does not cover: fp32 parity mode, ragged N)
+template <typename T>
+__global__ void dropout_rowcol_kernel(T* __restrict__ x, long long ldx, long long M, long long N, uint32_t thr, uint32_t seed_lo, uint32_t seed_hi,
+                                      float inv_keep) {
+  const long long total = M * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / N, c = i - r * N;
+    T* e = x + r * ldx + c;
+    *e = drop_keep(drop_row_key(seed_lo, seed_hi, uint32_t(r)), uint32_t(c), thr) ? from_f32<T>(to_f32(*e) * inv_keep) : from_f32<T>(0.f);
+  }
+}
+
 template <typename T>
 __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, float p, float inv_keep, uint64_t seed, uint64_t offset) {
   constexpr int VN = Vec16<T>::N;
@@ -493,21 +536,25 @@ using namespace b200f;
 extern "C" {
 
 int b200f_gat_fwd(const void* xp, const float* att_src, const float* att_dst, const float* bias, void* out, float* alpha, int64_t B,
-                  int32_t heads, int32_t C, float slope, int32_t dtype, void* stream) {
+                  int32_t heads, int32_t C, float slope, float dropout_p, uint32_t seed_lo, uint32_t seed_hi, int32_t dtype, void* stream) {
   if (B == 0) return B200F_OK;
+  B200F_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, B200F_ERR_SHAPE, "gat: dropout_p=%f", dropout_p);
   B200F_REQUIRE(heads >= 1 && heads <= GH, B200F_ERR_UNSUPPORTED, "gat: heads=%d (max %d)", heads, GH);
   DISPATCH_DTYPE(dtype, T, {
     B200F_REQUIRE(C % Vec16<T>::N == 0, B200F_ERR_SHAPE, "gat: C=%d must be a multiple of %d", C, Vec16<T>::N);
     B200F_REQUIRE(aligned16(xp) && aligned16(out), B200F_ERR_ALIGN, "gat: alignment");
     gat_fwd_kernel<T><<<(unsigned)((B + 3) / 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const T*>(xp), att_src, att_dst, bias,
-                                                                                               static_cast<T*>(out), alpha, B, heads, C, slope);
+                                                                                               static_cast<T*>(out), alpha, B, heads, C, slope,
+                                                                                               drop_threshold(dropout_p), seed_lo, seed_hi, 1.f / (1.f - dropout_p));
   })
   return check_launch("gat_fwd");
 }
 
 int b200f_gat_bwd(const void* dout, const void* out, const void* xp, const float* alpha, const float* att_src, const float* att_dst, void* dxp,
-                  float* datt_src, float* datt_dst, float* dbias, int64_t B, int32_t heads, int32_t C, float slope, int32_t dtype, void* stream) {
+                  float* datt_src, float* datt_dst, float* dbias, int64_t B, int32_t heads, int32_t C, float slope, float dropout_p,
+                  uint32_t seed_lo, uint32_t seed_hi, int32_t dtype, void* stream) {
   if (B == 0) return B200F_OK;
+  B200F_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, B200F_ERR_SHAPE, "gat: dropout_p=%f", dropout_p);
   B200F_REQUIRE(heads >= 1 && heads <= GH, B200F_ERR_UNSUPPORTED, "gat: heads=%d (max %d)", heads, GH);
   const size_t smem = (2 * (size_t)heads * C + C) * sizeof(float);
   B200F_REQUIRE(smem <= 160 * 1024, B200F_ERR_SHAPE, "gat: heads*C too large");
@@ -519,7 +566,7 @@ int b200f_gat_bwd(const void* dout, const void* out, const void* xp, const float
     if (blocks > 2LL * num_sms()) blocks = 2LL * num_sms();
     gat_bwd_kernel<T><<<(unsigned)blocks, 128, smem, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const T*>(dout), static_cast<const T*>(out), static_cast<const T*>(xp), alpha, att_src, att_dst, static_cast<T*>(dxp), datt_src,
-        datt_dst, dbias, B, heads, C, slope);
+        datt_dst, dbias, B, heads, C, slope, drop_threshold(dropout_p), seed_lo, seed_hi, 1.f / (1.f - dropout_p));
   })
   return check_launch("gat_bwd");
 }
@@ -543,19 +590,23 @@ int b200f_gat_bwd(const void* dout, const void* out, const void* xp, const float
     }                                                                                                                 \
   })
 
-int b200f_tok3_attn_fwd(const void* qkv, void* ctx, float* probs, float* avgw, int64_t B, int32_t heads, int32_t H, float scale, int32_t dtype,
-                        void* stream) {
+int b200f_tok3_attn_fwd(const void* qkv, void* ctx, float* probs, float* avgw, int64_t B, int32_t heads, int32_t H, float scale, float dropout_p,
+                        uint32_t seed_lo, uint32_t seed_hi, int32_t dtype, void* stream) {
   if (B == 0) return B200F_OK;
+  B200F_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, B200F_ERR_SHAPE, "tok3: dropout_p=%f", dropout_p);
   B200F_REQUIRE(aligned16(qkv) && aligned16(ctx), B200F_ERR_ALIGN, "tok3: alignment");
-  TOK3_DISPATCH(tok3_fwd_kernel, static_cast<const T*>(qkv), static_cast<T*>(ctx), probs, avgw, B, heads, H, scale)
+  TOK3_DISPATCH(tok3_fwd_kernel, static_cast<const T*>(qkv), static_cast<T*>(ctx), probs, avgw, B, heads, H, scale, drop_threshold(dropout_p), seed_lo,
+                seed_hi, 1.f / (1.f - dropout_p))
   return check_launch("tok3_fwd");
 }
 
 int b200f_tok3_attn_bwd(const void* dctx, const float* davgw, const void* qkv, const float* probs, void* dqkv, int64_t B, int32_t heads, int32_t H,
-                        float scale, int32_t dtype, void* stream) {
+                        float scale, float dropout_p, uint32_t seed_lo, uint32_t seed_hi, int32_t dtype, void* stream) {
   if (B == 0) return B200F_OK;
+  B200F_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, B200F_ERR_SHAPE, "tok3: dropout_p=%f", dropout_p);
   B200F_REQUIRE(aligned16(qkv) && aligned16(dctx) && aligned16(dqkv), B200F_ERR_ALIGN, "tok3: alignment");
-  TOK3_DISPATCH(tok3_bwd_kernel, static_cast<const T*>(dctx), davgw, static_cast<const T*>(qkv), probs, static_cast<T*>(dqkv), B, heads, H, scale)
+  TOK3_DISPATCH(tok3_bwd_kernel, static_cast<const T*>(dctx), davgw, static_cast<const T*>(qkv), probs, static_cast<T*>(dqkv), B, heads, H, scale,
+                drop_threshold(dropout_p), seed_lo, seed_hi, 1.f / (1.f - dropout_p))
   return check_launch("tok3_bwd");
 }
 
@@ -605,6 +656,19 @@ int b200f_modality_mask(float* mask, int64_t B, float rate, uint64_t seed, uint6
   if (B == 0) return B200F_OK;
   modality_mask_kernel<<<(unsigned)((B + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, B, rate, seed, offset);
   return check_launch("modality_mask");
+}
+
+int b200f_dropout_rowcol(void* x, int64_t ldx, int64_t M, int64_t N, float p, uint32_t seed_lo, uint32_t seed_hi, int32_t dtype, void* stream) {
+  if (M == 0 || N == 0 || p <= 0.f) return B200F_OK;
+  B200F_REQUIRE(p < 1.f, B200F_ERR_SHAPE, "dropout: p=%f", p);
+  const long long total = (long long)M * N;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
+  DISPATCH_DTYPE(dtype, T, {
+    dropout_rowcol_kernel<T><<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<T*>(x), ldx, M, N, drop_threshold(p), seed_lo, seed_hi,
+                                                                                             1.f / (1.f - p));
+  })
+  return check_launch("dropout_rowcol");
 }
 
 int b200f_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset, int32_t dtype, void* stream) {

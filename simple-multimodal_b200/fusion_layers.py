@@ -167,7 +167,8 @@ class CrossModalTransformer(_FusionBase):
         att = self.attention
         pq = ops.linear(q, att.in_proj_weight[:H], att.in_proj_bias[:H])
         pkv = ops.linear(kv, att.in_proj_weight[H:], att.in_proj_bias[H:])
-        ctx = ops.AttentionFn.apply(pq, pkv, 0, 0, H, H, heads, ops.mha_scale(H, heads))
+        drop = (self._p, *ops.next_drop_seed()) if (self.training and self._p > 0.0) else None
+        ctx = ops.AttentionFn.apply(pq, pkv, 0, 0, H, H, heads, ops.mha_scale(H, heads), drop)
         x = ops.LayerNormFn.apply(ops.AddFn.apply(q, ops.linear(ctx, att.out_proj.weight, att.out_proj.bias), None),
                                   self.norm1.weight, self.norm1.bias)
         h = ops.dropout(ops.linear(x, self.ffn[0].weight, self.ffn[0].bias, relu=True), self._p, self.training)
@@ -198,16 +199,14 @@ class MultimodalTransformer(_FusionBase):
             t, a, v = t.unsqueeze(1), a.unsqueeze(1), v.unsqueeze(1)
         if mask is not None:
             t, a, v = (ops.RowMaskFn.apply(x, mask, i) for i, x in enumerate((t, a, v)))
-        if self.training and self._p > 0.0:
-            raise B200FusionError("MulT: dropout inside the fused attention/FFN schedule is not implemented yet; "
-                                  "use fusion_dropout=0 or eval() (no silent fallback)")
+        drop = (self._p, *ops.next_drop_seed()) if (self.training and self._p > 0.0) else None     # one seed pair per call
         params = dict(self.named_parameters())
         H, heads = self.config.fusion_hidden_size, self.config.fusion_num_heads
         # memory the stash may use: what the driver reports free plus what torch's caching allocator holds but has not handed out
         free_bytes, _ = torch.cuda.mem_get_info(t.device)
         free_bytes += torch.cuda.memory_reserved(t.device) - torch.cuda.memory_allocated(t.device)
         budget = int(self.stash_fraction * free_bytes) if torch.is_grad_enabled() else 0
-        return mult_engine.MulTFn.apply(t, a, v, H, heads, int(self.chunk_size), budget, self._names, *[params[n] for n in self._names])
+        return mult_engine.MulTFn.apply(t, a, v, H, heads, int(self.chunk_size), budget, drop, self._names, *[params[n] for n in self._names])
 
     def forward(self, text_features, audio_features, video_features, mask=None) -> Dict[str, Tensor]:
         (t, a, v), mask, _ = self._prepare((text_features, audio_features, video_features), mask)
@@ -268,7 +267,9 @@ class GraphFusion(_FusionBase):
         x = emb.view(B, 3, H)
         for layer in self.gcn_layers:
             xp = ops.linear(x, layer.lin.weight, None)                            # [B,3,heads*C]
-            x = ops.GatFn.apply(xp, layer.att_src, layer.att_dst, layer.bias, layer.heads, GAT_SLOPE)
+            gp = float(getattr(self.config, "graph_dropout", 0.0))            # GATConv(dropout=config.graph_dropout), fusion_layers.py:228
+            drop = (gp, *ops.next_drop_seed()) if (self.training and gp > 0.0) else None
+            x = ops.GatFn.apply(xp, layer.att_src, layer.att_dst, layer.bias, layer.heads, GAT_SLOPE, drop)
         pooled = ops.MeanPoolFn.apply(x)                                          # global_mean_pool over the 3 nodes
         return ops.linear(pooled, self.output_projection.weight, self.output_projection.bias)
 
@@ -353,12 +354,11 @@ class AdaptiveFusion(_FusionBase):
 
     def _run(self, cat, feats):
         H, heads = self.config.fusion_hidden_size, self.config.fusion_num_heads
-        if self.training and self._p > 0.0:
-            raise B200FusionError("AdaptiveFusion: attention-probability dropout is not implemented yet; use fusion_dropout=0 or eval()")
+        drop = (self._p, *ops.next_drop_seed()) if (self.training and self._p > 0.0) else None
         tr = [ops.linear(x, m.weight, m.bias) for x, m in zip(feats, (self.text_transform, self.audio_transform, self.video_transform))]
         tokens = ops.Concat3Fn.apply(tr[0], tr[1], tr[2], None).view(-1, 3, H)           # stack(dim=1)
         qkv = ops.linear(tokens, self.attention.in_proj_weight, self.attention.in_proj_bias)  # [B,3,3H]
-        ctx, avgw = ops.Tok3AttnFn.apply(qkv, heads, ops.mha_scale(H, heads))
+        ctx, avgw = ops.Tok3AttnFn.apply(qkv, heads, ops.mha_scale(H, heads), drop)
         attended = ops.linear(ctx, self.attention.out_proj.weight, self.attention.out_proj.bias)
         wp0, wp2 = self.weight_predictor[0], self.weight_predictor[2]
         logits = ops.linear(ops.linear(cat, wp0.weight, wp0.bias, relu=True), wp2.weight, wp2.bias)

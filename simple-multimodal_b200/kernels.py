@@ -46,7 +46,7 @@ GEMM_PROFILE = None          # None, or a list collecting (start_event, stop_eve
 def gemm(a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_layout: int = 0, b_layout: int = 0,
          out: Optional[Tensor] = None, bias: Optional[Tensor] = None, residual: Optional[Tensor] = None,
          relu_mask: Optional[Tensor] = None, relu: bool = False, alpha: float = 1.0, accumulate: bool = False,
-         out_f32: bool = False, split_k: int = 1, colsum: Optional[Tensor] = None) -> Tensor:
+         out_f32: bool = False, split_k: int = 1, colsum: Optional[Tensor] = None, dropout=None) -> Tensor:
     """C[M,N] = epi(alpha * sum_k A(m,k) B(n,k)); see b200f_gemm in include/b200_fusion.h.
     `a`/`b` are 2-D views (row stride = leading dimension)."""
     require_cuda(a, b, out, bias, residual, relu_mask)
@@ -85,7 +85,7 @@ def gemm(a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_layout: int = 0, b_l
                       relu_mask=None if relu_mask is None else relu_mask.data_ptr(),
                       ldm=0 if relu_mask is None else relu_mask.stride(0),
                       alpha=alpha, flags=flags, dtype=dtype_code(dt), split_k=split_k,
-                      colsum=None if colsum is None else colsum.data_ptr())
+                      colsum=None if colsum is None else colsum.data_ptr(), **_drop_fields(dropout))
     if GEMM_PROFILE is None:
         check(lib().b200f_gemm(C.byref(args), stream_ptr()), "b200f_gemm")
         return out
@@ -98,23 +98,34 @@ def gemm(a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_layout: int = 0, b_l
     return out
 
 
+def _drop_fields(dropout):
+    """dropout = None or (p, seed_lo, seed_hi): in-kernel inverted dropout with a counter-based mask (csrc/common.cuh)."""
+    if dropout is None or dropout[0] <= 0.0:
+        return dict(dropout_p=0.0, drop_seed_lo=0, drop_seed_hi=0)
+    p, lo, hi = dropout
+    if not 0.0 <= p < 1.0:
+        raise B200FusionError(f"dropout probability {p} not in [0, 1)")
+    return dict(dropout_p=float(p), drop_seed_lo=int(lo) & 0xFFFFFFFF, drop_seed_hi=int(hi) & 0xFFFFFFFF)
+
+
 def _wgrad_split(tokens: int, n_out: int, k_in: int) -> int:
     tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
     want = max(1, (2 * 148) // max(tiles, 1))
     return max(1, min(want, tokens // 512 if tokens >= 512 else 1))
 
 
-def linear_fwd(x2: Tensor, w: Tensor, bias: Optional[Tensor], *, relu=False, residual=None, out=None) -> Tensor:
-    """y[M,N] = x2[M,K] w[N,K]^T + bias (+ residual) (relu)."""
+def linear_fwd(x2: Tensor, w: Tensor, bias: Optional[Tensor], *, relu=False, residual=None, out=None, dropout=None) -> Tensor:
+    """y[M,N] = dropout(relu(x2[M,K] w[N,K]^T + bias (+ residual)))  (relu / dropout optional)."""
     M, K = x2.shape
-    return gemm(x2, w, M=M, N=w.size(0), K=K, out=out, bias=bias, residual=residual, relu=relu)
+    return gemm(x2, w, M=M, N=w.size(0), K=K, out=out, bias=bias, residual=residual, relu=relu, dropout=dropout)
 
 
-def linear_dgrad(dy2: Tensor, w: Tensor, *, relu_mask=None, residual=None, out=None, colsum=None) -> Tensor:
+def linear_dgrad(dy2: Tensor, w: Tensor, *, relu_mask=None, residual=None, out=None, colsum=None, alpha: float = 1.0) -> Tensor:
     """dx[M,K] = dy2[M,N] w[N,K]  (B operand N-contiguous: no transposed weight copy).
     `colsum` [K] fp32 += column sums of dx: the bias gradient of the Linear that produced this GEMM's input activation."""
     M, N = dy2.shape
-    return gemm(dy2, w, M=M, N=w.size(1), K=N, a_layout=0, b_layout=1, out=out, relu_mask=relu_mask, residual=residual, colsum=colsum)
+    return gemm(dy2, w, M=M, N=w.size(1), K=N, a_layout=0, b_layout=1, out=out, relu_mask=relu_mask, residual=residual, colsum=colsum,
+                alpha=alpha)
 
 
 def linear_wgrad(dy2: Tensor, x2: Tensor, dw: Tensor) -> Tensor:
@@ -243,7 +254,7 @@ def _tokens(x: Tensor):
     return x.data_ptr(), x.stride(1)
 
 
-def attn_fwd(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float, out: Optional[Tensor] = None):
+def attn_fwd(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float, out: Optional[Tensor] = None, dropout=None):
     require_cuda(q, k, v)
     B, Lq, W = q.shape
     Lk = k.size(1)
@@ -253,14 +264,14 @@ def attn_fwd(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float, out: Opt
     lse = torch.empty((B, heads, Lq), device=q.device, dtype=torch.float32)
     (qp, ldq), (kp, ldk), (vp, ldv), (op, ldo) = _tokens(q), _tokens(k), _tokens(v), _tokens(out)
     args = L.AttnArgs(B=B, H=heads, Lq=Lq, Lk=Lk, D=D, Q=qp, ldq=ldq, K=kp, ldk=ldk, V=vp, ldv=ldv, O=op, ldo=ldo,
-                      LSE=lse.data_ptr(), scale=scale, dtype=dtype_code(q.dtype))
+                      LSE=lse.data_ptr(), scale=scale, dtype=dtype_code(q.dtype), **_drop_fields(dropout))
     check(lib().b200f_attn_fwd(C.byref(args), stream_ptr()), "b200f_attn_fwd")
     return out, lse
 
 
 def attn_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor, heads: int, scale: float,
              dq: Tensor, dk: Tensor, dv: Tensor, dbq: Optional[Tensor] = None, dbk: Optional[Tensor] = None,
-             dbv: Optional[Tensor] = None) -> None:
+             dbv: Optional[Tensor] = None, dropout=None) -> None:
     """dq/dk/dv <- attention backward.  dbq/dbk/dbv (optional fp32 [H*D] views, contiguous) are INCREMENTED by the column sums
     of dq/dk/dv over all tokens: the bias gradients of the producing projections, summed in the kernels' epilogue."""
     for t in (dbq, dbk, dbv):
@@ -276,7 +287,7 @@ def attn_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor
                       LSE=lse.data_ptr(), scale=scale, dtype=dtype_code(q.dtype), dO=gp, lddo=ldg, dQ=dqp, lddq=lddq,
                       dK=dkp, lddk=lddk, dV=dvp, lddv=lddv, delta=delta.data_ptr(),
                       dbq=None if dbq is None else dbq.data_ptr(), dbk=None if dbk is None else dbk.data_ptr(),
-                      dbv=None if dbv is None else dbv.data_ptr())
+                      dbv=None if dbv is None else dbv.data_ptr(), **_drop_fields(dropout))
     check(lib().b200f_attn_bwd(C.byref(args), stream_ptr()), "b200f_attn_bwd")
 
 
@@ -307,17 +318,22 @@ def infonce_grad(x: Tensor, y: Tensor, lse_x: Tensor, lse_y: Tensor, coef: float
                                    ptr(ws), C.c_size_t(ws.numel()), stream_ptr()), "b200f_infonce_grad")
 
 
-def gat_fwd(xp: Tensor, att_src: Tensor, att_dst: Tensor, bias: Tensor, heads: int, slope: float):
+def _drop_args(dropout):
+    d = _drop_fields(dropout)
+    return C.c_float(d["dropout_p"]), C.c_uint32(d["drop_seed_lo"]), C.c_uint32(d["drop_seed_hi"])
+
+
+def gat_fwd(xp: Tensor, att_src: Tensor, att_dst: Tensor, bias: Tensor, heads: int, slope: float, dropout=None):
     B = xp.size(0)
     Cc = bias.numel()
     out = torch.empty((B, 3, Cc), device=xp.device, dtype=xp.dtype)
     alpha = torch.empty((B, 3, heads, 3), device=xp.device, dtype=torch.float32)
     check(lib().b200f_gat_fwd(ptr(xp), ptr(att_src), ptr(att_dst), ptr(bias), ptr(out), ptr(alpha), C.c_int64(B), C.c_int32(heads), C.c_int32(Cc),
-                              C.c_float(slope), dtype_code(xp.dtype), stream_ptr()), "b200f_gat_fwd")
+                              C.c_float(slope), *_drop_args(dropout), dtype_code(xp.dtype), stream_ptr()), "b200f_gat_fwd")
     return out, alpha
 
 
-def gat_bwd(dout: Tensor, out: Tensor, xp: Tensor, alpha: Tensor, att_src: Tensor, att_dst: Tensor, heads: int, slope: float):
+def gat_bwd(dout: Tensor, out: Tensor, xp: Tensor, alpha: Tensor, att_src: Tensor, att_dst: Tensor, heads: int, slope: float, dropout=None):
     B = xp.size(0)
     Cc = out.size(-1)
     dxp = torch.empty_like(xp)
@@ -325,28 +341,29 @@ def gat_bwd(dout: Tensor, out: Tensor, xp: Tensor, alpha: Tensor, att_src: Tenso
     datt_dst = torch.zeros_like(datt_src)
     dbias = torch.zeros(Cc, device=xp.device, dtype=torch.float32)
     check(lib().b200f_gat_bwd(ptr(dout), ptr(out), ptr(xp), ptr(alpha), ptr(att_src), ptr(att_dst), ptr(dxp), ptr(datt_src), ptr(datt_dst),
-                              ptr(dbias), C.c_int64(B), C.c_int32(heads), C.c_int32(Cc), C.c_float(slope), dtype_code(xp.dtype), stream_ptr()),
+                              ptr(dbias), C.c_int64(B), C.c_int32(heads), C.c_int32(Cc), C.c_float(slope), *_drop_args(dropout),
+                              dtype_code(xp.dtype), stream_ptr()),
           "b200f_gat_bwd")
     return dxp, datt_src, datt_dst, dbias
 
 
-def tok3_attn_fwd(qkv: Tensor, heads: int, scale: float):
+def tok3_attn_fwd(qkv: Tensor, heads: int, scale: float, dropout=None):
     B = qkv.size(0)
     H = qkv.size(-1) // 3
     ctx = torch.empty((B, 3, H), device=qkv.device, dtype=qkv.dtype)
     probs = torch.empty((B, heads, 3, 3), device=qkv.device, dtype=torch.float32)
     avgw = torch.empty((B, 3, 3), device=qkv.device, dtype=torch.float32)
     check(lib().b200f_tok3_attn_fwd(ptr(qkv), ptr(ctx), ptr(probs), ptr(avgw), C.c_int64(B), C.c_int32(heads), C.c_int32(H), C.c_float(scale),
-                                    dtype_code(qkv.dtype), stream_ptr()), "b200f_tok3_attn_fwd")
+                                    *_drop_args(dropout), dtype_code(qkv.dtype), stream_ptr()), "b200f_tok3_attn_fwd")
     return ctx, probs, avgw
 
 
-def tok3_attn_bwd(dctx: Tensor, davgw: Optional[Tensor], qkv: Tensor, probs: Tensor, heads: int, scale: float) -> Tensor:
+def tok3_attn_bwd(dctx: Tensor, davgw: Optional[Tensor], qkv: Tensor, probs: Tensor, heads: int, scale: float, dropout=None) -> Tensor:
     B = qkv.size(0)
     H = qkv.size(-1) // 3
     dqkv = torch.empty_like(qkv)
     check(lib().b200f_tok3_attn_bwd(ptr(dctx), ptr(davgw), ptr(qkv), ptr(probs), ptr(dqkv), C.c_int64(B), C.c_int32(heads), C.c_int32(H),
-                                    C.c_float(scale), dtype_code(qkv.dtype), stream_ptr()), "b200f_tok3_attn_bwd")
+                                    C.c_float(scale), *_drop_args(dropout), dtype_code(qkv.dtype), stream_ptr()), "b200f_tok3_attn_bwd")
     return dqkv
 
 

@@ -84,9 +84,20 @@ class _Weights:
         return self.P[name].detach()
 
 
-def _chunk_forward(xs, W: _Weights, H: int, heads: int, pooled_out: Tensor, keep: bool):
+def _site(drop, site: int):
+    """Dropout arguments of one site of a chunk: drop = None or (p, seed_lo, seed_hi of this chunk).  Sites: 2*block = attention
+    probabilities of cross block `block`, 2*block + 1 = its FFN hidden layer, 12 + m = self-attention of modality m."""
+    if drop is None:
+        return None
+    p, lo, hi = drop
+    return p, (lo + 0x632BE5AB * (site + 1)) & 0xFFFFFFFF, hi
+
+
+def _chunk_forward(xs, W: _Weights, H: int, heads: int, pooled_out: Tensor, keep: bool, drop=None):
     """Forward of one chunk.  xs: 3 contiguous [Bc,L,H] tensors.  Writes the pooled attended features into
-    pooled_out [Bc,3H]; returns the stash needed by `_chunk_backward` when `keep`."""
+    pooled_out [Bc,3H]; returns the stash needed by `_chunk_backward` when `keep`.  `drop` (training with fusion_dropout > 0):
+    (p, seed_lo, seed_hi) of this chunk -- attention-probability dropout inside the attention kernels and FFN hidden dropout in
+    the FFN1 GEMM epilogue, both regenerated (not stored) by backward and by the recomputed forward."""
     scale = mha_scale(H, heads)
     Bc = xs[0].size(0)
     Ls = [x.size(1) for x in xs]
@@ -96,13 +107,14 @@ def _chunk_forward(xs, W: _Weights, H: int, heads: int, pooled_out: Tensor, keep
     blk_out = {}
     first_of = {}
     enhanced = [None, None, None]
-    for name, qm, km in BLOCKS:
+    for bi, (name, qm, km) in enumerate(BLOCKS):
         qo, ko = W.q_slot[name], W.kv_slot[name]
-        ctx_, lse = K.attn_fwd(proj[qm][:, :, qo:qo + H], proj[km][:, :, ko:ko + H], proj[km][:, :, ko + H:ko + 2 * H], heads, scale)
+        ctx_, lse = K.attn_fwd(proj[qm][:, :, qo:qo + H], proj[km][:, :, ko:ko + H], proj[km][:, :, ko + H:ko + 2 * H], heads, scale,
+                               dropout=_site(drop, 2 * bi))
         ctx2 = ctx_.view(-1, H)
         s1 = K.linear_fwd(ctx2, W.w(f"{name}.attention.out_proj.weight"), W.f32(f"{name}.attention.out_proj.bias"), residual=x2[qm])
         x1, mean1, rstd1 = K.layernorm_fwd(s1, W.f32(f"{name}.norm1.weight"), W.f32(f"{name}.norm1.bias"), LN_EPS)
-        hid = K.linear_fwd(x1, W.w(f"{name}.ffn.0.weight"), W.f32(f"{name}.ffn.0.bias"), relu=True)
+        hid = K.linear_fwd(x1, W.w(f"{name}.ffn.0.weight"), W.f32(f"{name}.ffn.0.bias"), relu=True, dropout=_site(drop, 2 * bi + 1))
         s2 = K.linear_fwd(hid, W.w(f"{name}.ffn.3.weight"), W.f32(f"{name}.ffn.3.bias"), residual=x1)
         if qm not in first_of:      # first block of this query modality: plain LN2
             first_of[qm] = name
@@ -119,7 +131,7 @@ def _chunk_forward(xs, W: _Weights, H: int, heads: int, pooled_out: Tensor, keep
     for m, mod in enumerate(MODS):
         pre = f"{mod}_self_attn."
         qkv = K.linear_fwd(enhanced[m], W.w(pre + "in_proj_weight"), W.f32(pre + "in_proj_bias")).view(Bc, Ls[m], 3 * H)
-        att, lse = K.attn_fwd(qkv[:, :, :H], qkv[:, :, H:2 * H], qkv[:, :, 2 * H:], heads, scale)
+        att, lse = K.attn_fwd(qkv[:, :, :H], qkv[:, :, H:2 * H], qkv[:, :, 2 * H:], heads, scale, dropout=_site(drop, 12 + m))
         pooled_ctx = K.meanpool_fwd(att)
         K.linear_fwd(pooled_ctx, W.w(pre + "out_proj.weight"), W.f32(pre + "out_proj.bias"), out=pooled_out[:, m * H:(m + 1) * H])
         if keep:
@@ -127,7 +139,7 @@ def _chunk_forward(xs, W: _Weights, H: int, heads: int, pooled_out: Tensor, keep
     return st
 
 
-def _chunk_backward(st, W: _Weights, H: int, heads: int, dpooled: Tensor, G: Dict[str, Tensor], dstack_w, dstack_b, need_dx: bool):
+def _chunk_backward(st, W: _Weights, H: int, heads: int, dpooled: Tensor, G: Dict[str, Tensor], dstack_w, dstack_b, need_dx: bool, drop=None):
     """Backward of one chunk.  dpooled [Bc,3H]; G: fp32 gradient accumulators keyed like the parameters;
     dstack_w/dstack_b: accumulators of the stacked projections.  Returns [dx_text, dx_audio, dx_video] or None."""
     scale = mha_scale(H, heads)
@@ -146,20 +158,23 @@ def _chunk_backward(st, W: _Weights, H: int, heads: int, dpooled: Tensor, G: Dic
         qkv = s["qkv"]
         db = G[pre + "in_proj_bias"]        # Q / V bias gradients are summed in the attention-backward epilogue; the K-bias
         K.attn_bwd(d_att, qkv[:, :, :H], qkv[:, :, H:2 * H], qkv[:, :, 2 * H:], s["att"], s["lse"], heads, scale,   # gradient is
-                   dqkv[:, :, :H], dqkv[:, :, H:2 * H], dqkv[:, :, 2 * H:], dbq=db[:H], dbv=db[2 * H:])            # identically 0 (softmax shift invariance)
+                   dqkv[:, :, :H], dqkv[:, :, H:2 * H], dqkv[:, :, 2 * H:], dbq=db[:H], dbv=db[2 * H:],           # identically 0 (softmax shift invariance)
+                   dropout=_site(drop, 12 + m))
         dqkv2 = dqkv.view(-1, 3 * H)
         K.linear_wgrad(dqkv2, s["enh"], G[pre + "in_proj_weight"])
         d_enh[m] = K.linear_dgrad(dqkv2, W.w(pre + "in_proj_weight"))
     dproj = [torch.empty_like(p) for p in proj]
     d_s1 = {}
-    for name, qm, km in BLOCKS:
+    inv_keep = 1.0 if drop is None else 1.0 / (1.0 - drop[0])
+    for bi, (name, qm, km) in enumerate(BLOCKS):
         s = st[name]
         # d(enhanced) reaches both blocks' LN2 outputs and the input unchanged
         ds2 = K.layernorm_bwd(d_enh[qm], s["s2"], s["mean2"], s["rstd2"], W.f32(f"{name}.norm2.weight"),
                               G[f"{name}.norm2.weight"], G[f"{name}.norm2.bias"], dxsum=G[f"{name}.ffn.3.bias"])   # + bias grad of FFN2
         K.linear_wgrad(ds2, s["hid"], G[f"{name}.ffn.3.weight"])
         dhid = K.linear_dgrad(ds2, W.w(f"{name}.ffn.3.weight"), relu_mask=s["hid"],       # ReLU' and the FFN1 bias gradient
-                              colsum=G[f"{name}.ffn.0.bias"])                                # (column sums) fused in the epilogue
+                              colsum=G[f"{name}.ffn.0.bias"], alpha=inv_keep)              # (column sums) fused in the epilogue;
+        # with dropout the stored hidden is zero where dropped, so the same mask covers it and alpha carries 1/(1-p)
         K.linear_wgrad(dhid, s["x1"], G[f"{name}.ffn.0.weight"])
         dx1 = K.linear_dgrad(dhid, W.w(f"{name}.ffn.0.weight"), residual=ds2)             # + residual path x1 -> s2
         ds1 = K.layernorm_bwd(dx1, s["s1"], s["mean1"], s["rstd1"], W.f32(f"{name}.norm1.weight"),
@@ -171,7 +186,7 @@ def _chunk_backward(st, W: _Weights, H: int, heads: int, dpooled: Tensor, G: Dic
         qo, ko = W.q_slot[name], W.kv_slot[name]
         K.attn_bwd(dctx, proj[qm][:, :, qo:qo + H], proj[km][:, :, ko:ko + H], proj[km][:, :, ko + H:ko + 2 * H], s["ctx"], s["lse"],
                    heads, scale, dproj[qm][:, :, qo:qo + H], dproj[km][:, :, ko:ko + H], dproj[km][:, :, ko + H:ko + 2 * H],
-                   dbq=dstack_b[qm][qo:qo + H], dbv=dstack_b[km][ko + H:ko + 2 * H])
+                   dbq=dstack_b[qm][qo:qo + H], dbv=dstack_b[km][ko + H:ko + 2 * H], dropout=_site(drop, 2 * bi))
     dxs = []
     for m in range(3):
         dp2 = dproj[m].view(-1, 6 * H)
@@ -192,6 +207,14 @@ def stash_bytes_per_sample(Ls, H: int, elem: int) -> int:
     return (per_tok + per_qtok) * tok * elem
 
 
+def _chunk_drop(drop, ci: int):
+    """(p, seed_lo, seed_hi) of chunk `ci`: every chunk (rows restart at 0 inside a chunk) gets its own high seed word."""
+    if drop is None:
+        return None
+    p, lo, hi = drop
+    return p, lo, (hi + 0x9E3779B1 * (ci + 1)) & 0xFFFFFFFF
+
+
 class MulTFn(torch.autograd.Function):
     """(text, audio, video [B,L,H]) + MulT parameters -> pooled attended features [B,3H].
 
@@ -199,7 +222,7 @@ class MulTFn(torch.autograd.Function):
     for backward; the remaining chunks are recomputed chunk by chunk in backward (bounded memory at any batch)."""
 
     @staticmethod
-    def forward(ctx, t, a, v, H, heads, chunk, stash_budget, names, *params):
+    def forward(ctx, t, a, v, H, heads, chunk, stash_budget, drop, names, *params):
         xs = [x.contiguous() for x in (t, a, v)]
         B = xs[0].size(0)
         P = dict(zip(names, params))
@@ -212,16 +235,16 @@ class MulTFn(torch.autograd.Function):
         for ci, b0 in enumerate(range(0, B, chunk)):
             b1 = min(B, b0 + chunk)
             keep = ci < n_keep
-            st = _chunk_forward([x[b0:b1] for x in xs], W, H, heads, pooled[b0:b1], keep=keep)
+            st = _chunk_forward([x[b0:b1] for x in xs], W, H, heads, pooled[b0:b1], keep=keep, drop=_chunk_drop(drop, ci))
             if keep:
                 stash[b0] = st
-        ctx.cfg = (H, heads, chunk, names)
+        ctx.cfg = (H, heads, chunk, names, drop)
         ctx.W, ctx.stash, ctx.xs = (W if need_grad else None), stash, (xs if need_grad else None)
         return pooled
 
     @staticmethod
     def backward(ctx, dpooled):
-        H, heads, chunk, names = ctx.cfg
+        H, heads, chunk, names, drop = ctx.cfg
         W, xs = ctx.W, ctx.xs
         B = xs[0].size(0)
         dev = xs[0].device
@@ -238,8 +261,8 @@ class MulTFn(torch.autograd.Function):
             if st is None:
                 if scratch is None:
                     scratch = torch.empty((min(chunk, B), 3 * H), device=dev, dtype=xs[0].dtype)
-                st = _chunk_forward([x[b0:b1] for x in xs], W, H, heads, scratch[:b1 - b0], keep=True)
-            out = _chunk_backward(st, W, H, heads, dpooled[b0:b1], G, dstack_w, dstack_b, need_dx)
+                st = _chunk_forward([x[b0:b1] for x in xs], W, H, heads, scratch[:b1 - b0], keep=True, drop=_chunk_drop(drop, b0 // chunk))
+            out = _chunk_backward(st, W, H, heads, dpooled[b0:b1], G, dstack_w, dstack_b, need_dx, drop=_chunk_drop(drop, b0 // chunk))
             if need_dx:
                 for m in range(3):
                     dxs[m][b0:b1].copy_(out[m])
@@ -255,6 +278,6 @@ class MulTFn(torch.autograd.Function):
                 dst_w[lo:lo + n].copy_(dstack_w[m][row:row + n])
                 dst_b[lo:lo + n].copy_(dstack_b[m][row:row + n])
                 row += n
-        grads = [G[n] if ctx.needs_input_grad[8 + i] else None for i, n in enumerate(names)]
+        grads = [G[n] if ctx.needs_input_grad[9 + i] else None for i, n in enumerate(names)]
         return (dxs[0] if need_dx else None, dxs[1] if need_dx else None, dxs[2] if need_dx else None,
-                None, None, None, None, None, *grads)
+                None, None, None, None, None, None, *grads)

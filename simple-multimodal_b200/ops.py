@@ -96,6 +96,18 @@ def manual_seed(seed: int) -> None:
     _DropoutState.seed, _DropoutState.offset = int(seed), 0
 
 
+def next_drop_seed():
+    """A fresh (seed_lo, seed_hi) pair for one in-kernel dropout site (attention probabilities, FFN hidden, GAT / 3-token
+    attention weights): splitmix64 of the running offset under the package seed.  The pair fully determines the mask, so
+    backward (and the recomputed forward of MulT chunks) regenerate it instead of storing it."""
+    _DropoutState.offset += 1
+    z = (_DropoutState.seed * 0x9E3779B97F4A7C15 + _DropoutState.offset * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    z ^= z >> 31
+    return z & 0xFFFFFFFF, z >> 32
+
+
 class Concat3Fn(torch.autograd.Function):
     """[t*m0 | a*m1 | v*m2] (fusion_layers.py:38,350,437 with the modality-dropout multiply folded in)."""
 
@@ -155,22 +167,22 @@ class AttentionFn(torch.autograd.Function):
     Q / K / V column offsets given (so no slicing copies)."""
 
     @staticmethod
-    def forward(ctx, pq, pkv, q_off, k_off, v_off, H, heads, scale):
+    def forward(ctx, pq, pkv, q_off, k_off, v_off, H, heads, scale, dropout=None):
         q, k, v = pq[:, :, q_off:q_off + H], pkv[:, :, k_off:k_off + H], pkv[:, :, v_off:v_off + H]
-        o, lse = K.attn_fwd(q, k, v, heads, scale)
-        ctx.cfg = (q_off, k_off, v_off, H, heads, scale, pq is pkv)
+        o, lse = K.attn_fwd(q, k, v, heads, scale, dropout=dropout)
+        ctx.cfg = (q_off, k_off, v_off, H, heads, scale, pq is pkv, dropout)
         ctx.save_for_backward(pq, pkv, o, lse)
         return o
 
     @staticmethod
     def backward(ctx, do):
         pq, pkv, o, lse = ctx.saved_tensors
-        q_off, k_off, v_off, H, heads, scale, same = ctx.cfg
+        q_off, k_off, v_off, H, heads, scale, same, dropout = ctx.cfg
         dpq = torch.zeros_like(pq)
         dpkv = dpq if same else torch.zeros_like(pkv)
         K.attn_bwd(_c(do), pq[:, :, q_off:q_off + H], pkv[:, :, k_off:k_off + H], pkv[:, :, v_off:v_off + H], o, lse, heads, scale,
-                   dpq[:, :, q_off:q_off + H], dpkv[:, :, k_off:k_off + H], dpkv[:, :, v_off:v_off + H])
-        return dpq, (None if same else dpkv), None, None, None, None, None, None
+                   dpq[:, :, q_off:q_off + H], dpkv[:, :, k_off:k_off + H], dpkv[:, :, v_off:v_off + H], dropout=dropout)
+        return dpq, (None if same else dpkv), None, None, None, None, None, None, None
 
 
 class LayerNormFn(torch.autograd.Function):
@@ -204,39 +216,39 @@ class GatFn(torch.autograd.Function):
     """relu(GATConv core) on dense 3-node graphs given the `lin` projection xp [B,3,heads*C]."""
 
     @staticmethod
-    def forward(ctx, xp, att_src, att_dst, bias, heads, slope):
+    def forward(ctx, xp, att_src, att_dst, bias, heads, slope, dropout=None):
         xp = _c(xp)
         a_s, a_d = att_src.detach().reshape(-1).contiguous(), att_dst.detach().reshape(-1).contiguous()
-        out, alpha = K.gat_fwd(xp, a_s, a_d, bias.detach(), heads, slope)
-        ctx.cfg = (heads, slope, att_src.shape)
+        out, alpha = K.gat_fwd(xp, a_s, a_d, bias.detach(), heads, slope, dropout=dropout)
+        ctx.cfg = (heads, slope, att_src.shape, dropout)
         ctx.save_for_backward(xp, out, alpha, a_s, a_d)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         xp, out, alpha, a_s, a_d = ctx.saved_tensors
-        heads, slope, ashape = ctx.cfg
-        dxp, ds, dd, dbias = K.gat_bwd(_c(dout), out, xp, alpha, a_s, a_d, heads, slope)
-        return dxp, ds.reshape(ashape), dd.reshape(ashape), dbias, None, None
+        heads, slope, ashape, dropout = ctx.cfg
+        dxp, ds, dd, dbias = K.gat_bwd(_c(dout), out, xp, alpha, a_s, a_d, heads, slope, dropout=dropout)
+        return dxp, ds.reshape(ashape), dd.reshape(ashape), dbias, None, None, None
 
 
 class Tok3AttnFn(torch.autograd.Function):
     """Self-attention over the 3 modality tokens; returns (ctx [B,3,H], head-averaged weights [B,3,3] fp32)."""
 
     @staticmethod
-    def forward(ctx, qkv, heads, scale):
+    def forward(ctx, qkv, heads, scale, dropout=None):
         qkv = _c(qkv)
-        out, probs, avgw = K.tok3_attn_fwd(qkv, heads, scale)
-        ctx.cfg = (heads, scale)
+        out, probs, avgw = K.tok3_attn_fwd(qkv, heads, scale, dropout=dropout)
+        ctx.cfg = (heads, scale, dropout)
         ctx.save_for_backward(qkv, probs)
         return out, avgw
 
     @staticmethod
     def backward(ctx, dctx, davgw):
         qkv, probs = ctx.saved_tensors
-        heads, scale = ctx.cfg
+        heads, scale, dropout = ctx.cfg
         davgw = None if davgw is None else _c(davgw.float())
-        return K.tok3_attn_bwd(_c(dctx), davgw, qkv, probs, heads, scale), None, None
+        return K.tok3_attn_bwd(_c(dctx), davgw, qkv, probs, heads, scale, dropout=dropout), None, None, None
 
 
 class GateMixFn(torch.autograd.Function):

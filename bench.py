@@ -132,6 +132,7 @@ def run_reference(args, kind, lens, flag, cpu_batch, world, rank):
     if rank != 0:
         return
     from oracle import fusion_oracle as fo
+    fo.TRAIN_DROPOUT = args.dropout
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     P = {k: v.requires_grad_(True) for k, v in fo.init_params(kind, H=H, heads=HEADS, seed=0).items()}
@@ -158,15 +159,16 @@ def run_reference(args, kind, lens, flag, cpu_batch, world, rank):
     line = {"impl": "reference", "metric": "fusion_head_fwd_bwd_samples_per_sec", "value": val, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "head": kind, "seq_lens": lens, "hidden": H, "note": "CPU, bounded sample"},
+            "config": {"workload": args.workload, "head": kind, "seq_lens": lens, "hidden": H, "dropout": args.dropout, "note": "CPU, bounded sample"},
             "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port",
                              "sample": f"{cpu_batch} samples/step x {args.steps} steps of the same workload (fp32, torch CPU ops, all host threads)"},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(kind, lens, flag, cpu_batch, budget_s=20.0):
+def cpu_baseline(kind, lens, flag, cpu_batch, budget_s=20.0, dropout=0.0):
     from oracle import fusion_oracle as fo
+    fo.TRAIN_DROPOUT = dropout
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     P = {k: v.requires_grad_(True) for k, v in fo.init_params(kind, H=H, heads=HEADS, seed=0).items()}
@@ -196,6 +198,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--chunk", type=int, default=0, help="MulT chunk size (samples)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.1,
+                    help="fusion_dropout / graph_dropout of the head in training mode (reference default, config.py:30,41: 0.1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -223,6 +227,7 @@ def main():
 
     b_global = batch * world
     torch.manual_seed(0)                              # random-init weights, the reference's default initialisers
+    Cfg.fusion_dropout = Cfg.graph_dropout = args.dropout
     head = getattr(pkg.fusion_layers, {"mult": "MultimodalTransformer", "hierarchical": "HierarchicalFusion",
                                        "contrastive": "ContrastiveFusion", "early": "EarlyFusion"}[kind])(Cfg).to(dev)
     head.train()
@@ -344,7 +349,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": args.workload, "head": kind, "batch_per_gpu": batch, "global_batch": b_global, "seq_lens": lens,
-                       "hidden": H, "heads": HEADS, "dropout": 0.0, "parallelism": f"dp{world}", "warmup_steps_run": warm_done,
+                       "hidden": H, "heads": HEADS, "dropout": args.dropout, "parallelism": f"dp{world}", "warmup_steps_run": warm_done,
                        "l2": "inputs+activations per step exceed the 126 MB L2" if h2d_bytes > 126e6 else "small working set (latency-bound config)",
                        "algorithmic_tflop_per_step": gflop * batch / 1e3,
                        "model_tflops_per_gpu": gflop * batch / 1e3 / (ms * 1e-3),
@@ -362,7 +367,7 @@ def main():
                          "share_of_step": gemm_ms / ms if ms else None},
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(kind, lens, flag, cpu_batch)
+            line["cpu_baseline"] = cpu_baseline(kind, lens, flag, cpu_batch, dropout=args.dropout)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -38,6 +38,10 @@ LN_EPS = 1e-5          # nn.LayerNorm default, models/fusion_layers.py:192-193
 L2_EPS = 1e-12         # F.normalize default, models/fusion_layers.py:338-340
 GAT_HEADS = 4          # models/fusion_layers.py:227
 GAT_SLOPE = 0.2        # GATConv default negative_slope
+# Timing knob for bench.py's CPU arm ONLY: > 0 adds the reference's training-mode dropouts of the MulT blocks (attention
+# probabilities, torch nn/functional.py:6647-6650; FFN hidden, models/fusion_layers.py:197-199) with torch's own RNG, so that
+# the CPU baseline does the same work as the CUDA arm at fusion_dropout = 0.1.  Parity (tests/) always runs with 0.
+TRAIN_DROPOUT = 0.0
 
 
 def _p(P: Params, prefix: str, name: str) -> Tensor:
@@ -92,6 +96,8 @@ def multi_head_attention(q_in: Tensor, kv_in: Tensor, P: Params, prefix: str,
     v = v.reshape(B, Lk, heads, d).permute(0, 2, 1, 3)
     scores = torch.matmul(q, k.transpose(-1, -2))          # [B,h,Lq,Lk]
     prob = softmax_lastdim(scores)
+    if TRAIN_DROPOUT > 0.0:
+        prob = torch.nn.functional.dropout(prob, TRAIN_DROPOUT, True)
     ctx = torch.matmul(prob, v)                            # [B,h,Lq,d]
     ctx = ctx.permute(0, 2, 1, 3).reshape(B, Lq, H)
     return affine(ctx, w_out, b_out), prob.mean(dim=1)
@@ -102,6 +108,8 @@ def cross_block(query: Tensor, key_value: Tensor, P: Params, prefix: str, heads:
     attn, _ = multi_head_attention(query, key_value, P, prefix + "attention.", heads)
     x = layer_norm(query + attn, _p(P, prefix, "norm1.weight"), _p(P, prefix, "norm1.bias"))
     hid = torch.relu(affine(x, _p(P, prefix, "ffn.0.weight"), _p(P, prefix, "ffn.0.bias")))
+    if TRAIN_DROPOUT > 0.0:
+        hid = torch.nn.functional.dropout(hid, TRAIN_DROPOUT, True)
     y = affine(hid, _p(P, prefix, "ffn.3.weight"), _p(P, prefix, "ffn.3.bias"))
     return layer_norm(x + y, _p(P, prefix, "norm2.weight"), _p(P, prefix, "norm2.bias"))
 

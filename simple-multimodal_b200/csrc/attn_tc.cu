@@ -482,7 +482,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const uint64_t nmc2 = f2_pack(nmc, nmc);
         uint64_t lsum2 = 0ull;
         if (j > 0) {                                   // PV_t(j-1) must have retired before P_t is overwritten / O_t rescaled
-          mbar_wait(&pv_done[t], pv_cnt & 1);
+          mbar_wait(&pv_done[t], pv_cnt & 1);          // (holding all of P_t in registers to wait later spills at 216 registers: measured slower)
           ++pv_cnt;
           tc_fence_after();
         }
@@ -1097,13 +1097,9 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sdp_free[t]);      // the next S_t / dP_t may be computed under this tile's exp work
-        if (j > 0) {                                   // dQ_t(j-1) must have retired before the dS_t tile is rewritten
-          mbar_wait(&ds_free[t], dsf_cnt & 1);
-          ++dsf_cnt;
-        }
+        uint32_t pk[2][16];                            // all of dS_t(j) in registers first: the wait for the smem tile comes after the math
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
-          uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {     // dS = P o (dP - delta) * scale, two elements per FFMA2 / FMUL2
             float x0, x1, d0, d1;
@@ -1115,12 +1111,19 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             }
             const uint64_t t2 = f2_fma(f2_pack_u(rp[hf][i], rp[hf][i + 1]), m2, ndl2);
             f2_unpack(f2_mul(f2_pack(ex2_approx(x0), ex2_approx(x1)), t2), d0, d1);
-            pk[i >> 1] = pack_bf16(d0, d1);
+            pk[hf][i >> 1] = pack_bf16(d0, d1);
           }
+        }
+        if (j > 0) {                                   // dQ_t(j-1) must have retired before the dS_t tile is rewritten
+          mbar_wait(&ds_free[t], dsf_cnt & 1);
+          ++dsf_cnt;
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4)
-            *reinterpret_cast<uint4*>(ds_tile + sw128_offset(row, hf * 4 + q4)) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
-        }
+            *reinterpret_cast<uint4*>(ds_tile + sw128_offset(row, hf * 4 + q4)) =
+                make_uint4(pk[hf][q4 * 4], pk[hf][q4 * 4 + 1], pk[hf][q4 * 4 + 2], pk[hf][q4 * 4 + 3]);
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
@@ -1297,14 +1300,21 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       const long long stat_base = ((long long)b * p.H + h) * p.Lq;
       const uint32_t jc = uint32_t(k0 + row) * kDropColMul;       // dropout: this thread's key column
       const float sck = p.scale * p.inv_keep;
+      // per-query statistics of a tile: thread t128 < 64 fetches LSE, the others delta; the NEXT tile's value is requested one
+      // iteration ahead so the global-load latency hides under this tile's exp work
+      auto load_stat = [&](int i) -> float {
+        const int qi = i * BT + (t128 & 63);
+        return qi < p.Lq ? (t128 < 64 ? p.LSE[stat_base + qi] : p.delta[stat_base + qi]) : 0.f;
+      };
+      float stat_next = load_stat(0);
       for (int i = 0; i < n_tiles; ++i) {
         float* sl = stats + (sf_cnt & 1) * 3 * BT;   // [lse2[64] | delta[64] | row key[64]] of this tile's queries; parity runs across items
         {
           const int qi = i * BT + (t128 & 63);
-          float v = 0.f;                             // stored negated (and delta pre-scaled) so the inner loop is pure FFMA2
-          if (qi < p.Lq) v = t128 < 64 ? -p.LSE[stat_base + qi] * LOG2E : -p.delta[stat_base + qi] * p.scale;
-          sl[t128] = v;
+          // stored negated (and delta pre-scaled) so the inner loop is pure FFMA2
+          sl[t128] = t128 < 64 ? -stat_next * LOG2E : -stat_next * p.scale;
           if (DROP && t128 < 64) reinterpret_cast<uint32_t*>(sl)[2 * BT + t128] = drop_row_key(p.drop_seed_lo, p.drop_seed_hi, uint32_t(stat_base + qi));
+          if (i + 1 < n_tiles) stat_next = load_stat(i + 1);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
         mbar_wait(&sdp_full[t], sf_cnt & 1);
@@ -1319,13 +1329,9 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sdp_free[t]);      // the next S^T_t / dP^T_t may be computed under this tile's exp work
-        if (i > 0) {                                   // dV_t / dK_t MMAs of the previous tile must have retired before P^T / dS^T are rewritten
-          mbar_wait(&ds_free[t], dsf_cnt & 1);
-          ++dsf_cnt;
-        }
+        uint32_t pp[2][16], pd[2][16];                 // P^T / dS^T of the tile in registers first: the wait for the smem tiles comes after the math
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
-          uint32_t pp[16], pd[16];
           const uint64_t* nl2 = reinterpret_cast<const uint64_t*>(sl + hf * 32);         // -lse2 of the queries, pairs (warp-broadcast reads)
           const uint64_t* nd2 = reinterpret_cast<const uint64_t*>(sl + BT + hf * 32);    // -delta*scale
 #pragma unroll
@@ -1344,16 +1350,22 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             }
             const uint64_t t2 = f2_fma(f2_pack_u(rp[hf][e], rp[hf][e + 1]), m2, nd2[e >> 1]);
             f2_unpack(f2_mul(f2_pack(p0, p1), t2), d0, d1);
-            pp[e >> 1] = pack_bf16(pd0, pd1);
-            pd[e >> 1] = pack_bf16(d0, d1);
+            pp[hf][e >> 1] = pack_bf16(pd0, pd1);
+            pd[hf][e >> 1] = pack_bf16(d0, d1);
           }
+        }
+        if (i > 0) {                                   // dV_t / dK_t MMAs of the previous tile must have retired before P^T / dS^T are rewritten
+          mbar_wait(&ds_free[t], dsf_cnt & 1);
+          ++dsf_cnt;
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
             const uint32_t off = sw128_offset(row, hf * 4 + q4);
-            *reinterpret_cast<uint4*>(p_tile + off) = make_uint4(pp[q4 * 4], pp[q4 * 4 + 1], pp[q4 * 4 + 2], pp[q4 * 4 + 3]);
-            *reinterpret_cast<uint4*>(ds_tile + off) = make_uint4(pd[q4 * 4], pd[q4 * 4 + 1], pd[q4 * 4 + 2], pd[q4 * 4 + 3]);
+            *reinterpret_cast<uint4*>(p_tile + off) = make_uint4(pp[hf][q4 * 4], pp[hf][q4 * 4 + 1], pp[hf][q4 * 4 + 2], pp[hf][q4 * 4 + 3]);
+            *reinterpret_cast<uint4*>(ds_tile + off) = make_uint4(pd[hf][q4 * 4], pd[hf][q4 * 4 + 1], pd[hf][q4 * 4 + 2], pd[hf][q4 * 4 + 3]);
           }
-        }
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();

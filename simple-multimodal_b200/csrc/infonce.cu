@@ -9,6 +9,16 @@
 
 namespace b200f {
 
+// fused tcgen05 path (infonce_tc.cu): the similarity block stays in TMEM; this file's GEMM + row-kernel route remains for fp32
+// parity mode, embedding widths the fused kernels do not take, and A/B testing (b200f_debug_set(6, 1))
+bool infonce_tc_eligible(const void* x, const void* y, int64_t Bl, int64_t Bg, int32_t D, int32_t dtype);
+size_t infonce_tc_workspace_bytes(int64_t Bl);
+int infonce_lse_tc(const void* x, const void* y, float* lse, float* diag, int64_t Bl, int64_t Bg, int32_t D, int64_t diag_off, float inv_tau,
+                   void* workspace, cudaStream_t st);
+int infonce_grad_tc(const void* x, const void* y, const float* lse_x, const float* lse_y, float coef, const float* gscale_dev, float* dx, int64_t Bl,
+                    int64_t Bg, int32_t D, int64_t diag_off, float inv_tau, cudaStream_t st);
+int g_infonce_variant = 0;       // 0 = fused tcgen05 kernels when eligible, 1 = GEMM + row kernels
+
 // warp per row: online (max, sum) over the row of S, float4 loads
 __global__ void __launch_bounds__(256) row_lse_kernel(const float* __restrict__ S, long long ld, float* __restrict__ lse, float* __restrict__ diag,
                                                       long long Bl, long long Bg, long long diag_off) {
@@ -87,6 +97,8 @@ int b200f_infonce_lse(const void* x, const void* y, float* lse, float* diag, int
   B200F_REQUIRE(!diag || (diag_off >= 0 && diag_off + Bl <= Bg), B200F_ERR_SHAPE, "infonce: diagonal offset %lld out of range", (long long)diag_off);
   B200F_REQUIRE(workspace && workspace_bytes >= b200f_infonce_workspace_bytes(Bl, Bg, dtype, 0) && aligned16(workspace), B200F_ERR_SHAPE,
                 "infonce: workspace too small (%zu bytes)", workspace_bytes);
+  if (g_infonce_variant == 0 && infonce_tc_eligible(x, y, Bl, Bg, D, dtype) && workspace_bytes >= infonce_tc_workspace_bytes(Bl))
+    return infonce_lse_tc(x, y, lse, diag, Bl, Bg, D, diag_off, inv_tau, workspace, static_cast<cudaStream_t>(stream));
   const long long bg8 = (Bg + 7) / 8 * 8;
   float* S = static_cast<float*>(workspace);
   int rc = sim_block(x, y, S, bg8, Bl, Bg, D, inv_tau, dtype, stream);
@@ -103,6 +115,10 @@ int b200f_infonce_grad(const void* x, const void* y, const float* lse_x, const f
   B200F_REQUIRE(workspace && workspace_bytes >= b200f_infonce_workspace_bytes(Bl, Bg, dtype, 1) && aligned16(workspace), B200F_ERR_SHAPE,
                 "infonce: workspace too small (%zu bytes)", workspace_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g_infonce_variant == 0 && infonce_tc_eligible(x, y, Bl, Bg, D, dtype) && aligned16(dx)) {
+    if (!accumulate) B200F_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)Bl * D * 4, st));
+    return infonce_grad_tc(x, y, lse_x, lse_y, coef, gscale_dev, dx, Bl, Bg, D, diag_off, inv_tau, st);
+  }
   const long long bg8 = (Bg + 7) / 8 * 8;
   float* S = static_cast<float*>(workspace);
   void* W = static_cast<char*>(workspace) + (size_t)Bl * bg8 * 4;

@@ -230,6 +230,21 @@ int b200f_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, uin
 int b200f_dropout_rowcol(void* x, int64_t ldx, int64_t M, int64_t N, float p, uint32_t seed_lo, uint32_t seed_hi, int32_t dtype,
                          void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Heads directly downstream of the fusion output.
+ * row_softmax: probs[b,:] = softmax(x[b,:C]) (F.softmax of the emotion / uncertainty logits, reference
+ * models/multimodal_model.py:160-164); ce_ls: nn.CrossEntropyLoss(label_smoothing) with mean reduction
+ * (training/advanced_trainer.py:53,139): *loss_sum += sum_b loss_b (caller divides by B), probs [B,C] fp32
+ * saved for backward; *bad_target is set to 1 if a target is outside [0, C).  C <= 64.
+ * ------------------------------------------------------------------------------------------- */
+int b200f_row_softmax_fwd(const void* x, int64_t ldx, float* probs, int64_t B, int32_t C, int32_t dtype, void* stream);
+int b200f_row_softmax_bwd(const float* probs, const float* dprobs, void* dx, int64_t lddx, int64_t B, int32_t C, int32_t dtype,
+                          void* stream);
+int b200f_ce_ls_fwd(const void* logits, int64_t ldx, const int64_t* target, float label_smoothing, float* probs, float* loss_sum,
+                    int32_t* bad_target, int64_t B, int32_t C, int32_t dtype, void* stream);
+int b200f_ce_ls_bwd(const float* probs, const int64_t* target, float label_smoothing, const float* gscale_dev, void* dlogits,
+                    int64_t lddx, int64_t B, int32_t C, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

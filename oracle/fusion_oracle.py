@@ -402,6 +402,41 @@ def synthetic_features(batch: int, lens=(None, None, None), H: int = 512, seed: 
     return tuple(out)
 
 
+# ----------------------------------------------------------------------------
+# heads directly downstream of the fusion output
+# ----------------------------------------------------------------------------
+def emotion_classifier(f: Tensor, P: Params, prefix: str = "") -> Tensor:
+    """EmotionClassifier.forward, models/multimodal_model.py:210-219: only the main logits are returned."""
+    h = torch.relu(affine(f, _p(P, prefix, "classifier.0.weight"), _p(P, prefix, "classifier.0.bias")))
+    return affine(h, _p(P, prefix, "classifier.3.weight"), _p(P, prefix, "classifier.3.bias"))
+
+
+def auxiliary_heads(f: Tensor, P: Params, prefix: str = "") -> Dict[str, Tensor]:
+    """valence / arousal regressors and the uncertainty head of MultimodalEmotionModel (multimodal_model.py:55-60,146-164)."""
+    lin = lambda n: affine(f, _p(P, prefix, n + ".weight"), _p(P, prefix, n + ".bias"))
+    return {"valence": lin("valence_regressor"), "arousal": lin("arousal_regressor"),
+            "uncertainty": softmax_lastdim(lin("uncertainty_head"))}
+
+
+def cross_entropy_label_smoothing(logits: Tensor, target: Tensor, eps: float = 0.1) -> Tensor:
+    """nn.CrossEntropyLoss(label_smoothing=eps), mean reduction (training/advanced_trainer.py:53,139):
+    (1-eps) * NLL(target) + eps * mean_c(-log p_c), averaged over the batch."""
+    logp = logits - torch.logsumexp(logits, dim=-1, keepdim=True)
+    nll = -logp.gather(1, target[:, None]).squeeze(1)
+    return ((1.0 - eps) * nll + eps * (-logp.mean(dim=-1))).mean()
+
+
+def init_head_params(H: int = 512, num_emotions: int = 7, seed: int = 0) -> Params:
+    """nn.Linear default init for EmotionClassifier + the three auxiliary heads (reference state_dict names)."""
+    g = torch.Generator().manual_seed(seed)
+    P: Params = {}
+    for name, o, i in (("classifier.0", H // 2, H), ("classifier.3", num_emotions, H // 2), ("sentiment_classifier", 3, H),
+                       ("positive_classifier", 2, H), ("negative_classifier", 4, H), ("valence_regressor", 1, H),
+                       ("arousal_regressor", 1, H), ("uncertainty_head", num_emotions, H)):
+        _put_linear(g, P, name, o, i)
+    return P
+
+
 HEADS = {
     "early": early_fusion, "late": late_fusion, "mult": mult_fusion, "graph": graph_fusion,
     "contrastive": contrastive_fusion, "adaptive": adaptive_fusion, "hierarchical": hierarchical_fusion,

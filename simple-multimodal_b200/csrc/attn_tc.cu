@@ -355,7 +355,8 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     }
     __syncwarp();
   } else if (warp == 9) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();   // warp-uniform loops; only the MMA / commit instructions are predicated
       constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, TK, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(TQ, HD, 0, 1);
       uint32_t g = 0, it = 0, pr_cnt[2] = {0, 0}, o_cnt[2] = {0, 0}, s_cnt[2] = {0, 0};
@@ -370,8 +371,8 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mbar_wait(&s_free[t], (s_cnt[t] & 1) ^ 1);     // first use passes immediately
         ++s_cnt[t];
         tc_fence_after();
-        umma_chain<HD / 16>(tmem_base + t * TK, q_lo + t * TILE16, 2, k_lo + st * TILE16, 2, idesc_s, 0);
-        umma_commit(&s_full[t]);
+        if (leader) umma_chain<HD / 16>(tmem_base + t * TK, q_lo + t * TILE16, 2, k_lo + st * TILE16, 2, idesc_s, 0);
+        if (leader) umma_commit(&s_full[t]);
       };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int qb = item % n_qblk;
@@ -382,7 +383,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           mbar_wait(&kv_full[st], (g / F2_ST) & 1);
           tc_fence_after();
           for (int t = 0; t < nt; ++t) issue_s(t, st);
-          if (n_tiles == 1) umma_commit(q_empty);
+          if (n_tiles == 1) if (leader) umma_commit(q_empty);
         }
         for (int j = 0; j < n_tiles; ++j) {
           const int st = (g + j) % F2_ST;
@@ -391,7 +392,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             mbar_wait(&kv_full[stn], ((g + j + 1) / F2_ST) & 1);
             tc_fence_after();
             for (int t = 0; t < nt; ++t) issue_s(t, stn);
-            if (j + 2 == n_tiles) umma_commit(q_empty);
+            if (j + 2 == n_tiles) if (leader) umma_commit(q_empty);
           }
           const int ksteps = (min(TK, p.Lk - j * TK) + 15) >> 4;   // P columns past ceil32(valid) are never written
           for (int t = 0; t < nt; ++t) {
@@ -402,20 +403,20 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             const uint32_t t_o = tmem_base + 2 * TK + t * HD;
             const uint32_t pa = p_lo + t * PT16, vb = v_lo + st * TILE16;     // P: two K-major halves of 64 keys, (TQ * 128) B apart
             if (ksteps == 8) {
-              umma_chain<4>(t_o, pa, 2, vb, 128, idesc_o, j > 0);
-              umma_chain<4>(t_o, pa + TQ * 128 / 16, 2, vb + 4 * 128, 128, idesc_o, 1);
+              if (leader) umma_chain<4>(t_o, pa, 2, vb, 128, idesc_o, j > 0);
+              if (leader) umma_chain<4>(t_o, pa + TQ * 128 / 16, 2, vb + 4 * 128, 128, idesc_o, 1);
             } else {
               for (int k = 0; k < ksteps; ++k)
-                umma_ss(t_o, umma_desc_lo(pa + (k >> 2) * (TQ * 128 / 16) + (k & 3) * 2), umma_desc_lo(vb + k * 128), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                if (leader) umma_ss(t_o, umma_desc_lo(pa + (k >> 2) * (TQ * 128 / 16) + (k & 3) * 2), umma_desc_lo(vb + k * 128), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
             }
             if (j + 1 < n_tiles) {
-              umma_commit(&pv_done[t]);
+              if (leader) umma_commit(&pv_done[t]);
             } else {
-              umma_commit(&o_full[t]);
+              if (leader) umma_commit(&o_full[t]);
               ++o_cnt[t];
             }
           }
-          umma_commit(&kv_empty[st]);
+          if (leader) umma_commit(&kv_empty[st]);
         }
         g += n_tiles;
       }
@@ -1005,7 +1006,8 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     }
     __syncwarp();
   } else if (warp == 9) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();   // warp-uniform loops; only the MMA / commit instructions are predicated
       constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, BT, 0, 0);     // S = Q K^T, dP = dO V^T   (N = 64 keys)
       constexpr uint32_t idesc_dq = umma_idesc_bf16(TQ, HD, 0, 1);    // dQ += dS K             (K MN-major, N = d)
       uint32_t g = 0, it = 0, ds_cnt[2] = {0, 0}, dq_cnt[2] = {0, 0}, sdp_cnt[2] = {0, 0};
@@ -1022,9 +1024,9 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         ++sdp_cnt[t];
         tc_fence_after();
         const uint32_t t_s = tmem_base + t * 192;
-        umma_chain<HD / 16>(t_s, q_lo + t * QT16, 2, k_lo + st * KT16, 2, idesc_s, 0);
-        umma_chain<HD / 16>(t_s + 64, do_lo + t * QT16, 2, v_lo + st * KT16, 2, idesc_s, 0);
-        umma_commit(&sdp_full[t]);
+        if (leader) umma_chain<HD / 16>(t_s, q_lo + t * QT16, 2, k_lo + st * KT16, 2, idesc_s, 0);
+        if (leader) umma_chain<HD / 16>(t_s + 64, do_lo + t * QT16, 2, v_lo + st * KT16, 2, idesc_s, 0);
+        if (leader) umma_commit(&sdp_full[t]);
       };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int qb = item % n_qblk;
@@ -1035,7 +1037,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           mbar_wait(&kv_full[st], (g / B2_ST) & 1);
           tc_fence_after();
           for (int t = 0; t < nt; ++t) issue_sdp(t, st);
-          if (n_tiles == 1) umma_commit(q_empty);
+          if (n_tiles == 1) if (leader) umma_commit(q_empty);
         }
         for (int j = 0; j < n_tiles; ++j) {
           const int st = (g + j) % B2_ST;
@@ -1044,17 +1046,17 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             mbar_wait(&kv_full[stn], ((g + j + 1) / B2_ST) & 1);
             tc_fence_after();
             for (int t = 0; t < nt; ++t) issue_sdp(t, stn);
-            if (j + 2 == n_tiles) umma_commit(q_empty);
+            if (j + 2 == n_tiles) if (leader) umma_commit(q_empty);
           }
           for (int t = 0; t < nt; ++t) {
             mbar_wait(&ds_ready[t], ds_cnt[t] & 1);
             ++ds_cnt[t];
             if (j == 0) { mbar_wait(&dq_empty[t], (dq_cnt[t] & 1) ^ 1); ++dq_cnt[t]; }   // the previous item's epilogue has drained dQ_t
             tc_fence_after();
-            umma_chain<BT / 16>(tmem_base + t * 192 + 128, ds_lo + t * DST16, 2, kmn_lo + st * KT16, 128, idesc_dq, j > 0);
-            umma_commit(&ds_free[t]);
+            if (leader) umma_chain<BT / 16>(tmem_base + t * 192 + 128, ds_lo + t * DST16, 2, kmn_lo + st * KT16, 128, idesc_dq, j > 0);
+            if (leader) umma_commit(&ds_free[t]);
           }
-          umma_commit(&kv_empty[st]);
+          if (leader) umma_commit(&kv_empty[st]);
         }
         g += n_tiles;
       }
@@ -1222,7 +1224,8 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
     __syncwarp();
   } else if (warp == 9) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();   // warp-uniform loops; only the MMA / commit instructions are predicated
       constexpr uint32_t idesc_s = umma_idesc_bf16(TK, BT, 0, 0);     // S^T = K Q^T, dP^T = V dO^T   (N = 64 queries)
       constexpr uint32_t idesc_acc = umma_idesc_bf16(TK, HD, 0, 1);   // dV += P^T dO, dK += dS^T Q   (B MN-major, N = d)
       uint32_t g = 0, it = 0, ds_cnt[2] = {0, 0}, acc_cnt[2] = {0, 0}, sdp_cnt[2] = {0, 0};
@@ -1238,9 +1241,9 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         ++sdp_cnt[t];
         tc_fence_after();
         const uint32_t t_s = tmem_base + t * 256;
-        umma_chain<HD / 16>(t_s, k_lo + t * KT16, 2, q_lo + st * QT16, 2, idesc_s, 0);
-        umma_chain<HD / 16>(t_s + 64, v_lo + t * KT16, 2, do_lo + st * QT16, 2, idesc_s, 0);
-        umma_commit(&sdp_full[t]);
+        if (leader) umma_chain<HD / 16>(t_s, k_lo + t * KT16, 2, q_lo + st * QT16, 2, idesc_s, 0);
+        if (leader) umma_chain<HD / 16>(t_s + 64, v_lo + t * KT16, 2, do_lo + st * QT16, 2, idesc_s, 0);
+        if (leader) umma_commit(&sdp_full[t]);
       };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int kb = item % n_kblk;
@@ -1251,7 +1254,7 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           mbar_wait(&q_full[st], (g / B2_ST) & 1);
           tc_fence_after();
           for (int t = 0; t < nt; ++t) issue_sdp(t, st);
-          if (n_tiles == 1) umma_commit(kv_empty);
+          if (n_tiles == 1) if (leader) umma_commit(kv_empty);
         }
         for (int i = 0; i < n_tiles; ++i) {
           const int st = (g + i) % B2_ST;
@@ -1260,7 +1263,7 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             mbar_wait(&q_full[stn], ((g + i + 1) / B2_ST) & 1);
             tc_fence_after();
             for (int t = 0; t < nt; ++t) issue_sdp(t, stn);
-            if (i + 2 == n_tiles) umma_commit(kv_empty);
+            if (i + 2 == n_tiles) if (leader) umma_commit(kv_empty);
           }
           for (int t = 0; t < nt; ++t) {
             mbar_wait(&ds_ready[t], ds_cnt[t] & 1);
@@ -1268,11 +1271,11 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             if (i == 0) { mbar_wait(&acc_empty[t], (acc_cnt[t] & 1) ^ 1); ++acc_cnt[t]; }
             tc_fence_after();
             const uint32_t t_dv = tmem_base + t * 256 + 128;
-            umma_chain<BT / 16>(t_dv, p_lo + t * PT16, 2, domn_lo + st * QT16, 128, idesc_acc, i > 0);
-            umma_chain<BT / 16>(t_dv + 64, ds_lo + t * PT16, 2, qmn_lo + st * QT16, 128, idesc_acc, i > 0);
-            umma_commit(&ds_free[t]);
+            if (leader) umma_chain<BT / 16>(t_dv, p_lo + t * PT16, 2, domn_lo + st * QT16, 128, idesc_acc, i > 0);
+            if (leader) umma_chain<BT / 16>(t_dv + 64, ds_lo + t * PT16, 2, qmn_lo + st * QT16, 128, idesc_acc, i > 0);
+            if (leader) umma_commit(&ds_free[t]);
           }
-          umma_commit(&q_empty[st]);
+          if (leader) umma_commit(&q_empty[st]);
         }
         g += n_tiles;
       }

@@ -147,6 +147,19 @@ __device__ __forceinline__ void umma_chain(uint32_t d_tmem, uint32_t a_lo, uint3
   for (int k = 1; k < NSTEP; ++k) umma_ss_acc(d_tmem, umma_desc_lo(a_lo + k * a_step), umma_desc_lo(b_lo + k * b_step), idesc);
 }
 
+// One lane of a CONVERGED warp (elect.sync).  The MMA-issuing warps run their loops warp-uniformly and predicate only the
+// tcgen05.mma / tcgen05.commit instructions with this: descriptor arithmetic then lives in uniform registers, and the
+// compiler does not wrap every UTCHMMA in the ELECT / BRA.U.ANY loop it emits inside an `if (lane == 0)` region.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--chunk", type=int, default=0, help="MulT chunk size (samples)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fixed-warmup", action="store_true", help="run exactly --warmup warm-up steps (profiler runs: ncu serialises every launch)")
     ap.add_argument("--dropout", type=float, default=0.1,
                     help="fusion_dropout / graph_dropout of the head in training mode (reference default, config.py:30,41: 0.1)")
     args = ap.parse_args()
@@ -284,7 +285,7 @@ def main():
         if warm_done == args.warmup:                    # the clock for the extra steps starts after the requested ones (lazy
             t_warm = time.perf_counter()                # initialisation, NCCL set-up and allocator growth sit in the first steps)
         elapsed = time.perf_counter() - t_warm
-        done = warm_done >= args.warmup and ((stable and elapsed >= 2.0) or elapsed >= 6.0 or warm_done >= args.warmup + 200)
+        done = warm_done >= args.warmup and (args.fixed_warmup or (stable and elapsed >= 2.0) or elapsed >= 6.0 or warm_done >= args.warmup + 200)
         if world > 1:                                   # steps contain collectives: every rank must run the same number of them
             flag = torch.tensor([0 if done else 1], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MAX)
@@ -293,9 +294,7 @@ def main():
             break
     sync_all()
 
-    # ---- device-timed region (inputs resident in HBM), GEMM launches timed live
-    K.prealloc_profile_events(2 * 400 * args.steps)
-    K.GEMM_PROFILE = []
+    # ---- device-timed region (inputs resident in HBM): K clean steps -> `value`
     l0 = pkg._lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
@@ -307,8 +306,21 @@ def main():
     sync_all()
     ms = e0.elapsed_time(e1) / args.steps
     launches = (pkg._lib.launch_count() - l0) // args.steps
-    prof, K.GEMM_PROFILE = K.GEMM_PROFILE, None
     clocks = sampler.stop()
+
+    # ---- the same K steps again with a CUDA-event pair around every GEMM launch (the dominant kernel) -> `roofline`.
+    # A separate pass: ~170 event records per step cost ~1.5 ms of launch gaps, which must not sit in `value`.
+    K.prealloc_profile_events(2 * 400 * args.steps)
+    K.GEMM_PROFILE = []
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    p0.record()
+    for _ in range(args.steps):
+        step(resident)
+    p1.record()
+    sync_all()
+    ms_prof = p0.elapsed_time(p1) / args.steps
+    prof, K.GEMM_PROFILE = K.GEMM_PROFILE, None
     gemm_ms = sum(a.elapsed_time(b) for a, b, _, tc in prof if tc) / args.steps
     gemm_flops = sum(f for _, _, f, tc in prof if tc) / args.steps
     n_gemm = sum(1 for *_, tc in prof if tc) // args.steps
@@ -366,7 +378,7 @@ def main():
                          "traffic_launch": None if traffic is None else f'{traffic["kernel"]}: {traffic["launch"]}; algorithmic bytes '
                                                                           f'{traffic["algorithmic_bytes_per_launch"]} ({traffic["source"]})',
                          "peak_source": pk["src"], "launches_per_step": n_gemm, "kernel_ms_per_step": gemm_ms,
-                         "share_of_step": gemm_ms / ms if ms else None},
+                         "share_of_step": gemm_ms / ms_prof if ms_prof else None, "instrumented_ms_per_step": ms_prof},
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(kind, lens, flag, cpu_batch, dropout=args.dropout)

@@ -99,7 +99,8 @@ infonce_lse_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();   // warp-uniform loops; only the MMA / commit instructions are predicated
       constexpr uint32_t idesc = umma_idesc_bf16(NT, NT, 0, 0);
       const uint32_t x_lo = umma_lo(smem_u32(smem + NceSmem::X_OFF), 16), y_lo = umma_lo(smem_u32(smem + NceSmem::Y_OFF), 16);
       mbar_wait(x_full, 0);
@@ -108,9 +109,9 @@ infonce_lse_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         mbar_wait(&y_full[st], (n >> 1) & 1);
         mbar_wait(&s_free[st], ((n >> 1) & 1) ^ 1);
         tc_fence_after();
-        nce_issue_s(tmem_base + st * NT, x_lo, y_lo + st * 4 * SUB16, p.nk, idesc);
-        umma_commit(&s_full[st]);
-        umma_commit(&y_empty[st]);
+        if (leader) nce_issue_s(tmem_base + st * NT, x_lo, y_lo + st * 4 * SUB16, p.nk, idesc);
+        if (leader) umma_commit(&s_full[st]);
+        if (leader) umma_commit(&y_empty[st]);
       }
     }
     __syncwarp();
@@ -246,7 +247,8 @@ infonce_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();   // warp-uniform loops; only the MMA / commit instructions are predicated
       constexpr uint32_t idesc_s = umma_idesc_bf16(NT, NT, 0, 0);
       constexpr uint32_t idesc_x = umma_idesc_bf16(NT, 64, 0, 1);      // dX[:, 64 kk .. +64) += W Y_kk   (Y MN-major, N = 64 columns of D)
       const uint32_t x_lo = umma_lo(smem_u32(smem + NceSmem::X_OFF), 16), y_lo = umma_lo(smem_u32(smem + NceSmem::Y_OFF), 16);
@@ -257,11 +259,11 @@ infonce_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         tc_fence_after();
         for (int kk = 0; kk < p.nk; ++kk) {
           const uint32_t yb = ymn_lo + st * 4 * SUB16 + kk * SUB16;
-          umma_chain<4>(t_dx + kk * 64, w_lo, 2, yb, 128, idesc_x, n > 0);
-          umma_chain<4>(t_dx + kk * 64, w_lo + SUB16, 2, yb + 4 * 128, 128, idesc_x, 1);
+          if (leader) umma_chain<4>(t_dx + kk * 64, w_lo, 2, yb, 128, idesc_x, n > 0);
+          if (leader) umma_chain<4>(t_dx + kk * 64, w_lo + SUB16, 2, yb + 4 * 128, 128, idesc_x, 1);
         }
-        umma_commit(w_free);
-        umma_commit(&y_empty[st]);
+        if (leader) umma_commit(w_free);
+        if (leader) umma_commit(&y_empty[st]);
       };
       mbar_wait(x_full, 0);
       for (int n = 0; n < nt; ++n) {
@@ -269,8 +271,8 @@ infonce_grad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         mbar_wait(&y_full[st], (n >> 1) & 1);
         mbar_wait(&s_free[st], ((n >> 1) & 1) ^ 1);
         tc_fence_after();
-        nce_issue_s(tmem_base + st * NT, x_lo, y_lo + st * 4 * SUB16, p.nk, idesc_s);
-        umma_commit(&s_full[st]);
+        if (leader) nce_issue_s(tmem_base + st * NT, x_lo, y_lo + st * 4 * SUB16, p.nk, idesc_s);
+        if (leader) umma_commit(&s_full[st]);
         if (n > 0) issue_dx(n - 1);                                   // S(n) runs ahead of the accumulation of tile n-1
       }
       if (nt > 0) issue_dx(nt - 1);

@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--chunk", type=int, default=0, help="MulT chunk size (samples)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying the captured step")
     ap.add_argument("--fixed-warmup", action="store_true", help="run exactly --warmup warm-up steps (profiler runs: ncu serialises every launch)")
     ap.add_argument("--dropout", type=float, default=0.1,
                     help="fusion_dropout / graph_dropout of the head in training mode (reference default, config.py:30,41: 0.1)")
@@ -249,7 +250,7 @@ def main():
     if mask is not None:
         kw["mask"] = mask
 
-    def step(inputs):
+    def eager_step(inputs):
         for p in params:
             p.grad = None
         for x in inputs:
@@ -257,6 +258,34 @@ def main():
         out = head(*inputs, **kw)
         loss = objective(out, b_global)
         loss.backward()
+        if world > 1:
+            pkg.allreduce_gradients(params)
+        return loss
+
+    # The step (forward + loss + backward) is captured once in a CUDA graph (pkg.GraphedTrainStep) and replayed: issuing its
+    # ~300 launches from Python costs ~16 ms of host time per step, which bounds the step when ranks share a CPU-limited host.
+    # Captured when the step has no collective inside forward/backward (the InfoNCE all-gather) and fits the graph's private
+    # pool comfortably; the gradient all-reduce stays outside the graph.  Falls back to eager issue if capture fails.
+    graphed, graph_note = None, "eager (--no-graph)"
+    if not args.no_graph:
+        in_graph_collective = world > 1 and kind in ("contrastive", "hierarchical")
+        if in_graph_collective or batch > 1024:
+            graph_note = "eager (collective inside the step)" if in_graph_collective else "eager (activation stash too large for a graph pool)"
+        else:
+            try:
+                for _ in range(2):
+                    eager_step(resident)
+                torch.cuda.synchronize()
+                graphed = pkg.GraphedTrainStep(head, resident, lambda out: objective(out, b_global), kw)
+                graph_note = "cuda-graph replay of forward+loss+backward (GraphedTrainStep)"
+            except Exception as exc:                         # noqa: BLE001 -- never let the capture take the bench down
+                graphed, graph_note = None, f"eager (capture failed: {type(exc).__name__}: {str(exc)[:120]})"
+                torch.cuda.synchronize()
+
+    def step(inputs):
+        if graphed is None:
+            return eager_step(inputs)
+        loss = graphed(*inputs)
         if world > 1:
             pkg.allreduce_gradients(params)
         return loss
@@ -300,12 +329,16 @@ def main():
     sync_all()
     sampler.mark()
     e0.record()
+    t_host = time.perf_counter()
     for _ in range(args.steps):
         step(resident)
-    e1.record()
+    host_issue_ms = (time.perf_counter() - t_host) * 1e3 / args.steps      # host time to ISSUE a step (no sync inside): if it approaches
+    e1.record()                                                            # ms_per_step the run is launch-bound on the host, not GPU-bound
     sync_all()
     ms = e0.elapsed_time(e1) / args.steps
     launches = (pkg._lib.launch_count() - l0) // args.steps
+    if graphed is not None:                          # a replay launches the kernels recorded at capture without passing through the host counter
+        launches = graphed.kernel_launches
     clocks = sampler.stop()
 
     # ---- the same K steps again with a CUDA-event pair around every GEMM launch (the dominant kernel) -> `roofline`.
@@ -316,7 +349,7 @@ def main():
     sync_all()
     p0.record()
     for _ in range(args.steps):
-        step(resident)
+        eager_step(resident)                         # events cannot be recorded inside a replay: the instrumented pass issues eagerly
     p1.record()
     sync_all()
     ms_prof = p0.elapsed_time(p1) / args.steps
@@ -333,7 +366,7 @@ def main():
     def e2e_steps(n):
         pf.submit(host)
         for k in range(n):
-            xs = [x.requires_grad_(True) for x in pf.get()]
+            xs = pf.get() if graphed is not None else [x.requires_grad_(True) for x in pf.get()]
             if k + 1 < n:
                 pf.submit(host)
             float(step(xs).detach().cpu())
@@ -363,7 +396,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": args.workload, "head": kind, "batch_per_gpu": batch, "global_batch": b_global, "seq_lens": lens,
-                       "hidden": H, "heads": HEADS, "dropout": args.dropout, "parallelism": f"dp{world}", "warmup_steps_run": warm_done,
+                       "hidden": H, "heads": HEADS, "dropout": args.dropout, "parallelism": f"dp{world}", "warmup_steps_run": warm_done, "host_issue_ms_per_step": host_issue_ms, "issue": graph_note,
                        "l2": "inputs+activations per step exceed the 126 MB L2" if h2d_bytes > 126e6 else "small working set (latency-bound config)",
                        "algorithmic_tflop_per_step": gflop * batch / 1e3,
                        "model_tflops_per_gpu": gflop * batch / 1e3 / (ms * 1e-3),

@@ -227,6 +227,10 @@ int b200f_modality_mask(float* mask, int64_t B, float rate, uint64_t seed, uint6
 int b200f_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset, int32_t dtype, void* stream);
 /* In-place inverted dropout of an [M, N] activation (row stride ldx) with the mask b200f_gemm's dropout epilogue generates:
  * element (m, n) kept iff the counter-based hash of (seed_lo, seed_hi, m, n) passes (csrc/common.cuh). */
+/* Dropout epoch: a device-side word every mask-generating kernel XORs into its seed.  add != 0: epoch += value, else
+ * epoch = value (stream-ordered).  A training step captured in a CUDA graph starts with b200f_dropout_epoch(1, 1, stream) so
+ * that each replay draws new masks although the seeds (kernel arguments) are frozen at capture; eager code never needs it. */
+int b200f_dropout_epoch(uint32_t value, int32_t add, void* stream);
 int b200f_dropout_rowcol(void* x, int64_t ldx, int64_t M, int64_t N, float p, uint32_t seed_lo, uint32_t seed_hi, int32_t dtype,
                          void* stream);
 

@@ -40,6 +40,10 @@ extern bool g_dbg_disable_pair;
 extern int g_attn_fwd_variant;
 extern int g_attn_bwd_variant;
 extern int g_infonce_variant;
+void attn_tc_epoch(uint32_t v, int add, cudaStream_t st);
+void attn_simt_epoch(uint32_t v, int add, cudaStream_t st);
+void gemm_tc_epoch(uint32_t v, int add, cudaStream_t st);
+void smallops_epoch(uint32_t v, int add, cudaStream_t st);
 
 }  // namespace b200f
 
@@ -81,6 +85,16 @@ int b200f_gemm(const b200f_gemm_args* a, void* stream) {
   if (a->dropout_p > 0.f && (rc = b200f_dropout_rowcol(a->C, a->ldc, a->M, a->N, a->dropout_p, a->drop_seed_lo, a->drop_seed_hi, a->dtype, stream))) return rc;
   if (!a->colsum) return B200F_OK;
   return b200f_colsum_accum(a->C, a->ldc, a->colsum, a->M, a->N, a->dtype, stream);
+}
+
+// Dropout epoch (see csrc/common.cuh): add != 0 -> epoch += value, else epoch = value; stream-ordered, capturable in a CUDA graph.
+int b200f_dropout_epoch(uint32_t value, int32_t add, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  b200f::attn_tc_epoch(value, add, st);
+  b200f::attn_simt_epoch(value, add, st);
+  b200f::gemm_tc_epoch(value, add, st);
+  b200f::smallops_epoch(value, add, st);
+  return b200f::check_launch("dropout_epoch");
 }
 
 // debug: override MN-major UMMA descriptor geometry (0 restores the default). Not part of the product API.

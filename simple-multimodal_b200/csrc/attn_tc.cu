@@ -440,7 +440,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       if (q0 >= p.Lq) continue;                      // this warpgroup's tile does not exist (the MMA warp skips it too)
       float m = -INFINITY, l = 0.f;                  // m: reference max the stored P / O are scaled against (raw score units)
       // dropout: P (what multiplies V) is masked, the row sum l is not; the 1/(1-p) scale rides on the final 1/l
-      const uint32_t rk = DROP ? drop_row_key(p.drop_seed_lo, p.drop_seed_hi, uint32_t((b * p.H + h) * p.Lq + q0 + row)) : 0u;
+      const uint32_t rk = DROP ? drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, uint32_t((b * p.H + h) * p.Lq + q0 + row)) : 0u;
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(&s_full[t], sf_cnt & 1);
         ++sf_cnt;
@@ -1084,7 +1084,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       const float ndl = -(qrow < p.Lq ? p.delta[ri] : 0.f) * p.scale;
       const uint64_t nlse22 = f2_pack(nlse2, nlse2), ndl2 = f2_pack(ndl, ndl);
       // dropout: dP = keep/(1-p) * (dO V^T), so the mask and the scale ride on the multiplier of dP
-      const uint32_t rk = DROP ? drop_row_key(p.drop_seed_lo, p.drop_seed_hi, uint32_t((b * p.H + h) * p.Lq + qrow)) : 0u;
+      const uint32_t rk = DROP ? drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, uint32_t((b * p.H + h) * p.Lq + qrow)) : 0u;
       const float sck = p.scale * p.inv_keep;
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(&sdp_full[t], sf_cnt & 1);
@@ -1316,7 +1316,7 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const int qi = i * BT + (t128 & 63);
           // stored negated (and delta pre-scaled) so the inner loop is pure FFMA2
           sl[t128] = t128 < 64 ? -stat_next * LOG2E : -stat_next * p.scale;
-          if (DROP && t128 < 64) reinterpret_cast<uint32_t*>(sl)[2 * BT + t128] = drop_row_key(p.drop_seed_lo, p.drop_seed_hi, uint32_t(stat_base + qi));
+          if (DROP && t128 < 64) reinterpret_cast<uint32_t*>(sl)[2 * BT + t128] = drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, uint32_t(stat_base + qi));
           if (i + 1 < n_tiles) stat_next = load_stat(i + 1);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
@@ -1473,5 +1473,7 @@ int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st) {
   }
   return B200F_OK;
 }
+
+B200F_DEFINE_EPOCH_HOOK(attn_tc)
 
 }  // namespace b200f

@@ -122,6 +122,19 @@ __host__ __device__ __forceinline__ bool drop_keep_c(uint32_t row_key, uint32_t 
 __host__ __device__ __forceinline__ bool drop_keep(uint32_t row_key, uint32_t col, uint32_t thr32) {
   return drop_keep_c(row_key, col * kDropColMul, thr32);
 }
+// Dropout epoch: a device-side word XORed into seed_hi by every kernel that generates a mask.  It exists for CUDA graphs:
+// kernel arguments (the seeds) are frozen at capture, so a captured training step starts with a one-thread kernel that
+// advances the epoch -- every replay then draws fresh masks, and forward / backward of one replay still agree.  Eager use
+// leaves it at 0.  The library is built without relocatable device code, so each translation unit holds its own copy and
+// b200f_dropout_epoch() updates all of them (B200F_DEFINE_EPOCH_HOOK).
+static __device__ uint32_t g_drop_epoch = 0;
+__device__ __forceinline__ uint32_t drop_row_key_e(uint32_t seed_lo, uint32_t seed_hi, uint32_t row) {
+  return drop_row_key(seed_lo, seed_hi ^ g_drop_epoch, row);
+}
+#define B200F_DEFINE_EPOCH_HOOK(name)                                                                         \
+  __global__ void name##_epoch_kernel(uint32_t v, int add) { g_drop_epoch = add ? g_drop_epoch + v : v; }      \
+  void name##_epoch(uint32_t v, int add, cudaStream_t st) { name##_epoch_kernel<<<1, 1, 0, st>>>(v, add); }
+
 __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
   const double t = double(p) * 4294967296.0;
   return t <= 0.0 ? 0u : (t >= 4294967295.0 ? 4294967295u : uint32_t(t));

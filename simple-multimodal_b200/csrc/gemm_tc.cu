@@ -174,7 +174,7 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, uint8_
   const long long row = row0 + lane;
   const int crow = lane >> 3, cchunk = lane & 7;             // coalesced phase: 4 rows x 8 chunks per instruction
   const bool has_aux = p.residual || p.mask;
-  const uint32_t rk = p.drop_thr ? drop_row_key(p.drop_seed_lo, p.drop_seed_hi, uint32_t(row)) : 0u;
+  const uint32_t rk = p.drop_thr ? drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, uint32_t(row)) : 0u;
 #pragma unroll 1
   for (int blk = 0; blk < NBLK; ++blk) {
     const int c0 = c_begin + blk * 64;
@@ -766,5 +766,7 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
     default: return launch_cfg<256, 3, 1, 1>(ta, tb, p, grid, st);
   }
 }
+
+B200F_DEFINE_EPOCH_HOOK(gemm_tc)
 
 }  // namespace b200f

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128) gat_fwd_kernel(const T* __restrict__ xp, 
     for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int h = 0; h < GH; ++h) {
-        const uint32_t rk = drop_row_key(seed_lo, seed_hi, uint32_t((b * heads + h) * 3 + i));
+        const uint32_t rk = drop_row_key_e(seed_lo, seed_hi, uint32_t((b * heads + h) * 3 + i));
 #pragma unroll
         for (int j = 0; j < 3; ++j) al[i][h][j] = drop_keep(rk, uint32_t(j), drop_thr) ? al[i][h][j] * inv_keep : 0.f;
       }
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(128) gat_bwd_kernel(const T* __restrict__ dout
     for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int h = 0; h < GH; ++h) {
-        const uint32_t rk = drop_thr ? drop_row_key(seed_lo, seed_hi, uint32_t((b * heads + h) * 3 + i)) : 0u;
+        const uint32_t rk = drop_thr ? drop_row_key_e(seed_lo, seed_hi, uint32_t((b * heads + h) * 3 + i)) : 0u;
 #pragma unroll
         for (int j = 0; j < 3; ++j) mk[i][h][j] = !drop_thr ? 1.f : (drop_keep(rk, uint32_t(j), drop_thr) ? inv_keep : 0.f);
       }
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(128) tok3_fwd_kernel(const T* __restrict__ qkv
       for (int j = 0; j < 3; ++j) p[i][j] /= sum;
       float pd[3] = {p[i][0], p[i][1], p[i][2]};     // nn.MultiheadAttention(dropout=p): the weights are dropped before P V, and the
       if (drop_thr) {                                // returned (head-averaged) weights are the dropped ones (torch functional.py:6647-6665)
-        const uint32_t rk = drop_row_key(seed_lo, seed_hi, uint32_t((b * heads + head) * 3 + i));
+        const uint32_t rk = drop_row_key_e(seed_lo, seed_hi, uint32_t((b * heads + head) * 3 + i));
 #pragma unroll
         for (int j = 0; j < 3; ++j) pd[j] = drop_keep(rk, uint32_t(j), drop_thr) ? pd[j] * inv_keep : 0.f;
       }
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(128) tok3_bwd_kernel(const T* __restrict__ dct
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       float dot = 0.f;
-      const uint32_t rk = drop_thr ? drop_row_key(seed_lo, seed_hi, uint32_t((b * heads + head) * 3 + i)) : 0u;
+      const uint32_t rk = drop_thr ? drop_row_key_e(seed_lo, seed_hi, uint32_t((b * heads + head) * 3 + i)) : 0u;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         p[i][j] = pi[i * 3 + j];
@@ -502,7 +502,7 @@ __global__ void dropout_rowcol_kernel(T* __restrict__ x, long long ldx, long lon
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / N, c = i - r * N;
     T* e = x + r * ldx + c;
-    *e = drop_keep(drop_row_key(seed_lo, seed_hi, uint32_t(r)), uint32_t(c), thr) ? from_f32<T>(to_f32(*e) * inv_keep) : from_f32<T>(0.f);
+    *e = drop_keep(drop_row_key_e(seed_lo, seed_hi, uint32_t(r)), uint32_t(c), thr) ? from_f32<T>(to_f32(*e) * inv_keep) : from_f32<T>(0.f);
   }
 }
 
@@ -513,7 +513,7 @@ __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long 
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     Vec16<T> t; t.load(x + i * VN); float f[VN]; t.unpack(f);
 #pragma unroll
-    for (int e = 0; e < VN; ++e) f[e] = rng_uniform(seed, offset + i * VN + e) >= p ? f[e] * inv_keep : 0.f;
+    for (int e = 0; e < VN; ++e) f[e] = rng_uniform(seed ^ (uint64_t(g_drop_epoch) << 32), offset + i * VN + e) >= p ? f[e] * inv_keep : 0.f;
     t.pack(f); t.store(y + i * VN);
   }
 }
@@ -528,6 +528,8 @@ static inline int ew_grid2(long long n, int block) {
   if ((dtype) == B200F_F32) { using T = float; __VA_ARGS__ }                       \
   else if ((dtype) == B200F_BF16) { using T = bf16; __VA_ARGS__ }                  \
   else return fail(B200F_ERR_DTYPE, "unknown dtype %d", int(dtype));
+
+B200F_DEFINE_EPOCH_HOOK(smallops)
 
 }  // namespace b200f
 

@@ -203,9 +203,12 @@ class MultimodalTransformer(_FusionBase):
         params = dict(self.named_parameters())
         H, heads = self.config.fusion_hidden_size, self.config.fusion_num_heads
         # memory the stash may use: what the driver reports free plus what torch's caching allocator holds but has not handed out
-        free_bytes, _ = torch.cuda.mem_get_info(t.device)
-        free_bytes += torch.cuda.memory_reserved(t.device) - torch.cuda.memory_allocated(t.device)
-        budget = int(self.stash_fraction * free_bytes) if torch.is_grad_enabled() else 0
+        if torch.cuda.is_current_stream_capturing():
+            budget = 1 << 62                                 # CUDA-graph capture: the graph's private pool keeps every chunk anyway
+        else:
+            free_bytes, _ = torch.cuda.mem_get_info(t.device)
+            free_bytes += torch.cuda.memory_reserved(t.device) - torch.cuda.memory_allocated(t.device)
+            budget = int(self.stash_fraction * free_bytes) if torch.is_grad_enabled() else 0
         return mult_engine.MulTFn.apply(t, a, v, H, heads, int(self.chunk_size), budget, drop, self._names, *[params[n] for n in self._names])
 
     def forward(self, text_features, audio_features, video_features, mask=None) -> Dict[str, Tensor]:

@@ -410,6 +410,11 @@ def modality_mask(B: int, rate: float, seed: int, offset: int, device) -> Tensor
     return mask
 
 
+def dropout_epoch(value: int, add: bool = False) -> None:
+    """Device-side dropout epoch (csrc/common.cuh): epoch += value (add) or epoch = value, ordered on the current stream."""
+    check(lib().b200f_dropout_epoch(C.c_uint32(int(value) & 0xFFFFFFFF), C.c_int32(1 if add else 0), stream_ptr()), "b200f_dropout_epoch")
+
+
 def dropout(x: Tensor, p: float, seed: int, offset: int) -> Tensor:
     y = torch.empty_like(x)
     check(lib().b200f_dropout(ptr(x), ptr(y), C.c_int64(x.numel()), C.c_float(p), C.c_uint64(seed), C.c_uint64(offset), dtype_code(x.dtype),

@@ -38,6 +38,7 @@ struct GemmTcParams {
   float* colsum;  // optional [N]: += column sums of the stored bf16 C (N % 64 == 0; staged bf16 epilogue only)
   uint32_t drop_thr, drop_seed_lo, drop_seed_hi;   // inverted dropout on the output (staged bf16 epilogue only); 0 = off
   float inv_keep;
+  int epi_stride;  // byte distance of a warp's two epilogue staging tiles (EPI_STAGE_BYTES), or 0 when the launch has a single tile per warp
 };
 
 template <int BN, int STAGES>
@@ -167,21 +168,23 @@ __device__ __forceinline__ void epi_issue_aux(const GemmTcParams& p, uint8_t* st
 
 // bf16 output.  `stage`: this warp's two 4 KB tiles; `bias_s`: the tile's bias slice starting at this warp's first column;
 // columns [col_base, col_base + NCOLS) of rows [row0, row0 + 32).  Block 0's aux prefetch was issued by the caller.
-template <int NCOLS>
+// EXTRAS = dropout and/or column sums requested: a separate instantiation, so the plain epilogue (which bounds the K = 512
+// GEMMs) carries none of their instructions or registers (measured: the runtime-flag version cost those GEMMs 10-15 %).
+template <int NCOLS, bool EXTRAS>
 __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, uint8_t* stage, const float* bias_s, uint32_t t_row, long long row0,
                                                    int lane, int n_base, int c_begin, bool relu) {
   constexpr int NBLK = NCOLS / 64;
   const long long row = row0 + lane;
   const int crow = lane >> 3, cchunk = lane & 7;             // coalesced phase: 4 rows x 8 chunks per instruction
   const bool has_aux = p.residual || p.mask;
-  const uint32_t rk = p.drop_thr ? drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, uint32_t(row)) : 0u;
+  const uint32_t rk = (EXTRAS && p.drop_thr) ? drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, uint32_t(row)) : 0u;
 #pragma unroll 1
   for (int blk = 0; blk < NBLK; ++blk) {
     const int c0 = c_begin + blk * 64;
     const int col0 = n_base + c0;
-    uint8_t* st = stage + (blk & 1) * EPI_STAGE_BYTES;
+    uint8_t* st = stage + (blk & 1) * p.epi_stride;
     if (blk + 1 < NBLK) {
-      epi_issue_aux(p, stage + ((blk + 1) & 1) * EPI_STAGE_BYTES, row0, col0 + 64, lane);
+      epi_issue_aux(p, stage + ((blk + 1) & 1) * p.epi_stride, row0, col0 + 64, lane);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
@@ -220,7 +223,7 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, uint8_
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        if (p.drop_thr) {                                    // nn.Dropout behind Linear(+ReLU): mask from (seed, row, column)
+        if (EXTRAS && p.drop_thr) {                          // nn.Dropout behind Linear(+ReLU): mask from (seed, row, column)
           const uint32_t cc = uint32_t(col0 + h * 32 + g * 8) * kDropColMul;
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = drop_keep_c(rk, cc + uint32_t(j) * kDropColMul, p.drop_thr) ? v[j] * p.inv_keep : 0.f;
@@ -243,7 +246,7 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, uint8_
       const int rr = it * 4 + crow;
       if (row0 + rr < p.M) *reinterpret_cast<uint4*>(cbase + (long long)rr * p.ldc) = *reinterpret_cast<const uint4*>(st + sw128_offset(rr, cchunk));
     }
-    if (p.colsum) {
+    if (EXTRAS && p.colsum) {
       // bias gradient: column sums of the 32 x 64 block just staged (the rounded values that were stored).  A lane owns
       // columns 2*lane, 2*lane+1 (one conflict-free word per row); even lanes collect 4 columns and issue one vector RED.
       float a0 = 0.f, a1 = 0.f;
@@ -320,7 +323,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* st
   mbar_wait(full_bar, full_phase);
   tc_fence_after();
   if (staged16)
-    epilogue_tile_bf16<BN / 2>(p, stage, bias_tile + c_begin, t_row, row0, lane, n_base, c_begin, relu);
+    if (p.drop_thr || p.colsum) epilogue_tile_bf16<BN / 2, true>(p, stage, bias_tile + c_begin, t_row, row0, lane, n_base, c_begin, relu);
+    else epilogue_tile_bf16<BN / 2, false>(p, stage, bias_tile + c_begin, t_row, row0, lane, n_base, c_begin, relu);
   else if (out_f32 && p.vec_ok)
     epilogue_tile_f32<BN / 2>(p, stage, bias_tile + c_begin, t_row, row0, lane, n_base, c_begin, accum, relu);
   else
@@ -397,8 +401,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      // Warp-uniform issue loop; only tcgen05.mma / commit are predicated on the elected lane.  The descriptors of stage 0 are
+      // built once: a later stage / K step is one 64-bit add of (byte offset >> 4) to the address field (offsets < 256 KB).
+      const bool one = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      const uint64_t a_desc0 = umma_desc(smem_u32(smem), p.a_lbo, p.a_sbo);
+      const uint64_t b_desc0 = umma_desc(smem_u32(smem) + S::A_BYTES, p.b_lbo, p.b_sbo);
+      const uint32_t a_step = p.a_kadv >> 4, b_step = p.b_kadv >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -414,18 +424,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint32_t sb = sa + S::A_BYTES;
+          const uint64_t da = a_desc0 + uint64_t(stage * (S::STAGE_BYTES >> 4)), db = b_desc0 + uint64_t(stage * (S::STAGE_BYTES >> 4));
+          if (one) {
+            umma_ss(d_tmem, da, db, idesc, kb > kb0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = umma_desc(sa + k * p.a_kadv, p.a_lbo, p.a_sbo);
-            const uint64_t db = umma_desc(sb + k * p.b_kadv, p.b_lbo, p.b_sbo);
-            umma_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 1; k < BK / 16; ++k) umma_ss_acc(d_tmem, da + uint64_t(k * a_step), db + uint64_t(k * b_step), idesc);
+            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (one) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
       }
     }
     __syncwarp();
@@ -463,7 +471,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 // barrier; epilogue warps of both CTAs arrive on the leader's tmem-empty); smem-empty and tmem-full are local to each
 // CTA and signalled by multicast tcgen05.commit.
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+// EB = epilogue staging tiles per warp: 2 when a residual / ReLU-mask block is prefetched one block ahead, 1 otherwise -- the
+// 32 KB saved buy a sixth TMA stage (192 KB in flight per SM: the 5-stage ring holds exactly bandwidth x latency and runs dry)
+template <int BN, int STAGES, int EB = 2>
 struct PairSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;
@@ -471,14 +481,14 @@ struct PairSmem {
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;
   static constexpr int EPI_OFFSET = BIAS_OFFSET + 2 * BN * 4;
-  static constexpr int TOTAL = EPI_OFFSET + 8 * 2 * EPI_STAGE_BYTES;
+  static constexpr int TOTAL = EPI_OFFSET + 8 * EB * EPI_STAGE_BYTES;
   static_assert(TOTAL <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 };
 
-template <int BN, int STAGES, int A_MN, int B_MN>
+template <int BN, int STAGES, int A_MN, int B_MN, int EB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmTcParams p) {
-  using S = PairSmem<BN, STAGES>;
+  using S = PairSmem<BN, STAGES, EB>;
   constexpr int TMEM_COLS = 2 * BN;
   constexpr int HALF_N = BN / 2;
   extern __shared__ __align__(1024) uint8_t smem[];          // SWIZZLE_128B tiles need a 1024-byte aligned base (checked below)
@@ -553,8 +563,12 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {                                      // the whole warp of the leader CTA (warp-uniform); see the single-CTA kernel
+      const bool one = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, A_MN, B_MN);
+      const uint64_t a_desc0 = umma_desc(smem_u32(smem), p.a_lbo, p.a_sbo);
+      const uint64_t b_desc0 = umma_desc(smem_u32(smem) + S::A_BYTES, p.b_lbo, p.b_sbo);
+      const uint32_t a_step = p.a_kadv >> 4, b_step = p.b_kadv >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -570,25 +584,23 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint32_t sb = sa + S::A_BYTES;
+          const uint64_t da = a_desc0 + uint64_t(stage * (S::STAGE_BYTES >> 4)), db = b_desc0 + uint64_t(stage * (S::STAGE_BYTES >> 4));
+          if (one) {
+            umma_ss_pair(d_tmem, da, db, idesc, kb > kb0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = umma_desc(sa + k * p.a_kadv, p.a_lbo, p.a_sbo);
-            const uint64_t db = umma_desc(sb + k * p.b_kadv, p.b_lbo, p.b_sbo);
-            umma_ss_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 1; k < BK / 16; ++k) umma_ss_pair_acc(d_tmem, da + uint64_t(k * a_step), db + uint64_t(k * b_step), idesc);
+            umma_commit_pair(&empty_bar[stage]);
           }
-          umma_commit_pair(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(&tmem_full[acc]);
+        if (one) umma_commit_pair(&tmem_full[acc]);
       }
     }
     __syncwarp();
   } else {
     const int lane_grp = warp & 3;
     const int col_half = (warp - 2) >> 2;
-    uint8_t* stage = smem + S::EPI_OFFSET + (warp - 2) * 2 * EPI_STAGE_BYTES;
+    uint8_t* stage = smem + S::EPI_OFFSET + (warp - 2) * EB * EPI_STAGE_BYTES;
     float* bias_s = reinterpret_cast<float*>(smem + S::BIAS_OFFSET);
     int it = 0;
     for (int u = cluster_id; u < units; u += num_clusters, ++it) {
@@ -649,11 +661,14 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
 uint32_t g_dbg_mn_lbo = 0, g_dbg_mn_sbo = 0, g_dbg_mn_kadv = 0;
 
 bool g_dbg_disable_pair = false;     // b200f_debug_set(3, 1): force the single-CTA kernel (A/B testing)
+bool g_dbg_six_stages = false;       // b200f_debug_set(7, 1): 6-stage / one-staging-tile pair kernel for launches without an aux block.
+                                     // Measured no faster than 5 stages on any MulT shape (profiles/r01_e): the ring depth is not the limiter.
 
-template <int BN, int STAGES, int A_MN, int B_MN>
-static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcParams& p, int grid, cudaStream_t st) {
-  using S = PairSmem<BN, STAGES>;
-  auto kern = gemm_tc_pair_kernel<BN, STAGES, A_MN, B_MN>;
+template <int BN, int STAGES, int A_MN, int B_MN, int EB>
+static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, GemmTcParams p, int grid, cudaStream_t st) {
+  using S = PairSmem<BN, STAGES, EB>;
+  auto kern = gemm_tc_pair_kernel<BN, STAGES, A_MN, B_MN, EB>;
+  p.epi_stride = (EB - 1) * EPI_STAGE_BYTES;
   static bool configured = false;
   if (!configured) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -729,6 +744,7 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
   p.mask = static_cast<const bf16*>(a.relu_mask); p.ldm = a.ldm;
   p.alpha = a.alpha; p.flags = a.flags;
   p.vec_ok = vec_ok ? 1 : 0;
+  p.epi_stride = EPI_STAGE_BYTES;
   p.colsum = a.colsum;
   p.drop_thr = drop_threshold(a.dropout_p); p.drop_seed_lo = a.drop_seed_lo; p.drop_seed_hi = a.drop_seed_hi;
   p.inv_keep = 1.f / (1.f - a.dropout_p);
@@ -746,11 +762,19 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
   if (pair) {
     const int clusters = units < num_sms() / 2 ? units : num_sms() / 2;
     const int pkey = (a.a_layout ? 2 : 0) | (a.b_layout ? 1 : 0);
+    if (!a.residual && !a.relu_mask && g_dbg_six_stages) {     // experiment (b200f_debug_set(7, 1)): one staging tile per warp, six TMA stages
+      switch (pkey) {
+        case 0: return launch_pair<256, 6, 0, 0, 1>(ta, tb, p, 2 * clusters, st);
+        case 1: return launch_pair<256, 6, 0, 1, 1>(ta, tb, p, 2 * clusters, st);
+        case 2: return launch_pair<256, 6, 1, 0, 1>(ta, tb, p, 2 * clusters, st);
+        default: return launch_pair<256, 6, 1, 1, 1>(ta, tb, p, 2 * clusters, st);
+      }
+    }
     switch (pkey) {
-      case 0: return launch_pair<256, 5, 0, 0>(ta, tb, p, 2 * clusters, st);
-      case 1: return launch_pair<256, 5, 0, 1>(ta, tb, p, 2 * clusters, st);
-      case 2: return launch_pair<256, 5, 1, 0>(ta, tb, p, 2 * clusters, st);
-      default: return launch_pair<256, 5, 1, 1>(ta, tb, p, 2 * clusters, st);
+      case 0: return launch_pair<256, 5, 0, 0, 2>(ta, tb, p, 2 * clusters, st);
+      case 1: return launch_pair<256, 5, 0, 1, 2>(ta, tb, p, 2 * clusters, st);
+      case 2: return launch_pair<256, 5, 1, 0, 2>(ta, tb, p, 2 * clusters, st);
+      default: return launch_pair<256, 5, 1, 1, 2>(ta, tb, p, 2 * clusters, st);
     }
   }
   const int grid = units < num_sms() ? units : num_sms();

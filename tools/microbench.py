@@ -22,7 +22,10 @@ ap.add_argument("--chunk", type=int, default=256)
 ap.add_argument("--only", default="")
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--filter", default="")
+ap.add_argument("--six-stages", action="store_true", help="A/B: 6-stage pair GEMM for launches without an aux block (b200f_debug_set(7, 1))")
 args = ap.parse_args()
+if args.six_stages:
+    pkg._lib.lib().b200f_debug_set(7, 1)
 dev = torch.device("cuda")
 H = 512
 bf = torch.bfloat16

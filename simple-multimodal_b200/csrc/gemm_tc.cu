@@ -178,6 +178,7 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, uint8_
   const int crow = lane >> 3, cchunk = lane & 7;             // coalesced phase: 4 rows x 8 chunks per instruction
   const bool has_aux = p.residual || p.mask;
   const uint32_t rk = (EXTRAS && p.drop_thr) ? drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, uint32_t(row)) : 0u;
+  const uint64_t al2 = f2_pack(p.alpha, p.alpha);
 #pragma unroll 1
   for (int blk = 0; blk < NBLK; ++blk) {
     const int c0 = c_begin + blk * 64;
@@ -204,13 +205,17 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, uint8_
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[h][g * 8 + j]) * p.alpha;
-        if (p.bias) {
-          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + blk * 64 + h * 32 + g * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(bias_s + blk * 64 + h * 32 + g * 8 + 4);
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        {   // v = acc * alpha + bias as four FFMA2 (two accumulator columns per instruction)
+          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+          if (p.bias) {
+            b0 = *reinterpret_cast<const float4*>(bias_s + blk * 64 + h * 32 + g * 8);
+            b1 = *reinterpret_cast<const float4*>(bias_s + blk * 64 + h * 32 + g * 8 + 4);
+          }
+          const uint32_t* a = &r[h][g * 8];
+          f2_unpack(f2_fma(f2_pack_u(a[0], a[1]), al2, f2_pack(b0.x, b0.y)), v[0], v[1]);
+          f2_unpack(f2_fma(f2_pack_u(a[2], a[3]), al2, f2_pack(b0.z, b0.w)), v[2], v[3]);
+          f2_unpack(f2_fma(f2_pack_u(a[4], a[5]), al2, f2_pack(b1.x, b1.y)), v[4], v[5]);
+          f2_unpack(f2_fma(f2_pack_u(a[6], a[7]), al2, f2_pack(b1.z, b1.w)), v[6], v[7]);
         }
         uint8_t* cell = st + sw128_offset(lane, h * 4 + g);
         float f[8];

@@ -269,7 +269,8 @@ def main():
     graphed, graph_note = None, "eager (--no-graph)"
     if not args.no_graph:
         in_graph_collective = world > 1 and kind in ("contrastive", "hierarchical")
-        if in_graph_collective or batch > 1024:
+        too_big = kind in ("mult", "hierarchical") and lens is not None and batch > 1024      # MulT's stash: ~29 MB per sample
+        if in_graph_collective or too_big:
             graph_note = "eager (collective inside the step)" if in_graph_collective else "eager (activation stash too large for a graph pool)"
         else:
             try:

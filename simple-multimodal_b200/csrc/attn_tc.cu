@@ -34,7 +34,7 @@ struct AttnTcParams {
   bf16* O; long long ldo;
   float* LSE;
   // backward
-  const float* delta;
+  float* delta;                          // [B,H,Lq]: written by the dQ kernel (or attn_delta_kernel), read by the dKdV kernel
   bf16* dQ; long long lddq;
   bf16* dK; long long lddk;
   bf16* dV; long long lddv;
@@ -937,7 +937,8 @@ struct Dq2Smem {
   static constexpr int K_OFF = DO_OFF + 2 * TQ * HD * 2;       // B2_ST x [64 keys x 64]
   static constexpr int V_OFF = K_OFF + B2_ST * BT * HD * 2;    // B2_ST x [64 keys x 64]
   static constexpr int DS_OFF = V_OFF + B2_ST * BT * HD * 2;   // 2 x [128 x 64 keys] bf16, K-major SW128
-  static constexpr int BAR_OFF = DS_OFF + 2 * TQ * BT * 2;
+  static constexpr int O_OFF = DS_OFF + 2 * TQ * BT * 2;       // 2 x [128 x 64]: the forward output, only read by the softmax warps (delta)
+  static constexpr int BAR_OFF = O_OFF + 2 * TQ * HD * 2;
   static constexpr int TOTAL = BAR_OFF + 256;
 };
 
@@ -945,7 +946,8 @@ struct Dq2Smem {
 template <bool DROP>
 __global__ void __launch_bounds__(B2_THREADS, 1)
 attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
-                       const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p,
+                       const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                       const __grid_constant__ CUtensorMap tm_o, const AttnTcParams p,
                        const int n_qblk, const int n_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Dq2Smem::BAR_OFF);
@@ -964,8 +966,9 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 
   if (warp == 8 && lane == 0) {
     if (smem_u32(smem) & 1023u) __trap();
-    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
-    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_o);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1 + 8);      // the MMA warp's commit + the eight softmax warps (they read dO / O from the same buffers for delta)
     for (int i = 0; i < B2_ST; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&sdp_full[t], 1); mbar_init(&sdp_free[t], 4); mbar_init(&ds_ready[t], 4); mbar_init(&ds_free[t], 1); mbar_init(&dq_empty[t], 4);
@@ -988,12 +991,14 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         const int q0 = qb * 2 * TQ;
         const bool two = q0 + TQ < p.Lq;
         mbar_wait(q_empty, (it & 1) ^ 1);
-        mbar_expect_tx(q_full, (two ? 4 : 2) * TQ * HD * 2);
+        mbar_expect_tx(q_full, (two ? 6 : 3) * TQ * HD * 2);
         tma_load_4d(smem + Dq2Smem::Q_OFF, &tm_q, q_full, 0, h, q0, b);
         tma_load_4d(smem + Dq2Smem::DO_OFF, &tm_do, q_full, 0, h, q0, b);
+        tma_load_4d(smem + Dq2Smem::O_OFF, &tm_o, q_full, 0, h, q0, b);
         if (two) {
           tma_load_4d(smem + Dq2Smem::Q_OFF + TQ * HD * 2, &tm_q, q_full, 0, h, q0 + TQ, b);
           tma_load_4d(smem + Dq2Smem::DO_OFF + TQ * HD * 2, &tm_do, q_full, 0, h, q0 + TQ, b);
+          tma_load_4d(smem + Dq2Smem::O_OFF + TQ * HD * 2, &tm_o, q_full, 0, h, q0 + TQ, b);
         }
         for (int j = 0; j < n_tiles; ++j, ++g) {
           const int st = g % B2_ST;
@@ -1073,15 +1078,38 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     uint8_t* ds_tile = smem + Dq2Smem::DS_OFF + t * TQ * BT * 2;
     const float c = p.scale * LOG2E;
     const uint64_t c2 = f2_pack(c, c), sc2 = f2_pack(p.scale, p.scale);
-    uint32_t sf_cnt = 0, dsf_cnt = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    uint32_t sf_cnt = 0, dsf_cnt = 0, it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int qb = item % n_qblk, h = (item / n_qblk) % p.H, b = item / (n_qblk * p.H);
       const int q0 = qb * 2 * TQ + t * TQ;
-      if (q0 >= p.Lq) continue;                      // this warpgroup's tile does not exist (the MMA warp skips it too)
+      mbar_wait(q_full, it & 1);                     // dO / O of this item are in smem (also paces a warpgroup whose tile does not exist)
+      if (q0 >= p.Lq) {                              // this warpgroup's tile does not exist (the MMA warp skips it too)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(q_empty);
+        continue;
+      }
       const int qrow = q0 + row;
       const long long ri = ((long long)b * p.H + h) * p.Lq + qrow;
       const float nlse2 = -(qrow < p.Lq ? p.LSE[ri] : 0.f) * LOG2E;
-      const float ndl = -(qrow < p.Lq ? p.delta[ri] : 0.f) * p.scale;
+      // delta = rowsum(dO o O) from the TMA-loaded tiles (rows past Lq are zero-filled): no separate pass over dO and O
+      float dl = 0.f;
+      {
+        const uint8_t* so = smem + Dq2Smem::O_OFF + t * TQ * HD * 2;
+        const uint8_t* sg = smem + Dq2Smem::DO_OFF + t * TQ * HD * 2;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          Vec16<bf16> vo, vg;
+          vo.raw = *reinterpret_cast<const uint4*>(so + sw128_offset(row, ch));
+          vg.raw = *reinterpret_cast<const uint4*>(sg + sw128_offset(row, ch));
+          float fo[8], fg[8]; vo.unpack(fo); vg.unpack(fg);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dl = fmaf(fo[e], fg[e], dl);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_empty);           // this warp is done with the item's dO / O tiles
+      if (qrow < p.Lq) p.delta[ri] = dl;             // the dKdV kernel (next launch on the stream) reads it
+      const float ndl = -dl * p.scale;
       const uint64_t nlse22 = f2_pack(nlse2, nlse2), ndl2 = f2_pack(ndl, ndl);
       // dropout: dP = keep/(1-p) * (dO V^T), so the mask and the scale ride on the multiplier of dP
       const uint32_t rk = DROP ? drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, uint32_t((b * p.H + h) * p.Lq + qrow)) : 0u;
@@ -1411,8 +1439,10 @@ int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st) {
   const bool drop = p.drop_thr != 0;
   B200F_REQUIRE(!drop || g_attn_bwd_variant == 0, B200F_ERR_UNSUPPORTED, "attention(tcgen05): dropout needs the persistent kernels");
   const long long rows = (long long)a.B * a.H * a.Lq;
-  attn_delta_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(static_cast<const bf16*>(a.dO), a.lddo, static_cast<const bf16*>(a.O), a.ldo, a.delta, a.B, a.H, a.Lq);
-  if ((rc = check_launch("attn_delta_kernel"))) return rc;
+  if (g_attn_bwd_variant != 0) {                     // the persistent dQ kernel computes delta from its own dO / O tiles
+    attn_delta_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(static_cast<const bf16*>(a.dO), a.lddo, static_cast<const bf16*>(a.O), a.ldo, a.delta, a.B, a.H, a.Lq);
+    if ((rc = check_launch("attn_delta_kernel"))) return rc;
+  }
   static bool configured = false;
   if (!configured) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::TOTAL));
@@ -1423,8 +1453,10 @@ int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dkv2Smem::TOTAL));
     configured = true;
   }
-  CUtensorMap tq, tdo, tk, tv;
+  CUtensorMap tq, tdo, tk, tv, to;
   if (g_attn_bwd_variant == 0) {
+    B200F_REQUIRE(a.ldo % 8 == 0 && aligned16(a.O), B200F_ERR_ALIGN, "attention(tcgen05): O alignment");
+    if ((rc = make_head_tmap(&to, a.O, a.ldo, a.B, a.H, a.Lq, TQ))) return rc;
     {  // dQ: 128-row Q/dO boxes, 64-row K/V boxes; item = (batch, head, 256-query block)
       if ((rc = make_head_tmap(&tq, a.Q, a.ldq, a.B, a.H, a.Lq, TQ))) return rc;
       if ((rc = make_head_tmap(&tdo, a.dO, a.lddo, a.B, a.H, a.Lq, TQ))) return rc;
@@ -1434,8 +1466,8 @@ int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st) {
       const long long n_items = (long long)n_qblk * a.H * a.B;
       B200F_REQUIRE(n_items < (1ll << 31), B200F_ERR_SHAPE, "attention(tcgen05): too many work items");
       const int grid = int(n_items < num_sms() ? n_items : num_sms());
-      if (drop) attn_bwd_dq_tc2_kernel<true><<<grid, B2_THREADS, Dq2Smem::TOTAL, st>>>(tq, tdo, tk, tv, p, n_qblk, int(n_items));
-      else attn_bwd_dq_tc2_kernel<false><<<grid, B2_THREADS, Dq2Smem::TOTAL, st>>>(tq, tdo, tk, tv, p, n_qblk, int(n_items));
+      if (drop) attn_bwd_dq_tc2_kernel<true><<<grid, B2_THREADS, Dq2Smem::TOTAL, st>>>(tq, tdo, tk, tv, to, p, n_qblk, int(n_items));
+      else attn_bwd_dq_tc2_kernel<false><<<grid, B2_THREADS, Dq2Smem::TOTAL, st>>>(tq, tdo, tk, tv, to, p, n_qblk, int(n_items));
       if ((rc = check_launch("attn_bwd_dq_tc2_kernel"))) return rc;
     }
     {  // dKdV: 128-row K/V boxes, 64-row Q/dO boxes; item = (batch, head, 256-key block)

@@ -196,10 +196,21 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, uint8_
       epilogue_columns(p, t_row, row, row < p.M, n_base, c0, c0 + 64, false, false, relu);
       continue;
     }
+    // Three phases so that shared-memory loads and stores never interleave (an LDS must stay behind an earlier STS that may
+    // alias it): (1) aux cells and the accumulator into registers, (2) all the math, (3) eight STS; then eight LDS of full rows
+    // followed by eight global stores.  ncu on the K = 512 shapes: the epilogue warps are busy all the time (short-scoreboard
+    // stalls on shared-memory operations) while the tensor pipe is 56 % active -- the staging traffic competes with the TMA
+    // writes and UMMA operand reads of the mainloop for the 128 B/clk of shared-memory bandwidth; open item for round 2.
     uint32_t r[2][32];
     tmem_ld32(t_row + c0, r[0]);
     tmem_ld32(t_row + c0 + 32, r[1]);
+    uint4 aux[8];
+    if (has_aux) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) aux[q] = *reinterpret_cast<const uint4*>(st + sw128_offset(lane, q));
+    }
     tmem_ld_wait();
+    uint4 outv[8];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -217,9 +228,8 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, uint8_
           f2_unpack(f2_fma(f2_pack_u(a[4], a[5]), al2, f2_pack(b1.x, b1.y)), v[4], v[5]);
           f2_unpack(f2_fma(f2_pack_u(a[6], a[7]), al2, f2_pack(b1.z, b1.w)), v[6], v[7]);
         }
-        uint8_t* cell = st + sw128_offset(lane, h * 4 + g);
         float f[8];
-        if (has_aux) { Vec16<bf16> av; av.raw = *reinterpret_cast<const uint4*>(cell); av.unpack(f); }
+        if (has_aux) { Vec16<bf16> av; av.raw = aux[h * 4 + g]; av.unpack(f); }
         if (p.residual) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] += f[j];
@@ -241,15 +251,19 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, uint8_
           for (int j = 0; j < 8; ++j) v[j] = f[j] > 0.f ? v[j] : 0.f;
         }
         Vec16<bf16> ov; ov.pack(v);
-        *reinterpret_cast<uint4*>(cell) = ov.raw;            // same cell this lane just consumed
+        outv[h * 4 + g] = ov.raw;
       }
     }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(st + sw128_offset(lane, q)) = outv[q];   // the cells this lane consumed
     __syncwarp();
     bf16* cbase = reinterpret_cast<bf16*>(p.C) + row0 * p.ldc + col0 + cchunk * 8;
 #pragma unroll
+    for (int it = 0; it < 8; ++it) outv[it] = *reinterpret_cast<const uint4*>(st + sw128_offset(it * 4 + crow, cchunk));
+#pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int rr = it * 4 + crow;
-      if (row0 + rr < p.M) *reinterpret_cast<uint4*>(cbase + (long long)rr * p.ldc) = *reinterpret_cast<const uint4*>(st + sw128_offset(rr, cchunk));
+      if (row0 + rr < p.M) *reinterpret_cast<uint4*>(cbase + (long long)rr * p.ldc) = outv[it];
     }
     if (EXTRAS && p.colsum) {
       // bias gradient: column sums of the 32 x 64 block just staged (the rounded values that were stored).  A lane owns

@@ -268,6 +268,7 @@ def main():
     # pool comfortably; the gradient all-reduce stays outside the graph.  Falls back to eager issue if capture fails.
     graphed, graph_note = None, "eager (--no-graph)"
     if not args.no_graph:
+        # (capturing the NCCL all-gather of the InfoNCE step was tried at N=2 and hung in capture: those steps stay eager)
         in_graph_collective = world > 1 and kind in ("contrastive", "hierarchical")
         too_big = kind in ("mult", "hierarchical") and lens is not None and batch > 1024      # MulT's stash: ~29 MB per sample
         if in_graph_collective or too_big:

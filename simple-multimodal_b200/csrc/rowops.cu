@@ -20,7 +20,7 @@ __device__ __forceinline__ void load_param(const float* __restrict__ p, float (&
   }
 }
 
-template <typename T, int NV, int R>
+template <typename T, int NV, int R, bool POSTS = true>
 __global__ void __launch_bounds__(256, (NV <= 2 ? 2 : 1)) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, const T* __restrict__ post1,
                                                             const T* __restrict__ post2, T* __restrict__ y,
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256, (NV <= 2 ? 2 : 1)) layernorm_fwd_kernel(c
   const int nvec = H / VN;
   const float inv_h = 1.f / H;
   for (long long row0 = warp0 * R; row0 < rows; row0 += nwarps * R) {
-    Vec16<T> raw[R][NV], p1[R][NV], p2[R][NV];
+    Vec16<T> raw[R][NV], p1[POSTS ? R : 1][POSTS ? NV : 1], p2[POSTS ? R : 1][POSTS ? NV : 1];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(256, (NV <= 2 ? 2 : 1)) layernorm_fwd_kernel(c
         if (row0 + r < rows && vi < nvec) {
           const long long off = (row0 + r) * H + vi * VN;
           raw[r][i].load(x + off);
-          if (post1) p1[r][i].load(post1 + off);
-          if (post2) p2[r][i].load(post2 + off);
+          if (POSTS && post1) p1[POSTS ? r : 0][POSTS ? i : 0].load(post1 + off);
+          if (POSTS && post2) p2[POSTS ? r : 0][POSTS ? i : 0].load(post2 + off);
         }
       }
     float v[R][NV][VN], mean[R], rstd[R];
@@ -87,13 +87,13 @@ __global__ void __launch_bounds__(256, (NV <= 2 ? 2 : 1)) layernorm_fwd_kernel(c
             float o[VN];
 #pragma unroll
             for (int j = 0; j < VN; ++j) o[j] = (v[r][i][j] - mean[r]) * rstd[r] * gm[j] + bt[j];
-            if (post1) {
-              float f[VN]; p1[r][i].unpack(f);
+            if (POSTS && post1) {
+              float f[VN]; p1[POSTS ? r : 0][POSTS ? i : 0].unpack(f);
 #pragma unroll
               for (int j = 0; j < VN; ++j) o[j] += f[j];
             }
-            if (post2) {
-              float f[VN]; p2[r][i].unpack(f);
+            if (POSTS && post2) {
+              float f[VN]; p2[POSTS ? r : 0][POSTS ? i : 0].unpack(f);
 #pragma unroll
               for (int j = 0; j < VN; ++j) o[j] += f[j];
             }
@@ -522,6 +522,13 @@ int b200f_layernorm_fwd(const void* x, const float* gamma, const float* beta, co
       constexpr int R = NV <= 2 ? 2 : 1;
       const long long blocks = (rows + 8 * R - 1) / (8 * R);
       const int grid = int(blocks < (long long)num_sms() * 8 ? blocks : (long long)num_sms() * 8);
+      if (NV <= 2 && !post1 && !post2) {              // plain LayerNorm: four rows per warp iteration (nothing else to keep in flight)
+        constexpr int R4 = NV <= 2 ? 4 : 1;
+        const long long blocks4 = (rows + 8 * R4 - 1) / (8 * R4);
+        const int grid4 = int(blocks4 < (long long)num_sms() * 8 ? blocks4 : (long long)num_sms() * 8);
+        layernorm_fwd_kernel<T, NV, R4, false><<<grid4, 256, 0, st>>>(static_cast<const T*>(x), gamma, beta, nullptr, nullptr, static_cast<T*>(y), mean, rstd,
+                                                                rows, H, eps);
+      } else
       layernorm_fwd_kernel<T, NV, R><<<grid, 256, 0, st>>>(static_cast<const T*>(x), gamma, beta, static_cast<const T*>(post1),
                                                          static_cast<const T*>(post2), static_cast<T*>(y), mean, rstd, rows, H, eps);
     })

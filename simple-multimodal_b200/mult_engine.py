@@ -18,6 +18,7 @@ backward, accumulating parameter gradients in fp32.  Kernel-level scheduling per
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, List
 
 import torch
@@ -249,9 +250,18 @@ class MulTFn(torch.autograd.Function):
         B = xs[0].size(0)
         dev = xs[0].device
         dpooled = dpooled.contiguous()
-        G = {n: torch.zeros(W.P[n].shape, device=dev, dtype=torch.float32) for n in names}
-        dstack_w = [torch.zeros(w.shape, device=dev, dtype=torch.float32) for w in W.w_stack]
-        dstack_b = [torch.zeros(b.shape, device=dev, dtype=torch.float32) for b in W.b_stack]
+        # fp32 gradient accumulators of every parameter (+ the stacked projections) as views of ONE zeroed buffer: one fill kernel
+        # instead of ~100; every view starts on a 256-byte boundary (the GEMM / attention epilogues use 16-byte vector REDs)
+        shapes = [tuple(W.P[n].shape) for n in names] + [tuple(w.shape) for w in W.w_stack] + [tuple(b.shape) for b in W.b_stack]
+        offs, total = [], 0
+        for shp in shapes:
+            offs.append(total)
+            total += (math.prod(shp) + 63) // 64 * 64
+        flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        views = [flat[o:o + math.prod(shp)].view(shp) for o, shp in zip(offs, shapes)]
+        G = dict(zip(names, views[:len(names)]))
+        dstack_w = views[len(names):len(names) + len(W.w_stack)]
+        dstack_b = views[len(names) + len(W.w_stack):]
         need_dx = any(ctx.needs_input_grad[:3])
         dxs = [torch.empty_like(x) for x in xs] if need_dx else None
         scratch = None

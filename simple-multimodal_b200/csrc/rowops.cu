@@ -155,37 +155,35 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
         }
       }
     }
-    float xh[R][NV][VN], g[R][NV][VN], c1[R], c2[R];
+    // the R rows' loads are all in flight; the arithmetic then goes row by row so that only one row's fp32 values are live
+    // (registers buy bytes in flight here: R = 4 keeps 96 KB per SM outstanding with one block of 8 warps)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
+      if (row0 + r >= rows) break;                       // warp-uniform
+      float xh[NV][VN], g[NV][VN];
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int i = 0; i < NV; ++i)
-        if (row0 + r < rows && lane + i * 32 < nvec) {
+        if (lane + i * 32 < nvec) {
           float d[VN], xv[VN]; rdy[r][i].unpack(d); rx[r][i].unpack(xv);
 #pragma unroll
           for (int j = 0; j < VN; ++j) {
-            xh[r][i][j] = (xv[j] - mean[r]) * rstd[r];
-            g[r][i][j] = d[j] * gm[i][j];
-            s1 += g[r][i][j];
-            s2 += g[r][i][j] * xh[r][i][j];
-            pg[i][j] += d[j] * xh[r][i][j];
+            xh[i][j] = (xv[j] - mean[r]) * rstd[r];
+            g[i][j] = d[j] * gm[i][j];
+            s1 += g[i][j];
+            s2 += g[i][j] * xh[i][j];
+            pg[i][j] += d[j] * xh[i][j];
             pb[i][j] += d[j];
           }
         }
-      c1[r] = s1; c2[r] = s2;
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) { c1[r] = warp_sum(c1[r]) * inv_h; c2[r] = warp_sum(c2[r]) * inv_h; }
-#pragma unroll
-    for (int r = 0; r < R; ++r)
+      const float c1 = warp_sum(s1) * inv_h, c2 = warp_sum(s2) * inv_h;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int vi = lane + i * 32;
-        if (row0 + r < rows && vi < nvec) {
+        if (vi < nvec) {
           float o[VN];
 #pragma unroll
-          for (int j = 0; j < VN; ++j) o[j] = rstd[r] * (g[r][i][j] - c1[r] - xh[r][i][j] * c2[r]);
+          for (int j = 0; j < VN; ++j) o[j] = rstd[r] * (g[i][j] - c1 - xh[i][j] * c2);
           if (dres) {
             float f[VN]; rres[r][i].unpack(f);
 #pragma unroll
@@ -199,6 +197,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
           }
         }
       }
+    }
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -546,7 +545,7 @@ int b200f_layernorm_bwd(const void* dy, const void* x, const float* mean, const 
     B200F_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(dres), B200F_ERR_ALIGN, "layernorm: 16-byte alignment");
     const int need = (H / VN + 31) / 32;
     DISPATCH_NV(need, NV, {
-      constexpr int R = NV <= 2 ? 2 : 1;
+      constexpr int R = NV <= 2 ? 4 : 1;
       const long long blocks = (rows + 8 * R - 1) / (8 * R);
       const int grid = int(blocks < (long long)num_sms() * 4 ? blocks : (long long)num_sms() * 4);
       layernorm_bwd_kernel<T, NV, R><<<grid, 256, 3 * H * sizeof(float), st>>>(static_cast<const T*>(dy), static_cast<const T*>(x), mean, rstd, gamma,

@@ -38,6 +38,7 @@ struct GemmTcParams {
   float* colsum;  // optional [N]: += column sums of the stored bf16 C (N % 64 == 0; staged bf16 epilogue only)
   uint32_t drop_thr, drop_seed_lo, drop_seed_hi;   // inverted dropout on the output (staged bf16 epilogue only); 0 = off
   float inv_keep;
+  int tma_store;   // bf16 output without residual / mask: staged tiles leave through cp.async.bulk.tensor stores (tensor map of C)
   int epi_stride;  // byte distance of a warp's two epilogue staging tiles (EPI_STAGE_BYTES), or 0 when the launch has a single tile per warp
 };
 
@@ -48,7 +49,7 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;                         // 2 x BN fp32: this / next tile's bias slice
-  static constexpr int EPI_OFFSET = BIAS_OFFSET + 2 * BN * 4;                  // 8 warps x 2 x 4 KB epilogue staging tiles
+  static constexpr int EPI_OFFSET = (BIAS_OFFSET + 2 * BN * 4 + 1023) / 1024 * 1024;   // 8 warps x 2 x 4 KB staging tiles, 1024-byte aligned (TMA SWIZZLE_128B)
   static constexpr int TOTAL = EPI_OFFSET + 8 * 2 * EPI_STAGE_BYTES;
 };
 
@@ -171,8 +172,8 @@ __device__ __forceinline__ void epi_issue_aux(const GemmTcParams& p, uint8_t* st
 // EXTRAS = dropout and/or column sums requested: a separate instantiation, so the plain epilogue (which bounds the K = 512
 // GEMMs) carries none of their instructions or registers (measured: the runtime-flag version cost those GEMMs 10-15 %).
 template <int NCOLS, bool EXTRAS>
-__device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, uint8_t* stage, const float* bias_s, uint32_t t_row, long long row0,
-                                                   int lane, int n_base, int c_begin, bool relu) {
+__device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, const CUtensorMap* tmc, uint8_t* stage, const float* bias_s, uint32_t t_row,
+                                                   long long row0, int lane, int n_base, int c_begin, bool relu) {
   constexpr int NBLK = NCOLS / 64;
   const long long row = row0 + lane;
   const int crow = lane >> 3, cchunk = lane & 7;             // coalesced phase: 4 rows x 8 chunks per instruction
@@ -184,6 +185,10 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, uint8_
     const int c0 = c_begin + blk * 64;
     const int col0 = n_base + c0;
     uint8_t* st = stage + (blk & 1) * p.epi_stride;
+    if (p.tma_store) {                                        // the bulk store that last read this staging tile must be done reading it
+      if (lane == 0) { if (p.epi_stride) tma_store_wait_read1(); else tma_store_wait_read(); }
+      __syncwarp();
+    }
     if (blk + 1 < NBLK) {
       epi_issue_aux(p, stage + ((blk + 1) & 1) * p.epi_stride, row0, col0 + 64, lane);
       cp_async_wait<1>();
@@ -256,14 +261,22 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, uint8_
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(st + sw128_offset(lane, q)) = outv[q];   // the cells this lane consumed
-    __syncwarp();
-    bf16* cbase = reinterpret_cast<bf16*>(p.C) + row0 * p.ldc + col0 + cchunk * 8;
+    if (p.tma_store) {
+      // the staged [32 x 128 B] tile (SWIZZLE_128B layout, 1024-byte aligned) leaves as ONE bulk tensor store issued by one lane:
+      // no LDS / STG instructions and no address arithmetic in the epilogue warps; rows past M are clipped by the tensor map
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { tma_store_2d(tmc, st, col0, int(row0)); tma_store_commit(); }
+    } else {
+      __syncwarp();
+      bf16* cbase = reinterpret_cast<bf16*>(p.C) + row0 * p.ldc + col0 + cchunk * 8;
 #pragma unroll
-    for (int it = 0; it < 8; ++it) outv[it] = *reinterpret_cast<const uint4*>(st + sw128_offset(it * 4 + crow, cchunk));
+      for (int it = 0; it < 8; ++it) outv[it] = *reinterpret_cast<const uint4*>(st + sw128_offset(it * 4 + crow, cchunk));
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + crow;
-      if (row0 + rr < p.M) *reinterpret_cast<uint4*>(cbase + (long long)rr * p.ldc) = outv[it];
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + crow;
+        if (row0 + rr < p.M) *reinterpret_cast<uint4*>(cbase + (long long)rr * p.ldc) = outv[it];
+      }
     }
     if (EXTRAS && p.colsum) {
       // bias gradient: column sums of the 32 x 64 block just staged (the rounded values that were stored).  A lane owns
@@ -329,7 +342,7 @@ __device__ __forceinline__ void epilogue_tile_f32(const GemmTcParams& p, uint8_t
 // One tile's epilogue for one warp: bias slice -> smem (all 8 epilogue warps, named barrier 1), first aux prefetch, wait for
 // the accumulator, drain this warp's 32 rows x BN/2 columns.
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* stage, float* bias_tile, uint64_t* full_bar, uint32_t full_phase,
+__device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, const CUtensorMap* tmc, uint8_t* stage, float* bias_tile, uint64_t* full_bar, uint32_t full_phase,
                                               uint32_t t_row, long long row0, int lane, int et, int n_base, int col_half) {
   const bool out_f32 = (p.flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) != 0;
   const bool accum = (p.flags & B200F_EPI_ACCUM) != 0;
@@ -342,8 +355,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* st
   mbar_wait(full_bar, full_phase);
   tc_fence_after();
   if (staged16)
-    if (p.drop_thr || p.colsum) epilogue_tile_bf16<BN / 2, true>(p, stage, bias_tile + c_begin, t_row, row0, lane, n_base, c_begin, relu);
-    else epilogue_tile_bf16<BN / 2, false>(p, stage, bias_tile + c_begin, t_row, row0, lane, n_base, c_begin, relu);
+    if (p.drop_thr || p.colsum) epilogue_tile_bf16<BN / 2, true>(p, tmc, stage, bias_tile + c_begin, t_row, row0, lane, n_base, c_begin, relu);
+    else epilogue_tile_bf16<BN / 2, false>(p, tmc, stage, bias_tile + c_begin, t_row, row0, lane, n_base, c_begin, relu);
   else if (out_f32 && p.vec_ok)
     epilogue_tile_f32<BN / 2>(p, stage, bias_tile + c_begin, t_row, row0, lane, n_base, c_begin, accum, relu);
   else
@@ -352,7 +365,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* st
 
 template <int BN, int STAGES, int A_MN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmTcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_c,
+               const GemmTcParams p) {
   using S = GemmSmem<BN, STAGES>;
   constexpr int TMEM_COLS = 2 * BN;
   extern __shared__ __align__(1024) uint8_t smem[];          // SWIZZLE_128B tiles need a 1024-byte aligned base (checked below)
@@ -469,13 +483,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t acc_phase = (it >> 1) & 1;
       const long long row0 = (long long)m_blk * BM + lane_grp * 32;
       const uint32_t t_row = tmem_base + (uint32_t(lane_grp * 32) << 16) + acc * BN;
-      epilogue_tile<BN>(p, stage, bias_s + acc * BN, &tmem_full[acc], acc_phase, t_row, row0, lane, threadIdx.x - 64, n_blk * BN, col_half);
+      epilogue_tile<BN>(p, &tma_c, stage, bias_s + acc * BN, &tmem_full[acc], acc_phase, t_row, row0, lane, threadIdx.x - 64, n_blk * BN, col_half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
   }
 
+  if (p.tma_store && warp >= 2 && lane == 0) tma_store_wait_read();   // pending bulk stores still read this CTA's staging tiles
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -499,14 +514,15 @@ struct PairSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;
-  static constexpr int EPI_OFFSET = BIAS_OFFSET + 2 * BN * 4;
+  static constexpr int EPI_OFFSET = (BIAS_OFFSET + 2 * BN * 4 + 1023) / 1024 * 1024;
   static constexpr int TOTAL = EPI_OFFSET + 8 * EB * EPI_STAGE_BYTES;
   static_assert(TOTAL <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 };
 
 template <int BN, int STAGES, int A_MN, int B_MN, int EB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmTcParams p) {
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_c,
+                    const GemmTcParams p) {
   using S = PairSmem<BN, STAGES, EB>;
   constexpr int TMEM_COLS = 2 * BN;
   constexpr int HALF_N = BN / 2;
@@ -629,13 +645,14 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const uint32_t acc_phase = (it >> 1) & 1;
       const long long row0 = (long long)m_blk * 2 * BM + (long long)rank * BM + lane_grp * 32;
       const uint32_t t_row = tmem_base + (uint32_t(lane_grp * 32) << 16) + acc * BN;
-      epilogue_tile<BN>(p, stage, bias_s + acc * BN, &tmem_full[acc], acc_phase, t_row, row0, lane, threadIdx.x - 64, n_blk * BN, col_half);
+      epilogue_tile<BN>(p, &tma_c, stage, bias_s + acc * BN, &tmem_full[acc], acc_phase, t_row, row0, lane, threadIdx.x - 64, n_blk * BN, col_half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
     }
   }
 
+  if (p.tma_store && warp >= 2 && lane == 0) tma_store_wait_read();   // pending bulk stores still read this CTA's staging tiles
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                  // the peer may still read this CTA's smem / signal its barriers
@@ -680,11 +697,12 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
 uint32_t g_dbg_mn_lbo = 0, g_dbg_mn_sbo = 0, g_dbg_mn_kadv = 0;
 
 bool g_dbg_disable_pair = false;     // b200f_debug_set(3, 1): force the single-CTA kernel (A/B testing)
+bool g_dbg_no_tma_store = false;     // b200f_debug_set(8, 1): LDS + STG copy-out instead of bulk tensor stores (A/B testing)
 bool g_dbg_six_stages = false;       // b200f_debug_set(7, 1): 6-stage / one-staging-tile pair kernel for launches without an aux block.
                                      // Measured no faster than 5 stages on any MulT shape (profiles/r01_e): the ring depth is not the limiter.
 
 template <int BN, int STAGES, int A_MN, int B_MN, int EB>
-static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, GemmTcParams p, int grid, cudaStream_t st) {
+static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, GemmTcParams p, int grid, cudaStream_t st) {
   using S = PairSmem<BN, STAGES, EB>;
   auto kern = gemm_tc_pair_kernel<BN, STAGES, A_MN, B_MN, EB>;
   p.epi_stride = (EB - 1) * EPI_STAGE_BYTES;
@@ -693,12 +711,12 @@ static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, GemmTcParam
     B200F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, p);
+  kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, tc, p);
   return check_launch("gemm_tc_pair_kernel");
 }
 
 template <int BN, int STAGES, int A_MN, int B_MN>
-static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcParams& p, int grid, cudaStream_t st) {
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmTcParams& p, int grid, cudaStream_t st) {
   using S = GemmSmem<BN, STAGES>;
   auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN>;
   static bool configured = false;
@@ -706,7 +724,7 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTc
     B200F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, p);
+  kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, tc, p);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -763,6 +781,16 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
   p.mask = static_cast<const bf16*>(a.relu_mask); p.ldm = a.ldm;
   p.alpha = a.alpha; p.flags = a.flags;
   p.vec_ok = vec_ok ? 1 : 0;
+  // bf16 output, nothing to prefetch into the staging tiles, full 64-column blocks: the epilogue stores through TMA
+  p.tma_store = (!out_f32 && vec_ok && !a.residual && !a.relu_mask && a.N % 64 == 0 && !g_dbg_no_tma_store) ? 1 : 0;
+  CUtensorMap tc;
+  memset(&tc, 0, sizeof(tc));
+  if (p.tma_store) {
+    uint64_t dims[2] = {uint64_t(a.N), uint64_t(a.M)}, strides[1] = {uint64_t(a.ldc) * 2};
+    uint32_t box[2] = {64, 32};
+    int rc = make_tmap_bf16(&tc, a.C, 2, dims, strides, box);
+    if (rc) return rc;
+  }
   p.epi_stride = EPI_STAGE_BYTES;
   p.colsum = a.colsum;
   p.drop_thr = drop_threshold(a.dropout_p); p.drop_seed_lo = a.drop_seed_lo; p.drop_seed_hi = a.drop_seed_hi;
@@ -783,30 +811,30 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
     const int pkey = (a.a_layout ? 2 : 0) | (a.b_layout ? 1 : 0);
     if (!a.residual && !a.relu_mask && g_dbg_six_stages) {     // experiment (b200f_debug_set(7, 1)): one staging tile per warp, six TMA stages
       switch (pkey) {
-        case 0: return launch_pair<256, 6, 0, 0, 1>(ta, tb, p, 2 * clusters, st);
-        case 1: return launch_pair<256, 6, 0, 1, 1>(ta, tb, p, 2 * clusters, st);
-        case 2: return launch_pair<256, 6, 1, 0, 1>(ta, tb, p, 2 * clusters, st);
-        default: return launch_pair<256, 6, 1, 1, 1>(ta, tb, p, 2 * clusters, st);
+        case 0: return launch_pair<256, 6, 0, 0, 1>(ta, tb, tc, p, 2 * clusters, st);
+        case 1: return launch_pair<256, 6, 0, 1, 1>(ta, tb, tc, p, 2 * clusters, st);
+        case 2: return launch_pair<256, 6, 1, 0, 1>(ta, tb, tc, p, 2 * clusters, st);
+        default: return launch_pair<256, 6, 1, 1, 1>(ta, tb, tc, p, 2 * clusters, st);
       }
     }
     switch (pkey) {
-      case 0: return launch_pair<256, 5, 0, 0, 2>(ta, tb, p, 2 * clusters, st);
-      case 1: return launch_pair<256, 5, 0, 1, 2>(ta, tb, p, 2 * clusters, st);
-      case 2: return launch_pair<256, 5, 1, 0, 2>(ta, tb, p, 2 * clusters, st);
-      default: return launch_pair<256, 5, 1, 1, 2>(ta, tb, p, 2 * clusters, st);
+      case 0: return launch_pair<256, 5, 0, 0, 2>(ta, tb, tc, p, 2 * clusters, st);
+      case 1: return launch_pair<256, 5, 0, 1, 2>(ta, tb, tc, p, 2 * clusters, st);
+      case 2: return launch_pair<256, 5, 1, 0, 2>(ta, tb, tc, p, 2 * clusters, st);
+      default: return launch_pair<256, 5, 1, 1, 2>(ta, tb, tc, p, 2 * clusters, st);
     }
   }
   const int grid = units < num_sms() ? units : num_sms();
   const int key = (BN == 256 ? 4 : 0) | (a.a_layout ? 2 : 0) | (a.b_layout ? 1 : 0);
   switch (key) {
-    case 0: return launch_cfg<128, 4, 0, 0>(ta, tb, p, grid, st);
-    case 1: return launch_cfg<128, 4, 0, 1>(ta, tb, p, grid, st);
-    case 2: return launch_cfg<128, 4, 1, 0>(ta, tb, p, grid, st);
-    case 3: return launch_cfg<128, 4, 1, 1>(ta, tb, p, grid, st);
-    case 4: return launch_cfg<256, 3, 0, 0>(ta, tb, p, grid, st);
-    case 5: return launch_cfg<256, 3, 0, 1>(ta, tb, p, grid, st);
-    case 6: return launch_cfg<256, 3, 1, 0>(ta, tb, p, grid, st);
-    default: return launch_cfg<256, 3, 1, 1>(ta, tb, p, grid, st);
+    case 0: return launch_cfg<128, 4, 0, 0>(ta, tb, tc, p, grid, st);
+    case 1: return launch_cfg<128, 4, 0, 1>(ta, tb, tc, p, grid, st);
+    case 2: return launch_cfg<128, 4, 1, 0>(ta, tb, tc, p, grid, st);
+    case 3: return launch_cfg<128, 4, 1, 1>(ta, tb, tc, p, grid, st);
+    case 4: return launch_cfg<256, 3, 0, 0>(ta, tb, tc, p, grid, st);
+    case 5: return launch_cfg<256, 3, 0, 1>(ta, tb, tc, p, grid, st);
+    case 6: return launch_cfg<256, 3, 1, 0>(ta, tb, tc, p, grid, st);
+    default: return launch_cfg<256, 3, 1, 1>(ta, tb, tc, p, grid, st);
   }
 }
 

@@ -22,8 +22,11 @@ ap.add_argument("--chunk", type=int, default=256)
 ap.add_argument("--only", default="")
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--filter", default="")
+ap.add_argument("--no-tma-store", action="store_true", help="A/B: LDS + STG copy-out instead of bulk tensor stores (b200f_debug_set(8, 1))")
 ap.add_argument("--six-stages", action="store_true", help="A/B: 6-stage pair GEMM for launches without an aux block (b200f_debug_set(7, 1))")
 args = ap.parse_args()
+if args.no_tma_store:
+    pkg._lib.lib().b200f_debug_set(8, 1)
 if args.six_stages:
     pkg._lib.lib().b200f_debug_set(7, 1)
 dev = torch.device("cuda")

@@ -266,7 +266,7 @@ def main():
     # ~300 launches from Python costs ~16 ms of host time per step, which bounds the step when ranks share a CPU-limited host.
     # Captured when the step has no collective inside forward/backward (the InfoNCE all-gather) and fits the graph's private
     # pool comfortably; the gradient all-reduce stays outside the graph.  Falls back to eager issue if capture fails.
-    graphed, graph_note = None, "eager (--no-graph)"
+    graphed, graph_note, graph_inputs = None, "eager (--no-graph)", None
     if not args.no_graph:
         # (capturing the NCCL all-gather of the InfoNCE step was tried at N=2 and hung in capture: those steps stay eager)
         in_graph_collective = world > 1 and kind in ("contrastive", "hierarchical")
@@ -280,6 +280,7 @@ def main():
                 torch.cuda.synchronize()
                 graphed = pkg.GraphedTrainStep(head, resident, lambda out: objective(out, b_global), kw)
                 graph_note = "cuda-graph replay of forward+loss+backward (GraphedTrainStep)"
+                graph_inputs = graphed.static_inputs          # the device-timed leg feeds the graph's own input buffers (already resident)
             except Exception as exc:                         # noqa: BLE001 -- never let the capture take the bench down
                 graphed, graph_note = None, f"eager (capture failed: {type(exc).__name__}: {str(exc)[:120]})"
                 torch.cuda.synchronize()
@@ -287,7 +288,7 @@ def main():
     def step(inputs):
         if graphed is None:
             return eager_step(inputs)
-        loss = graphed(*inputs)
+        loss = graphed(*(graph_inputs if inputs is resident else inputs))
         if world > 1:
             pkg.allreduce_gradients(params)
         return loss

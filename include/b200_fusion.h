@@ -249,6 +249,19 @@ int b200f_ce_ls_fwd(const void* logits, int64_t ldx, const int64_t* target, floa
 int b200f_ce_ls_bwd(const float* probs, const int64_t* target, float label_smoothing, const float* gscale_dev, void* dlogits,
                     int64_t lddx, int64_t B, int32_t C, int32_t dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Trainer-side optimizer step over the fusion parameters: clip_grad_norm_ + AdamW
+ * (reference training/advanced_trainer.py:91-94,174-180) as multi-tensor kernels.  `table` is a device buffer laid out as
+ * params[T], grads[T], exp_avg[T], exp_avg_sq[T] (8-byte fp32 pointers), numel[T] (int64), chunks[n_chunks] ({int32 tensor,
+ * int32 first element}, 4096 elements per chunk).  b200f_grad_clip_coef leaves {sum of squares, total norm, clip coefficient}
+ * in scratch3 (device, 3 floats; nothing is read back to the host); b200f_adamw_step scales the gradients by *clip_coef
+ * (NULL = 1) and applies torch.optim.AdamW's update with bias correction for `step` (1-based); the hyper-parameters are doubles, like the Python
+ * scalars torch folds on the host before rounding to fp32.
+ * ------------------------------------------------------------------------------------------- */
+int b200f_grad_clip_coef(const void* table, int32_t n_tensors, int32_t n_chunks, float max_norm, float* scratch3, void* stream);
+int b200f_adamw_step(const void* table, int32_t n_tensors, int32_t n_chunks, const float* clip_coef, double lr, double beta1,
+                     double beta2, double eps, double weight_decay, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

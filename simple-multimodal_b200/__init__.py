@@ -12,8 +12,9 @@ from .fusion_layers import (AdaptiveFusion, ContrastiveFusion, CrossModalTransfo
 from .ops import allreduce_gradients, manual_seed                        # noqa: F401
 from .staging import FeaturePrefetcher                                   # noqa: F401
 from .graphs import GraphedTrainStep                                     # noqa: F401
+from .optim import FusedAdamW                                            # noqa: F401
 from . import prediction_heads                                           # noqa: F401
 from .prediction_heads import AuxiliaryHeads, EmotionClassifier, SmoothedCrossEntropy   # noqa: F401
 
 __all__ = ["EarlyFusion", "LateFusion", "MultimodalTransformer", "CrossModalTransformer", "GraphFusion", "ContrastiveFusion",
-           "AdaptiveFusion", "HierarchicalFusion", "ModalityDropout", "allreduce_gradients", "manual_seed", "FeaturePrefetcher", "GraphedTrainStep", "EmotionClassifier", "AuxiliaryHeads", "SmoothedCrossEntropy", "B200FusionError"]
+           "AdaptiveFusion", "HierarchicalFusion", "ModalityDropout", "allreduce_gradients", "manual_seed", "FeaturePrefetcher", "GraphedTrainStep", "FusedAdamW", "EmotionClassifier", "AuxiliaryHeads", "SmoothedCrossEntropy", "B200FusionError"]

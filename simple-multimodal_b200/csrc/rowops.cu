@@ -316,27 +316,54 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __rest
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __bfloat162float(src[i]);
 }
 
-// x[B,L,H] -> y[b,:] = mean_l x[b,l,:]; one thread per 16-byte column group, loop over L.
+// x[B,L,H] -> y[b,:] = mean_l x[b,l,:].  One block per (sample, group of CX 16-byte columns); the block's 512 threads are
+// CX column threads x RY row groups, each row group walks l = ry, ry + RY, ... with eight independent 16-byte loads in flight
+// (the one-thread-per-column loop it replaces kept 1 MB in flight over the whole GPU at B = 256: 1.9 TB/s); the row groups
+// are combined through shared memory.
 template <typename T>
-__global__ void __launch_bounds__(128) meanpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long ldy, int L, int H) {
+__global__ void __launch_bounds__(512) meanpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long ldy, int L, int H, int CX) {
   constexpr int VN = Vec16<T>::N;
-  const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * VN;
-  if (c0 >= H) return;
+  extern __shared__ float pool_red[];                 // [RY][CX * VN]
+  const int RY = blockDim.x / CX;
+  const int cx = threadIdx.x % CX, ry = threadIdx.x / CX;
+  const int c0 = (blockIdx.y * CX + cx) * VN;
+  const bool col_ok = c0 < H && ry < RY;
   const long long b = blockIdx.x;
   const T* xb = x + b * (long long)L * H + c0;
   float acc[VN];
 #pragma unroll
   for (int j = 0; j < VN; ++j) acc[j] = 0.f;
-#pragma unroll 4
-  for (int l = 0; l < L; ++l) {
-    Vec16<T> t; t.load(xb + (long long)l * H); float f[VN]; t.unpack(f);
+  if (col_ok) {
+    int l = ry;
+    for (; l + 7 * RY < L; l += 8 * RY) {
+      Vec16<T> t[8];
 #pragma unroll
-    for (int j = 0; j < VN; ++j) acc[j] += f[j];
+      for (int u = 0; u < 8; ++u) t[u].load(xb + (long long)(l + u * RY) * H);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float f[VN]; t[u].unpack(f);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) acc[j] += f[j];
+      }
+    }
+    for (; l < L; l += RY) {
+      Vec16<T> t; t.load(xb + (long long)l * H); float f[VN]; t.unpack(f);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < VN; ++j) pool_red[(ry * CX + cx) * VN + j] = acc[j];
   }
-  const float inv = 1.f / L;
+  __syncthreads();
+  if (col_ok && ry == 0) {
+    for (int r = 1; r < RY; ++r)
 #pragma unroll
-  for (int j = 0; j < VN; ++j) acc[j] *= inv;
-  Vec16<T> o; o.pack(acc); o.store(y + b * ldy + c0);
+      for (int j = 0; j < VN; ++j) acc[j] += pool_red[(r * CX + cx) * VN + j];
+    const float inv = 1.f / L;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) acc[j] *= inv;
+    Vec16<T> o; o.pack(acc); o.store(y + b * ldy + c0);
+  }
 }
 
 template <typename T>
@@ -502,6 +529,15 @@ static inline int ew_grid(long long n, int block) {
   else if ((nv_needed) <= 8) { constexpr int NV = 8; __VA_ARGS__ }                 \
   else return fail(B200F_ERR_SHAPE, "row too long for the row-wise kernels");
 
+// TMA-staged LayerNorm kernels (rownorm_tma.cu): taken for contiguous rows of up to 1 KB x 2 passes; b200f_debug_set(9, 1)
+// forces the register-staged kernels above (A/B testing)
+bool g_dbg_no_ln_tma = false;
+bool ln_tma_shape_ok(int64_t rows, int32_t H, int32_t dtype);
+int layernorm_fwd_tma(const void* x, const float* gamma, const float* beta, const void* post1, const void* post2, void* y, float* mean, float* rstd,
+                      int64_t rows, int32_t H, float eps, int32_t dtype, cudaStream_t st);
+int layernorm_bwd_tma(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, const void* dres, void* dx,
+                      float* dgamma, float* dbeta, float* dxsum, int64_t rows, int32_t H, int32_t dtype, cudaStream_t st);
+
 }  // namespace b200f
 
 using namespace b200f;
@@ -516,6 +552,7 @@ int b200f_layernorm_fwd(const void* x, const float* gamma, const float* beta, co
     constexpr int VN = Vec16<T>::N;
     B200F_REQUIRE(H % VN == 0 && H > 0, B200F_ERR_SHAPE, "layernorm: H=%d must be a multiple of %d", H, VN);
     B200F_REQUIRE(aligned16(x) && aligned16(y) && aligned16(post1) && aligned16(post2), B200F_ERR_ALIGN, "layernorm: 16-byte alignment");
+    if (!g_dbg_no_ln_tma && ln_tma_shape_ok(rows, H, dtype)) return layernorm_fwd_tma(x, gamma, beta, post1, post2, y, mean, rstd, rows, H, eps, dtype, st);
     const int need = (H / VN + 31) / 32;
     DISPATCH_NV(need, NV, {
       constexpr int R = NV <= 2 ? 2 : 1;
@@ -543,6 +580,7 @@ int b200f_layernorm_bwd(const void* dy, const void* x, const float* mean, const 
     constexpr int VN = Vec16<T>::N;
     B200F_REQUIRE(H % VN == 0 && H > 0, B200F_ERR_SHAPE, "layernorm: H=%d must be a multiple of %d", H, VN);
     B200F_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(dres), B200F_ERR_ALIGN, "layernorm: 16-byte alignment");
+    if (!g_dbg_no_ln_tma && ln_tma_shape_ok(rows, H, dtype)) return layernorm_bwd_tma(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, dxsum, rows, H, dtype, st);
     const int need = (H / VN + 31) / 32;
     DISPATCH_NV(need, NV, {
       constexpr int R = NV <= 2 ? 4 : 1;
@@ -620,8 +658,10 @@ int b200f_meanpool_fwd(const void* x, void* y, int64_t ldy, int32_t B, int32_t L
     constexpr int VN = Vec16<T>::N;
     B200F_REQUIRE(H % VN == 0 && ldy % VN == 0 && L > 0, B200F_ERR_SHAPE, "meanpool: shape");
     B200F_REQUIRE(aligned16(x) && aligned16(y), B200F_ERR_ALIGN, "meanpool: alignment");
-    const int gy = (H / VN + 127) / 128;
-    meanpool_fwd_kernel<T><<<dim3(B, gy), 128, 0, st>>>(static_cast<const T*>(x), static_cast<T*>(y), ldy, L, H);
+    const int hv = H / VN;
+    const int cx = hv < 64 ? hv : 64;                  // 16-byte column groups per block; the other 512 / cx thread rows split L
+    const int gy = (hv + cx - 1) / cx;
+    meanpool_fwd_kernel<T><<<dim3(B, gy), 512, 512 * VN * sizeof(float), st>>>(static_cast<const T*>(x), static_cast<T*>(y), ldy, L, H, cx);
   })
   return check_launch("meanpool_fwd");
 }

@@ -367,13 +367,26 @@ def main():
     # (pkg.FeaturePrefetcher) while step k computes, and each step ends with the device->host read of its loss.
     pf = pkg.FeaturePrefetcher(dev)
 
+    # The loss of every step is read back to the host inside the timed region, one step late: step k's loss goes to a pinned
+    # word with an asynchronous D2H copy and is consumed after step k+1 has been issued (the way a training loop logs it), so
+    # an eagerly issued step (hierarchical: ~300 ms of host issue time) does not start from an idle GPU after every read.
+    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+    losses = []
+
     def e2e_steps(n):
         pf.submit(host)
         for k in range(n):
             xs = pf.get() if graphed is not None else [x.requires_grad_(True) for x in pf.get()]
             if k + 1 < n:
                 pf.submit(host)
-            float(step(xs).detach().cpu())
+            loss_host[k % 2].copy_(step(xs).detach().float(), non_blocking=True)
+            loss_ready[k % 2].record()
+            if k > 0:
+                loss_ready[(k - 1) % 2].synchronize()
+                losses.append(float(loss_host[(k - 1) % 2]))
+        loss_ready[(n - 1) % 2].synchronize()
+        losses.append(float(loss_host[(n - 1) % 2]))
 
     e2e_steps(2)
     sync_all()

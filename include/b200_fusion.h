@@ -148,6 +148,11 @@ int b200f_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream)
  * backward: dx[b,l,:] = dy[b,:] / L. */
 int b200f_meanpool_fwd(const void* x, void* y, int64_t ldy, int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream);
 int b200f_meanpool_bwd(const void* dy, int64_t lddy, void* dx, int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream);
+/* weighted pooling over L: y[b,:] = sum_l w[b,l] * x[b,l,:], w fp32 [B,L].  With w = mask / max(sum_l mask, 1e-9)
+ * it is the attention-mask mean pooling of the text encoder (models/encoders.py:89-93) applied to per-token projected features;
+ * backward: dx[b,l,:] = w[b,l] * dy[b,:]. */
+int b200f_weighted_pool_fwd(const void* x, const float* w, void* y, int64_t ldy, int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream);
+int b200f_weighted_pool_bwd(const void* dy, int64_t lddy, const float* w, void* dx, int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream);
 /* cat = [t*m0 | a*m1 | v*m2]  rows of 3H (fusion_layers.py:38,350,437 + encoders.py:317-319);
  * mask is [B,3] fp32 keep-mask or NULL.  Backward splits and re-applies the mask, accumulating
  * into dt/da/dv when `accumulate`. */

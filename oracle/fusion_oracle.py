@@ -235,6 +235,29 @@ def adaptive_fusion(t: Tensor, a: Tensor, v: Tensor, P: Params, prefix: str = ""
     return {"fused_features": fused, "attention_weights": weights, "adaptive_weights": gate}
 
 
+def encoder_pool(seq: Tensor, pooling: str, attention_mask: Optional[Tensor] = None) -> Tensor:
+    """How the reference encoders reduce `sequence_output` [B,L,D] to one vector per sample before `projection`:
+    'cls' = token 0 (text encoder when 'bert' is in the backbone's model_type -- true for deberta-v2, models/encoders.py:86-87);
+    'masked_mean' = attention-mask mean with the 1e-9 clamp (text encoder otherwise, :88-93);
+    'mean' = plain mean over the sequence (audio :157, video :241)."""
+    if pooling == "cls":
+        return seq[:, 0]
+    if pooling == "mean":
+        return seq.mean(dim=1)
+    if pooling == "masked_mean":
+        m = attention_mask.to(seq.dtype).unsqueeze(-1).expand(seq.size())
+        return (seq * m).sum(1) / m.sum(1).clamp(min=1e-9)
+    raise ValueError(pooling)
+
+
+def sequence_projection(seq: Tensor, w: Tensor, b: Tensor, pooling: str, attention_mask: Optional[Tensor] = None) -> Dict[str, Tensor]:
+    """SURVEY 8f rank 2 (extension feeding MulT real sequences): the encoder's own `projection` Linear (models/encoders.py:35,134,207)
+    applied per token, and the encoder's pooled `features` = projection(pool(sequence_output)) (:96, :160, :244; dropout p = 0).
+    `features` is computed the reference's way (pool first, then project); pooling the projected tokens gives the same vector
+    because the pooling weights sum to one (checked in tests/test_oracle.py)."""
+    return {"sequence_features": affine(seq, w, b), "features": affine(encoder_pool(seq, pooling, attention_mask), w, b)}
+
+
 def pool_sequence(x: Tensor) -> Tensor:
     """The one explicit step the hierarchical head needs for [B,L,H] inputs
     (SURVEY F3): mean over L, the rule of models/fusion_layers.py:166-168."""
@@ -243,11 +266,12 @@ def pool_sequence(x: Tensor) -> Tensor:
 
 def hierarchical_fusion(t: Tensor, a: Tensor, v: Tensor, P: Params, prefix: str = "", heads: int = 8,
                         graph_layers: int = 3, temperature: float = 0.07,
-                        compute_contrastive_loss: bool = False) -> Dict[str, object]:
+                        compute_contrastive_loss: bool = False, pooled=None) -> Dict[str, object]:
     """HierarchicalFusion.forward, models/fusion_layers.py:478-520.  For 2-D
     inputs this is the literal reference; for 3-D inputs MulT sees the sequences
-    and the four 2-D-only heads see `pool_sequence` of them."""
-    t2, a2, v2 = pool_sequence(t), pool_sequence(a), pool_sequence(v)
+    and the four 2-D-only heads see `pool_sequence` of them, or the
+    encoders' own pooled features when `pooled=(t2, a2, v2)` is given."""
+    t2, a2, v2 = pooled if pooled is not None else (pool_sequence(t), pool_sequence(a), pool_sequence(v))
     early = early_fusion(t2, a2, v2, P, prefix + "early_fusion.")
     mult = mult_fusion(t, a, v, P, prefix + "mult_fusion.", heads)["fused_features"]
     graph = graph_fusion(t2, a2, v2, P, prefix + "graph_fusion.", graph_layers)

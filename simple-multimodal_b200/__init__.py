@@ -13,8 +13,9 @@ from .ops import allreduce_gradients, manual_seed                        # noqa:
 from .staging import FeaturePrefetcher                                   # noqa: F401
 from .graphs import GraphedTrainStep                                     # noqa: F401
 from .optim import FusedAdamW                                            # noqa: F401
+from .sequence_features import SequenceProjector, text_pooling_of        # noqa: F401
 from . import prediction_heads                                           # noqa: F401
 from .prediction_heads import AuxiliaryHeads, EmotionClassifier, SmoothedCrossEntropy   # noqa: F401
 
 __all__ = ["EarlyFusion", "LateFusion", "MultimodalTransformer", "CrossModalTransformer", "GraphFusion", "ContrastiveFusion",
-           "AdaptiveFusion", "HierarchicalFusion", "ModalityDropout", "allreduce_gradients", "manual_seed", "FeaturePrefetcher", "GraphedTrainStep", "FusedAdamW", "EmotionClassifier", "AuxiliaryHeads", "SmoothedCrossEntropy", "B200FusionError"]
+           "AdaptiveFusion", "HierarchicalFusion", "ModalityDropout", "allreduce_gradients", "manual_seed", "FeaturePrefetcher", "GraphedTrainStep", "FusedAdamW", "SequenceProjector", "text_pooling_of", "EmotionClassifier", "AuxiliaryHeads", "SmoothedCrossEntropy", "B200FusionError"]

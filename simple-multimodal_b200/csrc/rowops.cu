@@ -321,7 +321,8 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __rest
 // (the one-thread-per-column loop it replaces kept 1 MB in flight over the whole GPU at B = 256: 1.9 TB/s); the row groups
 // are combined through shared memory.
 template <typename T>
-__global__ void __launch_bounds__(512) meanpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long ldy, int L, int H, int CX) {
+__global__ void __launch_bounds__(512) meanpool_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y, long long ldy, int L,
+                                                           int H, int CX) {   // w: nullptr = plain mean (1/L), else per-(b,l) weights [B,L]
   constexpr int VN = Vec16<T>::N;
   extern __shared__ float pool_red[];                 // [RY][CX * VN]
   const int RY = blockDim.x / CX;
@@ -342,14 +343,16 @@ __global__ void __launch_bounds__(512) meanpool_fwd_kernel(const T* __restrict__
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         float f[VN]; t[u].unpack(f);
+        const float wl = w ? __ldg(w + b * L + l + u * RY) : 1.f;
 #pragma unroll
-        for (int j = 0; j < VN; ++j) acc[j] += f[j];
+        for (int j = 0; j < VN; ++j) acc[j] += wl * f[j];
       }
     }
     for (; l < L; l += RY) {
       Vec16<T> t; t.load(xb + (long long)l * H); float f[VN]; t.unpack(f);
+      const float wl = w ? __ldg(w + b * L + l) : 1.f;
 #pragma unroll
-      for (int j = 0; j < VN; ++j) acc[j] += f[j];
+      for (int j = 0; j < VN; ++j) acc[j] += wl * f[j];
     }
 #pragma unroll
     for (int j = 0; j < VN; ++j) pool_red[(ry * CX + cx) * VN + j] = acc[j];
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(512) meanpool_fwd_kernel(const T* __restrict__
     for (int r = 1; r < RY; ++r)
 #pragma unroll
       for (int j = 0; j < VN; ++j) acc[j] += pool_red[(r * CX + cx) * VN + j];
-    const float inv = 1.f / L;
+    const float inv = w ? 1.f : 1.f / L;
 #pragma unroll
     for (int j = 0; j < VN; ++j) acc[j] *= inv;
     Vec16<T> o; o.pack(acc); o.store(y + b * ldy + c0);
@@ -367,14 +370,16 @@ __global__ void __launch_bounds__(512) meanpool_fwd_kernel(const T* __restrict__
 }
 
 template <typename T>
-__global__ void meanpool_bwd_kernel(const T* __restrict__ dy, long long lddy, T* __restrict__ dx, long long B, int L, int H) {
+__global__ void meanpool_bwd_kernel(const T* __restrict__ dy, long long lddy, const float* __restrict__ w, T* __restrict__ dx, long long B, int L, int H) {
   constexpr int VN = Vec16<T>::N;
   const int hv = H / VN;
   const long long total = B * L * hv;
-  const float inv = 1.f / L;
+  const float inv_l = 1.f / L;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = int(i % hv);
-    const long long b = i / ((long long)hv * L);
+    const long long bl = i / hv;                      // b * L + l
+    const long long b = bl / L;
+    const float inv = w ? __ldg(w + bl) : inv_l;
     Vec16<T> t; t.load(dy + b * lddy + c * VN); float f[VN]; t.unpack(f);
 #pragma unroll
     for (int j = 0; j < VN; ++j) f[j] *= inv;
@@ -651,8 +656,7 @@ int b200f_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream)
   return check_launch("cast_bf16_f32");
 }
 
-int b200f_meanpool_fwd(const void* x, void* y, int64_t ldy, int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int pool_fwd(const void* x, const float* w, void* y, int64_t ldy, int32_t B, int32_t L, int32_t H, int32_t dtype, cudaStream_t st) {
   if (B == 0) return B200F_OK;
   DISPATCH_DTYPE(dtype, T, {
     constexpr int VN = Vec16<T>::N;
@@ -661,21 +665,38 @@ int b200f_meanpool_fwd(const void* x, void* y, int64_t ldy, int32_t B, int32_t L
     const int hv = H / VN;
     const int cx = hv < 64 ? hv : 64;                  // 16-byte column groups per block; the other 512 / cx thread rows split L
     const int gy = (hv + cx - 1) / cx;
-    meanpool_fwd_kernel<T><<<dim3(B, gy), 512, 512 * VN * sizeof(float), st>>>(static_cast<const T*>(x), static_cast<T*>(y), ldy, L, H, cx);
+    meanpool_fwd_kernel<T><<<dim3(B, gy), 512, 512 * VN * sizeof(float), st>>>(static_cast<const T*>(x), w, static_cast<T*>(y), ldy, L, H, cx);
   })
   return check_launch("meanpool_fwd");
 }
 
-int b200f_meanpool_bwd(const void* dy, int64_t lddy, void* dx, int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int pool_bwd(const void* dy, int64_t lddy, const float* w, void* dx, int32_t B, int32_t L, int32_t H, int32_t dtype, cudaStream_t st) {
   if (B == 0) return B200F_OK;
   DISPATCH_DTYPE(dtype, T, {
     constexpr int VN = Vec16<T>::N;
     B200F_REQUIRE(H % VN == 0 && lddy % VN == 0 && L > 0, B200F_ERR_SHAPE, "meanpool: shape");
     B200F_REQUIRE(aligned16(dx) && aligned16(dy), B200F_ERR_ALIGN, "meanpool: alignment");
-    meanpool_bwd_kernel<T><<<ew_grid((long long)B * L * (H / VN), 256), 256, 0, st>>>(static_cast<const T*>(dy), lddy, static_cast<T*>(dx), B, L, H);
+    meanpool_bwd_kernel<T><<<ew_grid((long long)B * L * (H / VN), 256), 256, 0, st>>>(static_cast<const T*>(dy), lddy, w, static_cast<T*>(dx), B, L, H);
   })
   return check_launch("meanpool_bwd");
+}
+
+int b200f_meanpool_fwd(const void* x, void* y, int64_t ldy, int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream) {
+  return pool_fwd(x, nullptr, y, ldy, B, L, H, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int b200f_meanpool_bwd(const void* dy, int64_t lddy, void* dx, int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream) {
+  return pool_bwd(dy, lddy, nullptr, dx, B, L, H, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int b200f_weighted_pool_fwd(const void* x, const float* w, void* y, int64_t ldy, int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream) {
+  B200F_REQUIRE(w != nullptr, B200F_ERR_SHAPE, "weighted_pool: weights are required");
+  return pool_fwd(x, w, y, ldy, B, L, H, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int b200f_weighted_pool_bwd(const void* dy, int64_t lddy, const float* w, void* dx, int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream) {
+  B200F_REQUIRE(w != nullptr, B200F_ERR_SHAPE, "weighted_pool: weights are required");
+  return pool_bwd(dy, lddy, w, dx, B, L, H, dtype, static_cast<cudaStream_t>(stream));
 }
 
 int b200f_concat3_fwd(const void* t, const void* a, const void* v, const float* mask, void* cat, int64_t B, int32_t H, int32_t dtype, void* stream) {

@@ -9,7 +9,8 @@ arithmetic runs in libb200fusion.so through `ops.py` / `mult_engine.py`, and the
 
 Extensions over the reference: an optional trailing `mask=None` keyword ([B,3] keep-mask,
 the ModalityDropout multiply of models/encoders.py:317-319 fused into the first load), and
-HierarchicalFusion accepts [B,L,H] sequences (MulT sees them, the other heads see their mean over L).
+HierarchicalFusion accepts [B,L,H] sequences (MulT sees them, the other heads see their mean over L, or the
+`pooled_features=(t, a, v)` given by the caller -- see sequence_features.SequenceProjector).
 
 Precision: bfloat16 inputs (or `compute_dtype=torch.bfloat16`, or CUDA autocast) run the tcgen05
 kernels; float32 inputs run the fp32 parity kernels.  Parameters are always fp32 masters.
@@ -388,9 +389,14 @@ class HierarchicalFusion(_FusionBase):
         # the reference's Sequential is Linear, ReLU, Dropout, Linear: drop the trailing activation slots
         self.meta_fusion = nn.Sequential(*list(self.meta_fusion)[:4])
 
-    def forward(self, text_features, audio_features, video_features, compute_contrastive_loss: bool = False, mask=None):
+    def forward(self, text_features, audio_features, video_features, compute_contrastive_loss: bool = False, mask=None, pooled_features=None):
         (t, a, v), mask, dt = self._prepare((text_features, audio_features, video_features), mask)
-        pooled2d = [x if x.dim() == 2 else ops.MeanPoolFn.apply(x) for x in (t, a, v)]
+        if pooled_features is not None:        # extension: the encoders' own pooled features for the 2-D heads
+            if len(pooled_features) != 3 or any(x.dim() != 2 or x.size(0) != t.size(0) for x in pooled_features):
+                raise B200FusionError("pooled_features must be three [B,H] tensors")
+            pooled2d, _, _ = self._prepare(tuple(pooled_features), None)
+        else:
+            pooled2d = [x if x.dim() == 2 else ops.MeanPoolFn.apply(x) for x in (t, a, v)]
         cat = _masked_cat(*pooled2d, mask)                                   # shared by early / graph / contrastive / adaptive
         feats = ops.Split3Fn.apply(cat) if mask is not None else pooled2d
         early = self.early_fusion._run(cat)

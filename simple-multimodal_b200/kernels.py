@@ -206,6 +206,24 @@ def meanpool_bwd(dy: Tensor, Lx: int) -> Tensor:
     return dx
 
 
+def weighted_pool_fwd(x: Tensor, w: Tensor) -> Tensor:
+    """y[b,:] = sum_l w[b,l] x[b,l,:]  (w fp32 [B,L], contiguous)"""
+    B, Lx, H = x.shape
+    out = torch.empty((B, H), device=x.device, dtype=x.dtype)
+    check(lib().b200f_weighted_pool_fwd(ptr(x), ptr(w), ptr(out), C.c_int64(out.stride(0)), C.c_int32(B), C.c_int32(Lx), C.c_int32(H),
+                                        dtype_code(x.dtype), stream_ptr()), "b200f_weighted_pool_fwd")
+    return out
+
+
+def weighted_pool_bwd(dy: Tensor, w: Tensor) -> Tensor:
+    B, H = dy.shape
+    Lx = w.size(1)
+    dx = torch.empty((B, Lx, H), device=dy.device, dtype=dy.dtype)
+    check(lib().b200f_weighted_pool_bwd(ptr(dy), C.c_int64(dy.stride(0)), ptr(w), ptr(dx), C.c_int32(B), C.c_int32(Lx), C.c_int32(H),
+                                        dtype_code(dy.dtype), stream_ptr()), "b200f_weighted_pool_bwd")
+    return dx
+
+
 def concat3_fwd(t: Tensor, a: Tensor, v: Tensor, mask: Optional[Tensor]) -> Tensor:
     B, H = t.shape
     cat = torch.empty((B, 3 * H), device=t.device, dtype=t.dtype)

@@ -149,6 +149,20 @@ class MeanPoolFn(torch.autograd.Function):
         return K.meanpool_bwd(_c(dy), ctx.L)
 
 
+class WeightedPoolFn(torch.autograd.Function):
+    """y[b,:] = sum_l w[b,l] x[b,l,:]; w is a constant fp32 [B,L] (normalised attention mask)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(w)
+        return K.weighted_pool_fwd(_c(x), w)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (w,) = ctx.saved_tensors
+        return K.weighted_pool_bwd(_c(dy), w), None
+
+
 class L2NormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y):

@@ -163,7 +163,7 @@ def run_reference(args, kind, lens, flag, cpu_batch, world, rank):
             "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port",
                              "sample": f"{cpu_batch} samples/step x {args.steps} steps of the same workload (fp32, torch CPU ops, all host threads)"},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(kind, lens, flag, cpu_batch, budget_s=20.0, dropout=0.0):
@@ -188,7 +188,30 @@ def cpu_baseline(kind, lens, flag, cpu_batch, budget_s=20.0, dropout=0.0):
 
 
 # ------------------------------------------------------------------------------------------------------------
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: native libraries write there too (NCCL prints its version banner to stdout when the box
+    sets NCCL_DEBUG=VERSION), so fd 1 is pointed at stderr for the run and the result goes to a duplicate of the original fd 1."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -432,7 +455,7 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(kind, lens, flag, cpu_batch, dropout=args.dropout)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -77,8 +77,9 @@ class FusedAdamW(torch.optim.Optimizer):
         all_ps: List[torch.Tensor] = []
         for gi, group in enumerate(self.param_groups):
             all_ps += self._group_tensors(gi, group)
-        if not all_ps:
-            return torch.zeros((), device="cuda")
+        if not all_ps:                                 # no gradients anywhere: norm 0 on the parameters' device, nothing to launch
+            dev = next((p.device for g in self.param_groups for p in g["params"]), torch.device("cpu"))
+            return torch.zeros((), device=dev)
         tab = self._table("clip", all_ps)
         scratch = torch.empty(3, device=all_ps[0].device, dtype=torch.float32)
         check(lib().b200f_grad_clip_coef(ptr(tab.buf), C.c_int32(tab.n_tensors), C.c_int32(tab.n_chunks), C.c_float(max_norm), ptr(scratch), stream_ptr()),

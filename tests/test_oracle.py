@@ -126,3 +126,29 @@ def test_modality_mask_keeps_at_least_one():
     mt, ma, mv = fo.apply_modality_mask(t, a, v, m[:8])
     torch.testing.assert_close(ma, a * m[:8, 1][:, None, None])       # no 1/(1-p) rescale
     torch.testing.assert_close(mt, t * m[:8, 0][:, None])
+
+
+def test_pooled_self_attention_identity_fp64():
+    """Groundwork for the next attention kernel ("Next kernels"): MulT's self-attention outputs are only used through
+    their mean over the sequence (models/fusion_layers.py:161-168), and  mean_q(P V) = (mean_q P) V.  Backward then needs no
+    dO·V^T and no P^T·dO product: with g = d(pooled)/L the same row for every query,  dV = (sum_q P)^T (x) g  is rank one and
+    dP[q, k] = g · V[k]  does not depend on q.  Checked against autograd through the explicit per-query attention, fp64."""
+    torch.manual_seed(5)
+    B, h, L, d = 2, 3, 17, 8
+    q, k, v = (torch.randn(B, h, L, d, dtype=torch.float64, requires_grad=True) for _ in range(3))
+    scale = d ** -0.5
+    P = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)                 # [B,h,L,L]
+    pooled = (P @ v).mean(dim=2)                                                # what the reference computes, then pools
+    pooled_id = P.mean(dim=2, keepdim=True) @ v                                 # column means of P, one vector-matrix product
+    assert float((pooled - pooled_id.squeeze(2)).abs().max()) < 1e-14
+    up = torch.randn_like(pooled)
+    dq, dk, dv = torch.autograd.grad(pooled, (q, k, v), up)
+    with torch.no_grad():
+        g = up / L                                                              # [B,h,d]: dO is this row for every query
+        dv_id = P.sum(dim=2).unsqueeze(-1) * g.unsqueeze(2)                     # (sum_q P)[k] * g   -- rank one per (b, head)
+        dp_row = (v * g.unsqueeze(2)).sum(-1)                                   # [B,h,L_k]: dP[q,k] = g . V[k] for every q
+        delta = (P * dp_row.unsqueeze(2)).sum(-1, keepdim=True)                 # rowsum(P o dP)
+        ds = P * (dp_row.unsqueeze(2) - delta) * scale
+        dq_id, dk_id = ds @ k, ds.transpose(-1, -2) @ q
+    for a, b in ((dv, dv_id), (dq, dq_id), (dk, dk_id)):
+        assert float((a - b).abs().max()) < 1e-13

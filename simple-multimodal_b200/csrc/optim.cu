@@ -8,7 +8,7 @@
 namespace b200f {
 
 struct ChunkRef { int tensor; int start; };        // chunk of OPT_CHUNK elements of tensor `tensor` beginning at element `start`
-static constexpr int OPT_CHUNK = 4096;
+static constexpr int OPT_CHUNK = 4096;             // = 256 threads x 4 vectors x 4 elements (the kernels rely on it)
 
 // sumsq += sum over all gradients of g^2
 __global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* const* __restrict__ grads, const long long* __restrict__ numel,
@@ -22,7 +22,15 @@ __global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* const* __r
   int done = 0;
   if ((reinterpret_cast<uintptr_t>(gc) & 15) == 0) {               // 128-bit loads over the aligned body of the chunk
     const float4* g4 = reinterpret_cast<const float4*>(gc);
-    for (int i = threadIdx.x; i < (len >> 2); i += 256) { const float4 x = g4[i]; acc += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w; }
+    const int nv = len >> 2;
+    float4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = threadIdx.x + u * 256;
+      x[u] = i < nv ? g4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc += x[u].x * x[u].x + x[u].y * x[u].y + x[u].z * x[u].z + x[u].w * x[u].w;
     done = len & ~3;
   }
   for (int i = done + threadIdx.x; i < len; i += 256) { const float x = gc[i]; acc += x * x; }
@@ -73,11 +81,23 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* const* __restrict__ p
     const float4* g4 = reinterpret_cast<const float4*>(g);
     float4* m4 = reinterpret_cast<float4*>(m);
     float4* v4 = reinterpret_cast<float4*>(v);
-    for (int i = threadIdx.x; i < (len >> 2); i += 256) {          // 128-bit loads/stores: 28 B of HBM traffic per element, nothing else
-      const float4 gg = g4[i];
-      float4 pp = p4[i], mm = m4[i], vv = v4[i];
-      update(gg.x, pp.x, mm.x, vv.x); update(gg.y, pp.y, mm.y, vv.y); update(gg.z, pp.z, mm.z, vv.z); update(gg.w, pp.w, mm.w, vv.w);
-      p4[i] = pp; m4[i] = mm; v4[i] = vv;
+    // 128-bit loads/stores: 28 B of HBM traffic per element, nothing else.  A full chunk is 4 vectors per thread: all 16 loads are
+    // issued before the first update so that every thread keeps 256 B in flight
+    const int nv = len >> 2;
+    float4 gg[4], pp[4], mm[4], vv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = threadIdx.x + u * 256;
+      if (i < nv) { gg[u] = g4[i]; pp[u] = p4[i]; mm[u] = m4[i]; vv[u] = v4[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = threadIdx.x + u * 256;
+      if (i < nv) {
+        update(gg[u].x, pp[u].x, mm[u].x, vv[u].x); update(gg[u].y, pp[u].y, mm[u].y, vv[u].y);
+        update(gg[u].z, pp[u].z, mm[u].z, vv[u].z); update(gg[u].w, pp[u].w, mm[u].w, vv[u].w);
+        p4[i] = pp[u]; m4[i] = mm[u]; v4[i] = vv[u];
+      }
     }
     done = len & ~3;
   }

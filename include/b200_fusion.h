@@ -162,6 +162,9 @@ int b200f_concat3_bwd(const void* dcat, const float* mask, void* dt, void* da, v
                       int64_t B, int32_t H, int32_t dtype, void* stream);
 /* x[b, l, :] *= mask[b, col]   in place (modality dropout on [B,L,H] sequences). */
 int b200f_rowmask_apply(void* x, const float* mask, int32_t col, int64_t B, int64_t L, int32_t H, int32_t dtype, void* stream);
+/* dst[b, l, :] = src[b, l, :] * mask[b, col]  out of place; mask NULL = plain copy (the staging pass of the chunk-graph
+ * MulT engine: ModalityDropout's multiply, models/encoders.py:317-319, rides on the copy into the static input buffers). */
+int b200f_rowmask_copy(const void* src, void* dst, const float* mask, int32_t col, int64_t B, int64_t L, int32_t H, int32_t dtype, void* stream);
 /* z = y / max(||y||_2, eps) per row (F.normalize, fusion_layers.py:338-340); norm saved. */
 int b200f_l2norm_fwd(const void* y, void* z, float* norm, int64_t rows, int32_t D, float eps, int32_t dtype, void* stream);
 int b200f_l2norm_bwd(const void* dz, const void* z, const float* norm, void* dy, int64_t rows, int32_t D, float eps,

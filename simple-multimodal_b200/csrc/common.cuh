@@ -122,14 +122,23 @@ __host__ __device__ __forceinline__ bool drop_keep_c(uint32_t row_key, uint32_t 
 __host__ __device__ __forceinline__ bool drop_keep(uint32_t row_key, uint32_t col, uint32_t thr32) {
   return drop_keep_c(row_key, col * kDropColMul, thr32);
 }
-// Dropout epoch: a device-side word XORed into seed_hi by every kernel that generates a mask.  It exists for CUDA graphs:
+// Dropout epoch: a device-side word mixed into the row key by every kernel that generates a mask.  It exists for CUDA graphs:
 // kernel arguments (the seeds) are frozen at capture, so a captured training step starts with a one-thread kernel that
 // advances the epoch -- every replay then draws fresh masks, and forward / backward of one replay still agree.  Eager use
-// leaves it at 0.  The library is built without relocatable device code, so each translation unit holds its own copy and
-// b200f_dropout_epoch() updates all of them (B200F_DEFINE_EPOCH_HOOK).
+// leaves it at 0 (the key is then drop_row_key itself).  The epoch goes through its own avalanche hash and is ADDED to seed_lo,
+// i.e. outside the inner hash that carries the row: XORing it next to the row index (the first version) made replay e's mask of
+// row r equal replay 0's mask of row r ^ e -- a row permutation, not a fresh draw.  The library is built without relocatable
+// device code, so each translation unit holds its own copy and b200f_dropout_epoch() updates all of them
+// (B200F_DEFINE_EPOCH_HOOK).
 static __device__ uint32_t g_drop_epoch = 0;
+__host__ __device__ __forceinline__ uint32_t drop_epoch_mix(uint32_t epoch) {
+  return epoch ? hash32(epoch * 0x9E3779B1u + 0x7F4A7C15u) : 0u;
+}
+__host__ __device__ __forceinline__ uint32_t drop_row_key_at(uint32_t seed_lo, uint32_t seed_hi, uint32_t row, uint32_t epoch) {
+  return drop_row_key(seed_lo + drop_epoch_mix(epoch), seed_hi, row);
+}
 __device__ __forceinline__ uint32_t drop_row_key_e(uint32_t seed_lo, uint32_t seed_hi, uint32_t row) {
-  return drop_row_key(seed_lo, seed_hi ^ g_drop_epoch, row);
+  return drop_row_key_at(seed_lo, seed_hi, row, g_drop_epoch);
 }
 #define B200F_DEFINE_EPOCH_HOOK(name)                                                                         \
   __global__ void name##_epoch_kernel(uint32_t v, int add) { g_drop_epoch = add ? g_drop_epoch + v : v; }      \

@@ -451,6 +451,35 @@ __global__ void rowmask_kernel(T* __restrict__ x, const float* __restrict__ mask
   }
 }
 
+// dst[b, l, :] = src[b, l, :] * mask[b, col]  (mask == nullptr: plain copy).  Staging pass of the chunk-graph MulT engine: the
+// modality-dropout multiply rides on the copy into the static input buffers the captured chunk graphs read.
+template <typename T>
+__global__ void rowmask_copy_kernel(const T* __restrict__ src, T* __restrict__ dst, const float* __restrict__ mask, int col, long long B,
+                                    long long L, int H) {
+  constexpr int VN = Vec16<T>::N;
+  const long long per_b = L * (H / VN);
+  const long long total = B * per_b;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float k = mask ? mask[(i / per_b) * 3 + col] : 1.f;
+    Vec16<T> t;
+    if (k == 0.f) {                       // a dropped modality: nothing to read
+      float z[VN];
+#pragma unroll
+      for (int j = 0; j < VN; ++j) z[j] = 0.f;
+      t.pack(z);
+    } else {
+      t.load(src + i * VN);
+      if (k != 1.f) {
+        float f[VN]; t.unpack(f);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) f[j] *= k;
+        t.pack(f);
+      }
+    }
+    t.store(dst + i * VN);
+  }
+}
+
 // L2 row normalisation: one warp per row.
 template <typename T, int NV>
 __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const T* __restrict__ y, T* __restrict__ z, float* __restrict__ norm_out,
@@ -734,6 +763,18 @@ int b200f_rowmask_apply(void* x, const float* mask, int32_t col, int64_t B, int6
     rowmask_kernel<T><<<ew_grid(B * L * (H / VN), 256), 256, 0, st>>>(static_cast<T*>(x), mask, col, B, L, H);
   })
   return check_launch("rowmask");
+}
+
+int b200f_rowmask_copy(const void* src, void* dst, const float* mask, int32_t col, int64_t B, int64_t L, int32_t H, int32_t dtype, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B == 0 || L == 0) return B200F_OK;
+  B200F_REQUIRE(col >= 0 && col < 3, B200F_ERR_SHAPE, "rowmask_copy: col");
+  DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec16<T>::N;
+    B200F_REQUIRE(H % VN == 0 && aligned16(src) && aligned16(dst), B200F_ERR_ALIGN, "rowmask_copy: alignment");
+    rowmask_copy_kernel<T><<<ew_grid(B * L * (H / VN), 256), 256, 0, st>>>(static_cast<const T*>(src), static_cast<T*>(dst), mask, col, B, L, H);
+  })
+  return check_launch("rowmask_copy");
 }
 
 int b200f_l2norm_fwd(const void* y, void* z, float* norm, int64_t rows, int32_t D, float eps, int32_t dtype, void* stream) {

@@ -477,9 +477,12 @@ __global__ void __launch_bounds__(256) late_bwd_kernel(const T* dfused, const T*
 }
 
 // ------------------------------------------------------------------------------------------------
+// The dropout epoch (common.cuh) is folded into the seed like in dropout_kernel: a mask generated inside a captured training
+// step is therefore re-drawn by every replay (the host-side offset of ModalityDropout.sample_mask is frozen at capture).
 __global__ void modality_mask_kernel(float* mask, long long B, float rate, uint64_t seed, uint64_t offset) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  seed ^= uint64_t(g_drop_epoch) << 32;
   float k[3];
   bool any = false;
 #pragma unroll

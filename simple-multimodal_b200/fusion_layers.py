@@ -182,6 +182,12 @@ class MultimodalTransformer(_FusionBase):
 
     chunk_size = 256            # samples per MulT chunk (~7.4 GB of bf16 activations at L=512/512/30, H=512)
     stash_fraction = 0.72       # share of the currently free device memory that forward may keep resident for backward
+    graph_chunks = True         # bf16 training steps replay captured per-chunk CUDA graphs (mult_engine.ChunkGraphEngine)
+    graph_min_tokens = 16384    # ... when a chunk is big enough for launch overhead to matter (tokens per chunk, all modalities)
+    _engine = None              # the ChunkGraphEngine of the last shape seen (one is kept: its pool holds the activation stash)
+    _engine_key = None
+    _engine_builds = 0
+    _weights = None             # dtype -> mult_engine._Weights (operand copies at static addresses)
 
     def __init__(self, config):
         super().__init__()
@@ -195,22 +201,79 @@ class MultimodalTransformer(_FusionBase):
         self.final_fusion = _mlp_container([3 * H, H], config.fusion_dropout, final_relu=True)
         self._names = mult_engine.param_names()
 
+    def __getstate__(self):                                  # copies / pickles of the module never carry graphs or operand caches
+        state = dict(self.__dict__)
+        state["_engine"], state["_engine_key"], state["_weights"] = None, None, {}
+        return state
+
+    def _operands(self, dt):
+        """the persistent operand copies of the parameters for compute dtype `dt` (rebuilt if the parameters were re-created,
+        e.g. by .to(device))"""
+        params = dict(self.named_parameters())
+        P = {n: params[n] for n in self._names}
+        cache = self.__dict__.setdefault("_weights", {})
+        W = cache.get(dt)
+        if W is None or any(W.P[n] is not P[n] for n in self._names) or W.w_stack[0].device != P[self._names[0]].device:
+            self.release_graphs()
+            W = cache[dt] = mult_engine._Weights(P, self.config.fusion_hidden_size, dt)
+        return W, [P[n] for n in self._names]
+
+    def release_graphs(self) -> None:
+        """free the captured chunk graphs and the activation stash their pool holds"""
+        if self.__dict__.get("_engine") is not None:
+            self._engine.release()
+        self._engine, self._engine_key = None, None
+
+    def _graph_engine(self, W, xs, need_dx, p_drop):
+        """ChunkGraphEngine for this step, or None when the step is issued eagerly: fp32 parity mode, inference, inside an outer
+        CUDA-graph capture, tiny chunks, shapes that keep changing, or too little free memory to keep every chunk's stash."""
+        t = xs[0]
+        if not (self.graph_chunks and t.dtype == torch.bfloat16 and torch.is_grad_enabled() and not torch.cuda.is_current_stream_capturing()):
+            return None
+        B, Ls, chunk = t.size(0), [x.size(1) for x in xs], int(self.chunk_size)
+        if min(B, chunk) * sum(Ls) < self.graph_min_tokens:
+            return None
+        key = (B, tuple(Ls), chunk, t.device, float(p_drop), bool(need_dx), id(W))
+        if self._engine is not None and self._engine_key == key:
+            return self._engine
+        if self._engine_builds >= 4:                     # shapes keep changing: capturing each of them costs more than it saves
+            return None
+        self.release_graphs()
+        H = self.config.fusion_hidden_size
+        torch.cuda.empty_cache()
+        free_bytes, _ = torch.cuda.mem_get_info(t.device)
+        stash = mult_engine.stash_bytes_per_sample(Ls, H, t.element_size())
+        static = (2 if need_dx else 1) * B * sum(Ls) * H * t.element_size()        # masked inputs (+ input gradients)
+        need = B * stash + static + 3 * min(B, chunk) * stash // 2     # + backward temporaries of the chunk in flight
+        if B * stash > self.stash_fraction * free_bytes or need > 0.92 * free_bytes:
+            return None                                      # not every chunk can stay resident: eager issue with recomputed chunks
+        self._engine = mult_engine.ChunkGraphEngine(W, self._names, H, self.config.fusion_num_heads, chunk, B, Ls, t.dtype, t.device,
+                                                    p_drop, need_dx)
+        self._engine_key = key
+        self._engine_builds += 1
+        return self._engine
+
     def _pooled(self, t, a, v, mask):
         if t.dim() == 2:                                     # fusion_layers.py:140-143
             t, a, v = t.unsqueeze(1), a.unsqueeze(1), v.unsqueeze(1)
-        if mask is not None:
-            t, a, v = (ops.RowMaskFn.apply(x, mask, i) for i, x in enumerate((t, a, v)))
-        drop = (self._p, *ops.next_drop_seed()) if (self.training and self._p > 0.0) else None     # one seed pair per call
-        params = dict(self.named_parameters())
+        training_drop = self.training and self._p > 0.0
         H, heads = self.config.fusion_hidden_size, self.config.fusion_num_heads
+        W, plist = self._operands(t.dtype)
+        need_dx = torch.is_grad_enabled() and any(x.requires_grad for x in (t, a, v))
+        engine = self._graph_engine(W, (t, a, v), need_dx, self._p if training_drop else 0.0)
+        drop = None
+        if engine is None and training_drop:
+            drop = (self._p, *ops.next_drop_seed())          # one seed pair per call
         # memory the stash may use: what the driver reports free plus what torch's caching allocator holds but has not handed out
-        if torch.cuda.is_current_stream_capturing():
+        if engine is not None:
+            budget = 0
+        elif torch.cuda.is_current_stream_capturing():
             budget = 1 << 62                                 # CUDA-graph capture: the graph's private pool keeps every chunk anyway
         else:
             free_bytes, _ = torch.cuda.mem_get_info(t.device)
             free_bytes += torch.cuda.memory_reserved(t.device) - torch.cuda.memory_allocated(t.device)
             budget = int(self.stash_fraction * free_bytes) if torch.is_grad_enabled() else 0
-        return mult_engine.MulTFn.apply(t, a, v, H, heads, int(self.chunk_size), budget, drop, self._names, *[params[n] for n in self._names])
+        return mult_engine.MulTFn.apply(t, a, v, mask, H, heads, int(self.chunk_size), budget, drop, self._names, W, engine, *plist)
 
     def forward(self, text_features, audio_features, video_features, mask=None) -> Dict[str, Tensor]:
         (t, a, v), mask, _ = self._prepare((text_features, audio_features, video_features), mask)

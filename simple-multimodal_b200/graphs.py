@@ -25,8 +25,14 @@ class GraphedTrainStep:
     `step.input_grads` the gradients of the inputs; `step.outputs` is the head's output structure (static tensors)."""
 
     def __init__(self, head: torch.nn.Module, example_inputs: Sequence[torch.Tensor], loss_fn: Callable, forward_kwargs: Optional[Dict] = None,
-                 warmup: int = 2):
+                 warmup: int = 2, grad_bucket=None, modality_dropout=None):
+        """`grad_bucket` (ops.GradBucket over the head's parameters): gradients accumulate into its flat buffer, which the
+        captured step zeroes first -- the buffer can then be all-reduced in place after each replay.
+        `modality_dropout` (fusion_layers.ModalityDropout): its keep-mask is sampled INSIDE the captured step and passed to the
+        head as `mask=`; the device-side epoch re-draws it on every replay (a mask tensor passed through `forward_kwargs` is a
+        static buffer instead: refresh it in place before a replay if it should change)."""
         self.head, self.loss_fn, self.kw = head, loss_fn, dict(forward_kwargs or {})
+        self.bucket, self.md = grad_bucket, modality_dropout
         self.static_inputs = [x.detach().clone().requires_grad_(x.requires_grad) for x in example_inputs]
         # parameters that already stepped eagerly keep AccumulateGrad nodes tied to the default stream; capture runs on a side
         # stream on purpose, so torch's advisory about that mismatch does not apply here
@@ -38,21 +44,32 @@ class GraphedTrainStep:
         with torch.cuda.stream(side):                                   # warm-up off the default stream, as torch's capture recipe asks
             for _ in range(warmup):
                 self._clear_grads()
-                self.loss_fn(self.head(*self.static_inputs, **self.kw)).backward()
+                self.loss_fn(self._forward()).backward()
         torch.cuda.current_stream().wait_stream(side)
         self._clear_grads()
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             K.dropout_epoch(1, add=True)
-            self.outputs = self.head(*self.static_inputs, **self.kw)
+            if self.bucket is not None:
+                self.bucket.flat.zero_()
+            self.outputs = self._forward()
             self.loss = self.loss_fn(self.outputs)
             self.loss.backward()
         self.kernel_launches = _lib.launch_count() - n0          # kernels of this library inside the graph = launched by every replay
 
+    def _forward(self):
+        kw = self.kw
+        if self.md is not None:
+            kw = dict(kw, mask=self.md.sample_mask(self.static_inputs[0].size(0), self.static_inputs[0].device))
+        return self.head(*self.static_inputs, **kw)
+
     def _clear_grads(self):
-        for p in self.head.parameters():
-            p.grad = None
+        if self.bucket is not None:
+            self.bucket.zero()
+        else:
+            for p in self.head.parameters():
+                p.grad = None
         for x in self.static_inputs:
             x.grad = None
 

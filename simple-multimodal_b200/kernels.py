@@ -175,9 +175,11 @@ def relu_bwd(dy: Tensor, ref: Tensor) -> Tensor:
     return dx
 
 
-def cast_to_bf16(src: Tensor, scale: float = 1.0) -> Tensor:
+def cast_to_bf16(src: Tensor, scale: float = 1.0, out: Optional[Tensor] = None) -> Tensor:
     src = src.contiguous()
-    dst = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    dst = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16) if out is None else out
+    if dst.dtype != torch.bfloat16 or dst.numel() != src.numel() or not dst.is_contiguous():
+        raise B200FusionError("cast_to_bf16: `out` must be a contiguous bfloat16 tensor of the source's size")
     check(lib().b200f_cast_f32_to_bf16(ptr(src), ptr(dst), C.c_int64(src.numel()), C.c_float(scale), stream_ptr()), "b200f_cast_f32_to_bf16")
     return dst
 
@@ -246,6 +248,18 @@ def rowmask_apply_(x: Tensor, mask: Tensor, col: int) -> Tensor:
     check(lib().b200f_rowmask_apply(ptr(x), ptr(mask), C.c_int32(col), C.c_int64(B), C.c_int64(Lx), C.c_int32(x.size(-1)),
                                     dtype_code(x.dtype), stream_ptr()), "b200f_rowmask_apply")
     return x
+
+
+def rowmask_copy(src: Tensor, dst: Tensor, mask: Optional[Tensor], col: int) -> Tensor:
+    """dst[b, l, :] = src[b, l, :] * mask[b, col] (mask None: plain copy); src/dst contiguous [B,L,H] (or [B,H]) of one dtype."""
+    require_cuda(src, dst, mask)
+    if src.shape != dst.shape or src.dtype != dst.dtype or not src.is_contiguous() or not dst.is_contiguous():
+        raise B200FusionError("rowmask_copy: src/dst must be contiguous tensors of one shape and dtype")
+    B = src.size(0)
+    Lx = 1 if src.dim() == 2 else src.size(1)
+    check(lib().b200f_rowmask_copy(ptr(src), ptr(dst), ptr(mask), C.c_int32(col), C.c_int64(B), C.c_int64(Lx), C.c_int32(src.size(-1)),
+                                   dtype_code(src.dtype), stream_ptr()), "b200f_rowmask_copy")
+    return dst
 
 
 def l2norm_fwd(y: Tensor, eps: float):

@@ -24,6 +24,7 @@ from typing import Dict, List
 import torch
 
 from . import kernels as K
+from ._lib import B200FusionError
 from .ops import LN_EPS, mha_scale, operand
 
 Tensor = torch.Tensor
@@ -62,21 +63,47 @@ def _layout(H: int):
 
 
 class _Weights:
-    """Per-step operand copies (stacked projections, bf16 casts) built once and shared by all chunks."""
+    """Contraction operands of the MulT parameters (stacked projections, bf16 casts) at STATIC addresses, shared by all chunks
+    and all steps.  `refresh()` re-derives them from the fp32 masters only when a parameter changed (tensor version counters,
+    bumped by every in-place optimizer update), so a step whose weights did not move issues no cast kernel and the captured
+    chunk graphs (`ChunkGraphEngine`) keep reading the same buffers."""
 
     def __init__(self, P: Dict[str, Tensor], H: int, dtype: torch.dtype):
-        self.P = P
+        self.P, self.H, self.dtype = P, H, dtype
         self.q_slot, self.kv_slot, self.order = _layout(H)
-        self.w_stack, self.b_stack = [], []
+        dev = next(iter(P.values())).device
+        self.w_stack = [torch.empty((6 * H, H), device=dev, dtype=dtype) for _ in range(3)]
+        self.b_stack = [torch.empty(6 * H, device=dev, dtype=torch.float32) for _ in range(3)]
+        self.op = {k: torch.empty(tuple(v.shape), device=dev, dtype=dtype) for k, v in P.items() if v.dim() == 2}
+        self._key = None
+        self.refresh()
+
+    def _fingerprint(self):
+        return tuple((v.data_ptr(), v._version) for v in self.P.values())
+
+    def refresh(self, force: bool = False) -> None:
+        key = self._fingerprint()
+        if key == self._key and not force:
+            return
+        H, P = self.H, self.P
+
+        def put(dst: Tensor, src: Tensor):
+            if dst.dtype == torch.bfloat16:
+                K.cast_to_bf16(src.detach(), out=dst)
+            else:
+                dst.copy_(src.detach())
+
         for m in range(3):
-            ws, bs = [], []
+            row = 0
             for kind, name in self.order[m]:
-                w, b = P[f"{name}.attention.in_proj_weight"].detach(), P[f"{name}.attention.in_proj_bias"].detach()
-                ws.append(w[:H] if kind == "q" else w[H:])
-                bs.append(b[:H] if kind == "q" else b[H:])
-            self.w_stack.append(operand(torch.cat(ws, 0), dtype))
-            self.b_stack.append(torch.cat(bs, 0).contiguous())
-        self.op = {k: operand(v, dtype) for k, v in P.items() if v.dim() == 2}
+                w, b = P[f"{name}.attention.in_proj_weight"], P[f"{name}.attention.in_proj_bias"]
+                lo, n = (0, H) if kind == "q" else (H, 2 * H)
+                put(self.w_stack[m][row:row + n], w[lo:lo + n])
+                self.b_stack[m][row:row + n].copy_(b.detach()[lo:lo + n])
+                row += n
+        for k, dst in self.op.items():
+            put(dst, P[k])
+        self._key = key
 
     def w(self, name: str) -> Tensor:
         return self.op[name]
@@ -140,9 +167,11 @@ def _chunk_forward(xs, W: _Weights, H: int, heads: int, pooled_out: Tensor, keep
     return st
 
 
-def _chunk_backward(st, W: _Weights, H: int, heads: int, dpooled: Tensor, G: Dict[str, Tensor], dstack_w, dstack_b, need_dx: bool, drop=None):
+def _chunk_backward(st, W: _Weights, H: int, heads: int, dpooled: Tensor, G: Dict[str, Tensor], dstack_w, dstack_b, dx_out, drop=None):
     """Backward of one chunk.  dpooled [Bc,3H]; G: fp32 gradient accumulators keyed like the parameters;
-    dstack_w/dstack_b: accumulators of the stacked projections.  Returns [dx_text, dx_audio, dx_video] or None."""
+    dstack_w/dstack_b: accumulators of the stacked projections; dx_out: None, or the three contiguous [Bc,L,H] slices of the
+    input-gradient buffers this chunk's input gradients are written into (the last dgrad GEMM stores there directly)."""
+    need_dx = dx_out is not None
     scale = mha_scale(H, heads)
     x2, Ls, proj = st["x2"], st["Ls"], st["proj"]
     Bc = dpooled.size(0)
@@ -188,15 +217,13 @@ def _chunk_backward(st, W: _Weights, H: int, heads: int, dpooled: Tensor, G: Dic
         K.attn_bwd(dctx, proj[qm][:, :, qo:qo + H], proj[km][:, :, ko:ko + H], proj[km][:, :, ko + H:ko + 2 * H], s["ctx"], s["lse"],
                    heads, scale, dproj[qm][:, :, qo:qo + H], dproj[km][:, :, ko:ko + H], dproj[km][:, :, ko + H:ko + 2 * H],
                    dbq=dstack_b[qm][qo:qo + H], dbv=dstack_b[km][ko + H:ko + 2 * H], dropout=_site(drop, 2 * bi))
-    dxs = []
     for m in range(3):
         dp2 = dproj[m].view(-1, 6 * H)
         K.linear_wgrad(dp2, x2[m], dstack_w[m])
         if need_dx:
             a_name, b_name = [n for n, qm, _ in BLOCKS if qm == m]
             direct = K.add(d_enh[m], d_s1[a_name], d_s1[b_name])      # residual paths into the input
-            dxs.append(K.linear_dgrad(dp2, W.w_stack[m], residual=direct).view(Bc, Ls[m], H))
-    return dxs if need_dx else None
+            K.linear_dgrad(dp2, W.w_stack[m], residual=direct, out=dx_out[m].view(-1, H))
 
 
 def stash_bytes_per_sample(Ls, H: int, elem: int) -> int:
@@ -216,20 +243,174 @@ def _chunk_drop(drop, ci: int):
     return p, lo, (hi + 0x9E3779B1 * (ci + 1)) & 0xFFFFFFFF
 
 
-class MulTFn(torch.autograd.Function):
-    """(text, audio, video [B,L,H]) + MulT parameters -> pooled attended features [B,3H].
+def _grad_buffers(W: _Weights, names, dev):
+    """fp32 gradient accumulators of every parameter (+ the stacked projections) as views of ONE buffer: one fill kernel
+    instead of ~100; every view starts on a 256-byte boundary (the GEMM / attention epilogues use 16-byte vector REDs)."""
+    shapes = [tuple(W.P[n].shape) for n in names] + [tuple(w.shape) for w in W.w_stack] + [tuple(b.shape) for b in W.b_stack]
+    offs, total = [], 0
+    for shp in shapes:
+        offs.append(total)
+        total += (math.prod(shp) + 63) // 64 * 64
+    flat = torch.empty(total, device=dev, dtype=torch.float32)
+    views = [flat[o:o + math.prod(shp)].view(shp) for o, shp in zip(offs, shapes)]
+    G = dict(zip(names, views[:len(names)]))
+    dstack_w = views[len(names):len(names) + len(W.w_stack)]
+    dstack_b = views[len(names) + len(W.w_stack):]
+    return flat, G, dstack_w, dstack_b
 
-    The batch runs in chunks of `chunk` samples.  Chunks whose activations fit in `stash_budget` bytes stay resident
-    for backward; the remaining chunks are recomputed chunk by chunk in backward (bounded memory at any batch)."""
+
+def _scatter_stacked(W: _Weights, H: int, G, dstack_w, dstack_b) -> None:
+    """the stacked-projection gradients go back onto the blocks' in_proj parameters"""
+    for m in range(3):
+        row = 0
+        for kind, name in W.order[m]:
+            n = H if kind == "q" else 2 * H
+            lo = 0 if kind == "q" else H
+            G[f"{name}.attention.in_proj_weight"][lo:lo + n].copy_(dstack_w[m][row:row + n])
+            G[f"{name}.attention.in_proj_bias"][lo:lo + n].copy_(dstack_b[m][row:row + n])
+            row += n
+
+
+class ChunkGraphEngine:
+    """The MulT step of one (batch, sequence lengths) shape as CUDA graphs: one captured forward and one captured backward PER
+    CHUNK, replayed back to back (reference models/fusion_layers.py:93-179 is per-sample independent, so chunks never interact).
+
+    Why: a chunk's forward + backward is ~150 kernel launches issued from Python (~18 ms of host time), about what the B200
+    needs to execute them; at B = 4096 (16 chunks) the step was issued in ~300 ms for ~330 ms of GPU work, and several ranks on a
+    CPU-limited host made it host-bound.  Replaying 32 graphs costs well under a millisecond of host time per step.
+
+    Everything a graph touches lives at a static address: the (masked) inputs `xs`, the pooled output, `dpooled`, the input
+    gradients `dx`, the fp32 parameter-gradient accumulators, the operand copies of the weights (`_Weights`) and, per chunk, the
+    activation stash its backward graph reads -- the same ~29 MB per sample the eager path keeps, held in the graphs' shared
+    private pool.  Dropout: the per-chunk seeds are frozen in the graphs; the device-side epoch (csrc/common.cuh) is raised by
+    this step's number around the forward replays and around the backward replays (and lowered again afterwards, so eager kernels
+    issued between them see the epoch they started with), giving every step fresh masks that forward and backward agree on.
+
+    One forward may be in flight: a second forward overwrites the static buffers, and the first one's backward then raises."""
+
+    def __init__(self, W: _Weights, names, H: int, heads: int, chunk: int, B: int, Ls, dtype, dev, drop_p: float, need_dx: bool):
+        from .ops import next_drop_seed
+        self.W, self.names, self.H, self.heads, self.chunk, self.B, self.Ls = W, list(names), H, heads, chunk, B, list(Ls)
+        self.need_dx, self.drop_p = need_dx, drop_p
+        self.drop = (drop_p, *next_drop_seed()) if drop_p > 0.0 else None
+        self.bounds = [(b0, min(B, b0 + chunk)) for b0 in range(0, B, chunk)]
+        self.xs = [torch.empty((B, L, H), device=dev, dtype=dtype) for L in Ls]
+        self.dx = [torch.empty_like(x) for x in self.xs] if need_dx else None
+        self.pooled = torch.empty((B, 3 * H), device=dev, dtype=dtype)
+        self.dpooled = torch.zeros((B, 3 * H), device=dev, dtype=dtype)
+        self.flat, self.G, self.dstack_w, self.dstack_b = _grad_buffers(W, names, dev)
+        self.step_no, self.live = 0, None
+        self.kernel_launches = 0
+        self._capture()
+
+    def _fwd(self, ci, keep=True):
+        b0, b1 = self.bounds[ci]
+        return _chunk_forward([x[b0:b1] for x in self.xs], self.W, self.H, self.heads, self.pooled[b0:b1], keep=keep,
+                              drop=_chunk_drop(self.drop, ci))
+
+    def _bwd(self, ci, st):
+        b0, b1 = self.bounds[ci]
+        _chunk_backward(st, self.W, self.H, self.heads, self.dpooled[b0:b1], self.G, self.dstack_w, self.dstack_b,
+                        [d[b0:b1] for d in self.dx] if self.need_dx else None, drop=_chunk_drop(self.drop, ci))
+
+    def _capture(self):
+        from . import _lib
+        for x in self.xs:
+            x.zero_()
+        self.flat.zero_()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                       # every kernel configures itself (opt-in shared memory) on first use:
+            last = len(self.bounds) - 1                     # run the two distinct chunk shapes once outside capture
+            for ci in sorted({0, last}):
+                st = self._fwd(ci)
+                self._bwd(ci, st)
+                del st
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.pool = torch.cuda.graph_pool_handle()
+        self.fwd_graphs, self.bwd_graphs, self.stash = [], [None] * len(self.bounds), []
+        n0 = _lib.launch_count()
+        for ci in range(len(self.bounds)):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
+                st = self._fwd(ci)
+            self.fwd_graphs.append(g)
+            self.stash.append(st)
+        for ci in reversed(range(len(self.bounds))):        # captured in replay order
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
+                self._bwd(ci, self.stash[ci])
+            self.bwd_graphs[ci] = g
+        self.final_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.final_graph, pool=self.pool, capture_error_mode="thread_local"):
+            _scatter_stacked(self.W, self.H, self.G, self.dstack_w, self.dstack_b)
+        self.kernel_launches = _lib.launch_count() - n0     # library kernels replayed by one forward + backward
+        self._views = [self.G[n] for n in self.names]       # held here so that autograd copies (never adopts) them into .grad
+
+    def _epoch(self, delta: int) -> None:
+        if self.drop is not None:
+            K.dropout_epoch(delta & 0xFFFFFFFF, add=True)
+
+    def forward(self, xs, mask) -> Tensor:
+        self.W.refresh()
+        for m in range(3):
+            K.rowmask_copy(xs[m], self.xs[m], mask, m)
+        self.step_no += 1
+        self.live = self.step_no
+        self._epoch(self.step_no)
+        for g in self.fwd_graphs:
+            g.replay()
+        self._epoch(-self.step_no)
+        return self.pooled.clone(), self.step_no
+
+    def backward(self, token: int, dpooled: Tensor, mask):
+        if token != self.live:
+            raise B200FusionError("MulT chunk graphs: the static activation buffers of this forward were overwritten by a later forward "
+                                    "(one forward may be in flight; set MultimodalTransformer.graph_chunks = False for several)")
+        self.dpooled.copy_(dpooled)
+        self.flat.zero_()
+        self._epoch(token)
+        for ci in reversed(range(len(self.bounds))):
+            self.bwd_graphs[ci].replay()
+        self._epoch(-token)
+        self.final_graph.replay()
+        if self.need_dx and mask is not None:
+            for m in range(3):
+                K.rowmask_apply_(self.dx[m], mask, m)
+        return self.dx, self._views
+
+    def release(self) -> None:
+        """drop the graphs and their pool (tens of GB): the engine is unusable afterwards"""
+        self.fwd_graphs = self.bwd_graphs = self.final_graph = self.stash = None
+        self.live = None
+
+
+class MulTFn(torch.autograd.Function):
+    """(text, audio, video [B,L,H]) [+ modality keep-mask [B,3]] + MulT parameters -> pooled attended features [B,3H].
+
+    The modality-dropout multiply (models/encoders.py:317-319) is applied here: on the copy into the engine's static input
+    buffers, or (eager path) by one masked copy; backward masks the input gradients in place.
+    `engine` (a ChunkGraphEngine for exactly this shape) replays captured chunk graphs; without it the batch runs in eagerly
+    issued chunks of `chunk` samples: chunks whose activations fit in `stash_budget` bytes stay resident for backward, the
+    remaining chunks are recomputed chunk by chunk in backward (bounded memory at any batch)."""
 
     @staticmethod
-    def forward(ctx, t, a, v, H, heads, chunk, stash_budget, drop, names, *params):
-        xs = [x.contiguous() for x in (t, a, v)]
-        B = xs[0].size(0)
-        P = dict(zip(names, params))
-        W = _Weights(P, H, xs[0].dtype)
-        pooled = torch.empty((B, 3 * H), device=t.device, dtype=t.dtype)
+    def forward(ctx, t, a, v, mask, H, heads, chunk, stash_budget, drop, names, W, engine, *params):
+        ctx.mask, ctx.engine = mask, engine
         need_grad = any(ctx.needs_input_grad)
+        if engine is not None:
+            pooled, ctx.token = engine.forward([x.contiguous() for x in (t, a, v)], mask)
+            ctx.cfg = (H, heads, chunk, names, drop)
+            return pooled
+        if mask is None:
+            xs = [x.contiguous() for x in (t, a, v)]
+        else:
+            xs = [K.rowmask_copy(x.contiguous(), torch.empty(x.shape, device=x.device, dtype=x.dtype), mask, m) for m, x in enumerate((t, a, v))]
+        B = xs[0].size(0)
+        W.refresh(force=torch.cuda.is_current_stream_capturing())     # inside a captured step the casts must be part of the graph
+        pooled = torch.empty((B, 3 * H), device=t.device, dtype=t.dtype)
         per_chunk = stash_bytes_per_sample([x.size(1) for x in xs], H, xs[0].element_size()) * min(chunk, B)
         n_keep = int(stash_budget // max(per_chunk, 1)) if need_grad else 0
         stash = {}
@@ -246,23 +427,19 @@ class MulTFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dpooled):
         H, heads, chunk, names, drop = ctx.cfg
+        need_dx = any(ctx.needs_input_grad[:3])
+        n_fixed = 12                                   # positional arguments before *params
+        if ctx.engine is not None:
+            dxs, views = ctx.engine.backward(ctx.token, dpooled, ctx.mask)
+            grads = [g if ctx.needs_input_grad[n_fixed + i] else None for i, g in enumerate(views)]
+            dxs = dxs if need_dx else (None, None, None)
+            return (dxs[0], dxs[1], dxs[2], *([None] * (n_fixed - 3)), *grads)
         W, xs = ctx.W, ctx.xs
         B = xs[0].size(0)
         dev = xs[0].device
         dpooled = dpooled.contiguous()
-        # fp32 gradient accumulators of every parameter (+ the stacked projections) as views of ONE zeroed buffer: one fill kernel
-        # instead of ~100; every view starts on a 256-byte boundary (the GEMM / attention epilogues use 16-byte vector REDs)
-        shapes = [tuple(W.P[n].shape) for n in names] + [tuple(w.shape) for w in W.w_stack] + [tuple(b.shape) for b in W.b_stack]
-        offs, total = [], 0
-        for shp in shapes:
-            offs.append(total)
-            total += (math.prod(shp) + 63) // 64 * 64
-        flat = torch.zeros(total, device=dev, dtype=torch.float32)
-        views = [flat[o:o + math.prod(shp)].view(shp) for o, shp in zip(offs, shapes)]
-        G = dict(zip(names, views[:len(names)]))
-        dstack_w = views[len(names):len(names) + len(W.w_stack)]
-        dstack_b = views[len(names) + len(W.w_stack):]
-        need_dx = any(ctx.needs_input_grad[:3])
+        flat, G, dstack_w, dstack_b = _grad_buffers(W, names, dev)
+        flat.zero_()
         dxs = [torch.empty_like(x) for x in xs] if need_dx else None
         scratch = None
         for b0 in reversed(range(0, B, chunk)):        # recomputed (late) chunks first, then the resident ones are released in turn
@@ -272,22 +449,14 @@ class MulTFn(torch.autograd.Function):
                 if scratch is None:
                     scratch = torch.empty((min(chunk, B), 3 * H), device=dev, dtype=xs[0].dtype)
                 st = _chunk_forward([x[b0:b1] for x in xs], W, H, heads, scratch[:b1 - b0], keep=True, drop=_chunk_drop(drop, b0 // chunk))
-            out = _chunk_backward(st, W, H, heads, dpooled[b0:b1], G, dstack_w, dstack_b, need_dx, drop=_chunk_drop(drop, b0 // chunk))
-            if need_dx:
-                for m in range(3):
-                    dxs[m][b0:b1].copy_(out[m])
-            del st, out
-        ctx.stash = None
-        # scatter the stacked-projection gradients back onto the blocks' in_proj parameters
-        for m in range(3):
-            row = 0
-            for kind, name in W.order[m]:
-                n = H if kind == "q" else 2 * H
-                dst_w, dst_b = G[f"{name}.attention.in_proj_weight"], G[f"{name}.attention.in_proj_bias"]
-                lo = 0 if kind == "q" else H
-                dst_w[lo:lo + n].copy_(dstack_w[m][row:row + n])
-                dst_b[lo:lo + n].copy_(dstack_b[m][row:row + n])
-                row += n
-        grads = [G[n] if ctx.needs_input_grad[9 + i] else None for i, n in enumerate(names)]
-        return (dxs[0] if need_dx else None, dxs[1] if need_dx else None, dxs[2] if need_dx else None,
-                None, None, None, None, None, None, *grads)
+            _chunk_backward(st, W, H, heads, dpooled[b0:b1], G, dstack_w, dstack_b, [d[b0:b1] for d in dxs] if need_dx else None,
+                            drop=_chunk_drop(drop, b0 // chunk))
+            del st
+        ctx.stash = {}
+        _scatter_stacked(W, H, G, dstack_w, dstack_b)
+        if need_dx and ctx.mask is not None:
+            for m in range(3):
+                K.rowmask_apply_(dxs[m], ctx.mask, m)
+        grads = [G[n] if ctx.needs_input_grad[n_fixed + i] else None for i, n in enumerate(names)]
+        dxs = dxs if need_dx else (None, None, None)
+        return (dxs[0], dxs[1], dxs[2], *([None] * (n_fixed - 3)), *grads)

@@ -82,6 +82,20 @@ class _DropoutState:
     """Counter-based dropout stream: (seed, running offset) so forward/backward regenerate the same mask."""
     seed = 0x5EED
     offset = 0
+    per_rank = True       # fold the data-parallel rank into the seed (every rank draws its own masks, like per-rank torch RNG)
+
+
+def _rank_seed() -> int:
+    """The package seed of THIS rank: with a default process group initialised, rank r uses seed ^ splitmix(r), so
+    data-parallel replicas do not share dropout masks (`manual_seed(s)` on every rank still gives distinct streams)."""
+    s = _DropoutState.seed
+    if _DropoutState.per_rank and dist.is_available() and dist.is_initialized():
+        r = dist.get_rank()
+        if r:
+            z = (r * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+            s ^= (z ^ (z >> 27)) & 0x7FFFFFFFFFFFFFFF
+    return s
 
 
 def dropout(x: Tensor, p: float, training: bool) -> Tensor:
@@ -89,11 +103,11 @@ def dropout(x: Tensor, p: float, training: bool) -> Tensor:
         return x
     off = _DropoutState.offset
     _DropoutState.offset += x.numel()
-    return DropoutFn.apply(x, p, _DropoutState.seed, off)
+    return DropoutFn.apply(x, p, _rank_seed(), off)
 
 
-def manual_seed(seed: int) -> None:
-    _DropoutState.seed, _DropoutState.offset = int(seed), 0
+def manual_seed(seed: int, per_rank: bool = True) -> None:
+    _DropoutState.seed, _DropoutState.offset, _DropoutState.per_rank = int(seed), 0, bool(per_rank)
 
 
 def next_drop_seed():
@@ -101,7 +115,7 @@ def next_drop_seed():
     attention weights): splitmix64 of the running offset under the package seed.  The pair fully determines the mask, so
     backward (and the recomputed forward of MulT chunks) regenerate it instead of storing it."""
     _DropoutState.offset += 1
-    z = (_DropoutState.seed * 0x9E3779B97F4A7C15 + _DropoutState.offset * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = (_rank_seed() * 0x9E3779B97F4A7C15 + _DropoutState.offset * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
     z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
     z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
     z ^= z >> 31
@@ -379,26 +393,88 @@ class InfoNCE3Fn(torch.autograd.Function):
         return dz[0], dz[1], dz[2], None, None
 
 
-def allreduce_gradients(params, group=None, bucket_bytes: int = 256 << 20) -> None:
-    """One bucketed SUM all-reduce of the parameter gradients per step.  Losses on the path are
-    normalised by the GLOBAL batch, so the sum over ranks is the exact full-batch gradient."""
+def global_batch_scale(group=None) -> float:
+    """1 / world_size: the factor that turns a LOCAL-mean loss (the reference trainer's CrossEntropy / MSE terms,
+    training/advanced_trainer.py:136-150, or `SmoothedCrossEntropy`) into this rank's share of the GLOBAL-mean loss.
+    Contract of `allreduce_gradients` / `GradBucket.all_reduce`: gradients are SUMMED over ranks, so every loss term must be
+    normalised by the global batch before `backward()`.  InfoNCE3Fn already is (its negatives and its 1/B span the global
+    batch); multiply every other term by this factor, or pass `scale=` to the all-reduce when NO InfoNCE term is present."""
+    return 1.0 / _world(group)[0]
+
+
+class GradBucket:
+    """All parameter gradients of a module in ONE flat fp32 buffer, `p.grad` being views of it (the layout DDP calls
+    gradient_as_bucket_view): autograd accumulates into the views, `zero()` is one fill kernel, `all_reduce()` is one NCCL call on
+    the buffer in place -- no torch.cat, no per-tensor copy back -- and a fused optimizer sees one contiguous range.  Every
+    parameter has a slot whether or not it received a gradient this step, so the buffer layout is identical on every rank."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise B200FusionError("GradBucket: no parameter requires a gradient")
+        dev = self.params[0].device
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + 63) // 64 * 64            # 256-byte aligned slots
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.views = [self.flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, self.params)]
+        self.attach()
+
+    def attach(self) -> None:
+        """(re)install the views as .grad -- after `optimizer.zero_grad(set_to_none=True)` or `p.grad = None`"""
+        for p, v in zip(self.params, self.views):
+            if p.grad is not v:
+                p.grad = v
+
+    def zero(self) -> None:
+        self.attach()
+        self.flat.zero_()
+
+    def all_reduce(self, group=None, scale: Optional[float] = None, async_op: bool = False):
+        world, _ = _world(group)
+        if scale is not None and scale != 1.0:
+            self.flat.mul_(scale)
+        if world == 1:
+            return None
+        return dist.all_reduce(self.flat, group=group, async_op=async_op)
+
+
+def allreduce_gradients(params, group=None, bucket_bytes: int = 256 << 20, scale: Optional[float] = None) -> None:
+    """One bucketed SUM all-reduce of the parameter gradients per step, for gradients that live in separate
+    tensors (see GradBucket for the copy-free layout).  SUM, not mean: every loss term must already be normalised by the GLOBAL
+    batch (see `global_batch_scale`); `scale` multiplies the reduced gradients (1/world turns the sum into a mean when all loss
+    terms are local means).  A parameter without a gradient on this rank contributes zeros, so all ranks reduce buffers of
+    one layout (ranks with different `None` sets would otherwise mismatch or hang)."""
     world, _ = _world(group)
+    params = [p for p in params if p.requires_grad]
     if world == 1:
+        if scale is not None and scale != 1.0:
+            for p in params:
+                if p.grad is not None:
+                    p.grad.mul_(scale)
         return
-    grads = [p.grad for p in params if p.grad is not None]
     bucket, size = [], 0
+
     def flush():
         if not bucket:
             return
-        flat = torch.cat([g.reshape(-1) for g in bucket])
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p, dtype=torch.float32)).reshape(-1).float() for p in bucket])
         dist.all_reduce(flat, group=group)
+        if scale is not None and scale != 1.0:
+            flat.mul_(scale)
         o = 0
-        for g in bucket:
-            g.copy_(flat[o:o + g.numel()].view_as(g))
-            o += g.numel()
-    for g in grads:
-        bucket.append(g)
-        size += g.numel() * g.element_size()
+        for p in bucket:
+            g = flat[o:o + p.numel()].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            o += p.numel()
+
+    for p in params:
+        bucket.append(p)
+        size += p.numel() * 4
         if size >= bucket_bytes:
             flush()
             bucket, size = [], 0

@@ -34,7 +34,10 @@ class _Table:
         head = torch.tensor(ptrs + numel, dtype=torch.int64)
         tail = torch.tensor(chunks, dtype=torch.int32).reshape(-1)
         host = torch.cat([head.view(torch.uint8), tail.view(torch.uint8)])
-        self.buf = host.to(device)                       # one small H2D copy per (re)build
+        if torch.cuda.is_available():
+            host = host.pin_memory()                     # staged from pinned memory: the copy below does not block the host
+        self.buf = host.to(device, non_blocking=True)    # one small H2D copy per (re)build (stream-ordered before the kernels)
+        self._host = host                                # keeps the pinned staging buffer alive until the copy has run
         self.n_tensors, self.n_chunks = T, len(chunks)
         self.key = tuple(ptrs)
 
@@ -53,6 +56,8 @@ class FusedAdamW(torch.optim.Optimizer):
             if not p.is_contiguous() or not p.grad.is_contiguous():
                 raise B200FusionError("FusedAdamW: parameters and gradients must be contiguous")
             st = self.state[p]
+            if st and torch.is_tensor(st.get("step")):          # an optimizer_state_dict saved by torch.optim.AdamW (the reference
+                st["step"] = int(st["step"].item())             # trainer checkpoints it) keeps `step` as a tensor: normalise once
             if not st:
                 st["step"] = 0
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
@@ -107,6 +112,9 @@ class FusedAdamW(torch.optim.Optimizer):
                 tab = self._table((gi, si), ps)
                 for p in ps:
                     self.state[p]["step"] = s_prev + 1
+                    # the kernel writes the parameter through its raw pointer: tell autograd / the operand caches keyed on the
+                    # tensor version (mult_engine._Weights) that its contents changed
+                    torch.autograd.graph.increment_version(p)
                 check(lib().b200f_adamw_step(ptr(tab.buf), C.c_int32(tab.n_tensors), C.c_int32(tab.n_chunks), ptr(coef), C.c_double(group["lr"]),
                                              C.c_double(b1), C.c_double(b2), C.c_double(group["eps"]), C.c_double(group["weight_decay"]),
                                              C.c_int64(s_prev + 1), stream_ptr()), "b200f_adamw_step")

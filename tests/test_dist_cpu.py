@@ -63,10 +63,25 @@ def _worker(rank, port, Bl, D, tau, ret):
         params = [torch.nn.Parameter(torch.full((n,), float(rank + 1))) for n in (3, 1000, 17, 5)]
         for p in params:
             p.grad = torch.arange(p.numel(), dtype=torch.float32) * (rank + 1)
-        params.append(torch.nn.Parameter(torch.zeros(2)))               # no grad: must be skipped
+        params.append(torch.nn.Parameter(torch.zeros(2)))               # no grad on either rank: zero-filled slot
+        lonely = torch.nn.Parameter(torch.zeros(6))                     # a gradient on rank 1 only: rank 0 contributes zeros, so
+        if rank == 1:                                                   # both ranks reduce buffers of one layout (no mismatch / hang)
+            lonely.grad = torch.full((6,), 7.0)
+        params.append(lonely)
+        params.append(torch.nn.Parameter(torch.zeros(3), requires_grad=False))      # frozen: not part of the exchange at all
         ops.allreduce_gradients(params, bucket_bytes=2048)
+        # GradBucket: the gradients live in one flat buffer, all-reduced in place
+        bp = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 130, 64)]
+        bucket = ops.GradBucket(bp)
+        bucket.zero()
+        for i, q in enumerate(bp):
+            (q * float((rank + 1) * (i + 1))).sum().backward()           # autograd accumulates into the views
+        same_storage = all(q.grad.untyped_storage().data_ptr() == bucket.flat.untyped_storage().data_ptr() for q in bp)
+        bucket.all_reduce(scale=ops.global_batch_scale())
+        seeds = (ops.next_drop_seed(), ops._rank_seed())
         ret[rank] = dict(losses=[float(l.detach()) for l in losses], dz=[t.grad.clone() for t in z], zg=zg,
-                         grads=[p.grad.clone() for p in params[:-1]], none_grad=params[-1].grad is None)
+                         grads=[p.grad.clone() for p in params[:4]], none_grad=params[4].grad.clone(), lonely=lonely.grad.clone(),
+                         frozen=params[-1].grad is None, bucket=[q.grad.clone() for q in bp], same_storage=same_storage, seeds=seeds)
     finally:
         dist.destroy_process_group()
 
@@ -94,7 +109,12 @@ def test_infonce_global_negatives_two_ranks_gloo(Bl, D):
             assert float((res[r]["dz"][m] - want).abs().max()) < 1e-6 * float(want.abs().max())   # dz accumulates in fp32 by design
         for n, gr in zip((3, 1000, 17, 5), res[r]["grads"]):
             assert torch.equal(gr, torch.arange(n, dtype=torch.float32) * 3.0)      # (1 + 2) * arange: SUM over ranks
-        assert res[r]["none_grad"]
+        assert torch.equal(res[r]["none_grad"], torch.zeros(2)) and res[r]["frozen"]
+        assert torch.equal(res[r]["lonely"], torch.full((6,), 7.0))
+        assert res[r]["same_storage"]
+        for i, gr in enumerate(res[r]["bucket"]):                                    # (1 + 2) * (i + 1) summed, times 1/world
+            assert torch.equal(gr, torch.full_like(gr, 3.0 * (i + 1) / WORLD))
+    assert res[0]["seeds"] != res[1]["seeds"]                                        # every rank draws its own dropout masks
 
 
 def test_single_process_is_identity():
@@ -106,3 +126,14 @@ def test_single_process_is_identity():
     p.grad = torch.ones(3)
     pkg.ops.allreduce_gradients([p])
     assert torch.equal(p.grad, torch.ones(3))
+    pkg.ops.allreduce_gradients([p], scale=0.5)
+    assert torch.equal(p.grad, torch.full((3,), 0.5))
+    assert pkg.ops.global_batch_scale() == 1.0
+    b = pkg.ops.GradBucket([p])                       # adopts the parameter: .grad becomes a view of the flat buffer
+    b.zero()
+    (p * 2.0).sum().backward()
+    b.all_reduce()
+    assert torch.equal(p.grad, torch.full((3,), 2.0)) and torch.equal(b.flat[:3], p.grad)
+    p.grad = None
+    b.zero()                                          # re-attaches after zero_grad(set_to_none=True)
+    assert p.grad is b.views[0]

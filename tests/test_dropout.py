@@ -24,9 +24,15 @@ def hash32(x):
     return x
 
 
-def row_key(lo, hi, rows):
+def epoch_mix(epoch):
+    """drop_epoch_mix: 0 for the eager default epoch 0, else an avalanche hash of the epoch (added to seed_lo)"""
+    return 0 if epoch == 0 else int(hash32((epoch * 0x9E3779B1 + 0x7F4A7C15) & 0xFFFFFFFF))
+
+
+def row_key(lo, hi, rows, epoch=0):
     rows = np.asarray(rows, dtype=np.uint64) & M32
-    return hash32((np.uint64(lo) + hash32(np.uint64(hi) ^ rows)) & M32)
+    lo = np.uint64((int(lo) + epoch_mix(epoch)) & 0xFFFFFFFF)
+    return hash32((lo + hash32(np.uint64(hi) ^ rows)) & M32)
 
 
 def threshold(p):
@@ -34,9 +40,9 @@ def threshold(p):
     return 0 if t <= 0 else min(int(t), 4294967295)
 
 
-def keep_mask(lo, hi, rows, cols, p):
+def keep_mask(lo, hi, rows, cols, p, epoch=0):
     """[len(rows), len(cols)] bool: element kept"""
-    rk = row_key(lo, hi, rows)[:, None]
+    rk = row_key(lo, hi, rows, epoch)[:, None]
     cm = (np.asarray(cols, dtype=np.uint64) * np.uint64(0x9E3779B1)) & M32
     h = ((rk ^ cm[None, :]) * np.uint64(0x85EBCA6B)) & M32
     return h >= np.uint64(threshold(p))
@@ -60,6 +66,23 @@ def test_mask_rate_and_independence(p):
         assert abs((a * b).mean() / var) < 5 / math.sqrt(a.size)                              # neighbours uncorrelated
     other = keep_mask(0x1234ABCE, 0x9876FEDC, np.arange(4096), np.arange(512), p).astype(np.float64)
     assert abs(((other - other.mean()) * c).mean() / var) < 5 / math.sqrt(n)                 # a new seed is a new mask
+
+
+def test_epochs_are_fresh_masks_not_row_permutations():
+    """CUDA-graph replays advance the device-side epoch 1, 2, 3 ...: the masks of two replays must be independent draws.  (The
+    first version XORed the epoch next to the row index, so replay e's row r was replay 0's row r ^ e.)"""
+    rows, cols, p = np.arange(1024), np.arange(256), 0.3
+    base = keep_mask(0xC0FFEE, 0x51DE, rows, cols, p, epoch=0)
+    sigs0 = {m.tobytes() for m in base}
+    var = p * (1 - p)
+    for e in (1, 2, 3, 7):
+        m = keep_mask(0xC0FFEE, 0x51DE, rows, cols, p, epoch=e)
+        assert abs(m.mean() - (1 - p)) < 4 * math.sqrt(var / m.size)
+        assert not any(r.tobytes() in sigs0 for r in m)                                       # no row of epoch e is a row of epoch 0
+        c = ((m - m.mean()) * (base - base.mean())).mean() / var
+        assert abs(c) < 5 / math.sqrt(m.size)                                                 # and the draws are uncorrelated
+        prev = keep_mask(0xC0FFEE, 0x51DE, rows, cols, p, epoch=e + 1)
+        assert not any(r.tobytes() in {x.tobytes() for x in m} for r in prev)                 # consecutive epochs too
 
 
 def test_seed_stream_is_reproducible():
@@ -239,3 +262,46 @@ def test_every_head_trains_with_reference_default_dropout():
     assert all(p_.grad is not None and torch.isfinite(p_.grad).all() for p_ in head.parameters())
     # the dropped adaptive attention weights still average to rows of mean ~1 (inverted dropout is unbiased)
     assert abs(float(out["attention_weights"].sum(-1).mean()) - 1.0) < 0.2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 8, 300, 200), (3, 8, 512, 30), (3, 8, 30, 512)])
+def test_attention_dropout_mask_at_nonzero_epoch(shape):
+    """the kernels fold the device-side epoch exactly as `row_key(..., epoch)` restates it (forward and backward agree)"""
+    B, heads, Lq, Lk = shape
+    W, p, lo, hi = heads * 64, 0.25, 0x13579BDF, 0x2468ACE0
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q, k, v, do = (torch.randn(B, L, W, device="cuda", generator=g).to(torch.bfloat16) for L in (Lq, Lk, Lk, Lq))
+    try:
+        K.dropout_epoch(5)
+        o, lse = K.attn_fwd(q, k, v, heads, 0.125, dropout=(p, lo, hi))
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        K.attn_bwd(do, q, k, v, o, lse, heads, 0.125, dq, dk, dv, dropout=(p, lo, hi))
+        torch.cuda.synchronize()
+    finally:
+        K.dropout_epoch(0)
+    mask = torch.from_numpy(keep_mask(lo, hi, np.arange(B * heads * Lq), np.arange(Lk), p, epoch=5)).view(B, heads, Lq, Lk).double()
+    qd, kd, vd = (t.detach().double().cpu().requires_grad_(True) for t in (q, k, v))
+    split = lambda t, L: t.view(B, L, heads, 64).transpose(1, 2)
+    s_ = split(qd, Lq) @ split(kd, Lk).transpose(-1, -2) * 0.125
+    pd = torch.softmax(s_, -1) * mask * inv_keep(p)
+    o_ref = (pd @ split(vd, Lk)).transpose(1, 2).reshape(B, Lq, W)
+    (o_ref * do.double().cpu()).sum().backward()
+    assert rel(o, o_ref) < 2e-2
+    assert rel(dq, qd.grad) < 2e-2 and rel(dk, kd.grad) < 2e-2 and rel(dv, vd.grad) < 2e-2
+
+
+@pytest.mark.gpu
+def test_modality_mask_follows_the_epoch():
+    """ModalityDropout.sample_mask inside a captured step: the host offset is frozen, the device epoch re-draws the mask"""
+    try:
+        K.dropout_epoch(0)
+        a = K.modality_mask(4096, 0.3, 99, 0, "cuda")
+        K.dropout_epoch(1)
+        b = K.modality_mask(4096, 0.3, 99, 0, "cuda")
+        K.dropout_epoch(0)
+        c = K.modality_mask(4096, 0.3, 99, 0, "cuda")
+    finally:
+        K.dropout_epoch(0)
+    assert torch.equal(a, c) and not torch.equal(a, b)
+    assert float(b.sum(1).min()) >= 1.0 and abs(float(b.mean()) - 0.7) < 0.05

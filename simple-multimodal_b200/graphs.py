@@ -33,6 +33,10 @@ class GraphedTrainStep:
         static buffer instead: refresh it in place before a replay if it should change)."""
         self.head, self.loss_fn, self.kw = head, loss_fn, dict(forward_kwargs or {})
         self.bucket, self.md = grad_bucket, modality_dropout
+        for m in head.modules():                                        # the whole step becomes one graph: per-chunk graphs inside the
+            if hasattr(m, "release_graphs"):                            # head (mult_engine.ChunkGraphEngine) would only hold memory
+                m.graph_chunks = False
+                m.release_graphs()
         self.static_inputs = [x.detach().clone().requires_grad_(x.requires_grad) for x in example_inputs]
         # parameters that already stepped eagerly keep AccumulateGrad nodes tied to the default stream; capture runs on a side
         # stream on purpose, so torch's advisory about that mismatch does not apply here

@@ -73,6 +73,8 @@ import os
 
 _FLOOR_PATH = os.path.join(os.path.dirname(__file__), "golden", "bf16_floor.json")
 BF16_FLOOR = json.load(open(_FLOOR_PATH)) if os.path.exists(_FLOOR_PATH) else {}
+GRAD_CAP = 0.10       # no bf16 gradient tensor may be further than 10 % (norm-wise) from the fp64 oracle, whatever the reference's own
+                      # bf16 deviation is; the measured errors of every tensor are in profiles/r02_bf16_parity_errors.json
 ZERO_FLOOR = 1e-4     # a gradient tensor whose oracle norm is < 1e-4 of the largest one is "numerically zero":
                       # its error is measured against that floor instead of its own (cancellation-level) norm
 
@@ -92,7 +94,8 @@ def compare(kind, cfg, B, lens, dtype, flag=False, mask=None, chunk=None, seed=7
     """Run the CUDA head and the fp64 oracle on identical data and check every tensor.
     fp32: 1e-5 norm-wise everywhere.  bf16: outputs 2e-2, losses 1e-3 (north_star); gradients 2e-2 or, where the
     reference's OWN bf16 autocast execution deviates more than 1e-2 from fp64 (tests/golden/bf16_floor.json, made by
-    oracle/make_bf16_floor.py), within 2x of that measured floor."""
+    oracle/make_bf16_floor.py), within 2x of that measured floor and never more than GRAD_CAP = 10 %.  Tensors whose oracle
+    norm is cancellation-level (< ZERO_FLOOR of the group's largest) are measured against that floor, not their own norm."""
     P = fo.init_params(kind, H=cfg.fusion_hidden_size, heads=cfg.fusion_num_heads, graph_hidden=cfg.graph_hidden_size,
                        graph_layers=cfg.graph_num_layers, seed=seed)
     feats = fo.synthetic_features(B, lens, H=cfg.fusion_hidden_size, seed=1234)
@@ -133,7 +136,12 @@ def compare(kind, cfg, B, lens, dtype, flag=False, mask=None, chunk=None, seed=7
             # reference-autocast deviation among tensors with the same role (same trailing name) as this tensor's floor
             role = ".".join(k.split(".")[-2:])
             fl = max([v for n, v in floor.items() if n.endswith(role) and n.split(".")[0] == k.split(".")[0]] + [0.0])
-            limits[k] = max(tol["rel"], 2.0 * min(fl, 0.25))
+            limits[k] = max(tol["rel"], min(2.0 * fl, GRAD_CAP))
+    table = os.environ.get("B200F_PARITY_TABLE")              # optional dump of every measured error next to its limit (JSON lines)
+    if table:
+        with open(table, "a") as f:
+            f.write(json.dumps({"case": case_id, "kind": kind, "dtype": str(dtype).replace("torch.", ""),
+                                "errors": {k: [float(v), float(limits[k])] for k, v in errs.items()}}) + "\n")
     bad = {k: (v, limits[k]) for k, v in errs.items() if not v <= limits[k]}
     worst = dict(sorted(((k, round(v / limits[k], 3)) for k, v in errs.items()), key=lambda kv: -kv[1])[:8])
     assert not bad, f"{kind} {dtype}: {len(bad)} tensors out of tolerance (err, limit): {dict(list(bad.items())[:10])}; worst err/limit: {worst}"

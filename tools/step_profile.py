@@ -31,6 +31,9 @@ torch.manual_seed(0)
 head = getattr(pkg.fusion_layers, {"mult": "MultimodalTransformer", "hierarchical": "HierarchicalFusion",
                                    "contrastive": "ContrastiveFusion", "early": "EarlyFusion"}[kind])(bench.Cfg).to(dev)
 head.train()
+mt = head.mult_fusion if kind == "hierarchical" else (head if kind == "mult" else None)
+if mt is not None:
+    mt.graph_chunks = False          # events cannot be recorded inside replayed chunk graphs: this tool profiles the eagerly issued step
 shapes = [(batch, bench.H)] * 3 if lens is None else [(batch, Ln, bench.H) for Ln in lens]
 xs = [torch.randn(s, device=dev).to(torch.bfloat16).requires_grad_(True) for s in shapes]
 kw = {"compute_contrastive_loss": flag} if kind in ("contrastive", "hierarchical") else {}

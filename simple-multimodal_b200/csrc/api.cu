@@ -44,6 +44,8 @@ extern int g_attn_fwd_variant;
 extern int g_attn_bwd_variant;
 extern int g_infonce_variant;
 void attn_tc_epoch(uint32_t v, int add, cudaStream_t st);
+void attn_narrow_epoch(uint32_t v, int add, cudaStream_t st);
+extern int g_attn_narrow;
 void attn_simt_epoch(uint32_t v, int add, cudaStream_t st);
 void gemm_tc_epoch(uint32_t v, int add, cudaStream_t st);
 void smallops_epoch(uint32_t v, int add, cudaStream_t st);
@@ -94,6 +96,7 @@ int b200f_gemm(const b200f_gemm_args* a, void* stream) {
 int b200f_dropout_epoch(uint32_t value, int32_t add, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   b200f::attn_tc_epoch(value, add, st);
+  b200f::attn_narrow_epoch(value, add, st);
   b200f::attn_simt_epoch(value, add, st);
   b200f::gemm_tc_epoch(value, add, st);
   b200f::smallops_epoch(value, add, st);
@@ -113,6 +116,7 @@ int b200f_debug_set(int key, unsigned value) {
     case 7: b200f::g_dbg_six_stages = value != 0; break;
     case 8: b200f::g_dbg_no_tma_store = value != 0; break;
     case 9: b200f::g_dbg_no_ln_tma = value != 0; break;
+    case 10: b200f::g_attn_narrow = int(value); break;
     default: return b200f::fail(B200F_ERR_UNSUPPORTED, "unknown debug key %d", key);
   }
   return B200F_OK;
@@ -125,6 +129,9 @@ int attn_fwd_simt_dispatch(const b200f_attn_args& a, cudaStream_t st);
 int attn_bwd_simt_dispatch(const b200f_attn_args& a, cudaStream_t st);
 int attn_fwd_tc(const b200f_attn_args& a, cudaStream_t st);
 int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st);
+int attn_narrow_kind(const b200f_attn_args& a);
+int attn_fwd_narrow(const b200f_attn_args& a, cudaStream_t st);
+int attn_bwd_narrow(const b200f_attn_args& a, cudaStream_t st);
 bool g_force_simt_attention = false;
 
 static int attn_check(const b200f_attn_args* a) {
@@ -143,7 +150,8 @@ int b200f_attn_fwd(const b200f_attn_args* a, void* stream) {
   int rc = b200f::attn_check(a);
   if (rc || a->B == 0) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->dtype == B200F_BF16 && a->D == 64 && !b200f::g_force_simt_attention) return b200f::attn_fwd_tc(*a, st);
+  if (a->dtype == B200F_BF16 && a->D == 64 && !b200f::g_force_simt_attention)      // one side <= 32 rows: the HBM-bound narrow kernels
+    return b200f::attn_narrow_kind(*a) ? b200f::attn_fwd_narrow(*a, st) : b200f::attn_fwd_tc(*a, st);
   return b200f::attn_fwd_simt_dispatch(*a, st);
 }
 
@@ -152,6 +160,7 @@ int b200f_attn_bwd(const b200f_attn_args* a, void* stream) {
   if (rc || a->B == 0) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool tc = a->dtype == B200F_BF16 && a->D == 64 && !b200f::g_force_simt_attention;
+  if (tc && b200f::attn_narrow_kind(*a)) return b200f::attn_bwd_narrow(*a, st);    // sums the bias gradients itself
   rc = tc ? b200f::attn_bwd_tc(*a, st) : b200f::attn_bwd_simt_dispatch(*a, st);
   if (rc || (tc && b200f::g_attn_bwd_variant == 0)) return rc;      // the persistent tcgen05 kernels sum the bias gradients in their epilogue
   const int64_t W = (int64_t)a->H * a->D;

@@ -45,9 +45,11 @@ def tc_variant(request):
     lib = pkg._lib.lib()
     lib.b200f_debug_set(4, 2 if request.param == 0 else 1)
     lib.b200f_debug_set(5, request.param)
+    lib.b200f_debug_set(10, 0)          # shapes with a narrow side stay on the tcgen05 tiles here (test_narrow_attention covers attn_narrow.cu)
     yield request.param
     lib.b200f_debug_set(4, 0)
     lib.b200f_debug_set(5, 0)
+    lib.b200f_debug_set(10, 1)
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
@@ -83,6 +85,56 @@ def test_attention_forward_backward(shape, dtype, tc_variant):
     for acc, grad in ((db[0], dpq[:, :, W:]), (db[1], dpkv[:, :, :W]), (db[2], dpkv[:, :, 2 * W:])):
         want = grad.double().sum(dim=(0, 1)) + 1.0
         assert float((acc.double() - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max())) + 1e-3 * float(grad.float().abs().max())
+
+
+NARROW_SHAPES = [(3, 8, 512, 30), (3, 8, 30, 512), (2, 8, 1, 1), (150, 8, 30, 30), (2, 8, 200, 7), (2, 8, 7, 200), (2, 8, 33, 32), (2, 8, 32, 33),
+                 (4, 8, 130, 30), (4, 8, 30, 130), (2, 8, 64, 1), (2, 8, 1, 64), (2, 8, 17, 1000), (2, 8, 1000, 17), (40, 8, 512, 30), (40, 8, 30, 512),
+                 (1, 1, 5, 3), (2, 3, 30, 70)]
+
+
+@pytest.mark.parametrize("shape", NARROW_SHAPES)
+def test_narrow_attention(shape):
+    """attn_narrow.cu (one side <= 32 rows: the video blocks of MulT, reference models/fusion_layers.py:146-153): forward output, LSE,
+    dQ / dK / dV and the fused bias gradients against fp64 torch math on strided packed projections, ragged tiles on both sides."""
+    B, heads, Lq, Lk = shape
+    W = heads * 64
+    scale = 1 / math.sqrt(64)
+    dtype = torch.bfloat16
+    pq = packed(B, Lq, 2 * W, dtype, 11)
+    pkv = packed(B, Lk, 3 * W, dtype, 12)
+    q, k, v = pq[:, :, W:], pkv[:, :, :W], pkv[:, :, 2 * W:]
+    n0 = pkg._lib.launch_count()
+    o, lse = K.attn_fwd(q, k, v, heads, scale)
+    assert pkg._lib.launch_count() - n0 == 1
+    torch.cuda.synchronize()
+    qd, kd, vd = (t.detach().double().requires_grad_(True) for t in (q, k, v))
+    o_ref, lse_ref = reference(qd, kd, vd, heads, scale)
+    assert rel(o, o_ref) < 1e-2, f"O rel err {rel(o, o_ref)}"
+    assert float((lse.double() - lse_ref).abs().max()) < 2e-2
+    do = packed(B, Lq, W, dtype, 13)
+    (o_ref * do.double()).sum().backward()
+    dpq, dpkv = torch.zeros_like(pq), torch.zeros_like(pkv)
+    db = torch.ones(3, W, device="cuda", dtype=torch.float32)
+    n0 = pkg._lib.launch_count()
+    K.attn_bwd(do, q, k, v, o, lse, heads, scale, dpq[:, :, W:], dpkv[:, :, :W], dpkv[:, :, 2 * W:], dbq=db[0], dbk=db[1], dbv=db[2])
+    assert pkg._lib.launch_count() - n0 == 1                 # one kernel: no separate delta / dKdV / column-sum pass
+    torch.cuda.synchronize()
+    assert rel(dpq[:, :, W:], qd.grad) < 2e-2, f"dQ {rel(dpq[:, :, W:], qd.grad)}"
+    assert rel(dpkv[:, :, :W], kd.grad) < 2e-2, f"dK {rel(dpkv[:, :, :W], kd.grad)}"
+    assert rel(dpkv[:, :, 2 * W:], vd.grad) < 2e-2, f"dV {rel(dpkv[:, :, 2 * W:], vd.grad)}"
+    assert float(dpq[:, :, :W].abs().max()) == 0 and float(dpkv[:, :, W:2 * W].abs().max()) == 0
+    for acc, grad in ((db[0], dpq[:, :, W:]), (db[1], dpkv[:, :, :W]), (db[2], dpkv[:, :, 2 * W:])):
+        want = grad.double().sum(dim=(0, 1)) + 1.0
+        assert float((acc.double() - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max())) + 1e-3 * float(grad.float().abs().max())
+    # the 128-wide tcgen05 tiles on the same operands agree (A/B switch b200f_debug_set(10, 0))
+    lib = pkg._lib.lib()
+    lib.b200f_debug_set(10, 0)
+    try:
+        o2, lse2 = K.attn_fwd(q, k, v, heads, scale)
+        torch.cuda.synchronize()
+    finally:
+        lib.b200f_debug_set(10, 1)
+    assert rel(o, o2) < 1e-2 and float((lse - lse2).abs().max()) < 2e-2
 
 
 def test_attention_tc_matches_cuda_core_path():

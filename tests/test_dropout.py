@@ -102,7 +102,8 @@ def rel(x, r):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype,shape", [(torch.bfloat16, (3, 8, 300, 200)), (torch.bfloat16, (2, 8, 512, 512)), (torch.bfloat16, (5, 8, 30, 70)),
-                                         (torch.float32, (2, 8, 65, 40))])
+                                         (torch.bfloat16, (3, 8, 512, 30)), (torch.bfloat16, (3, 8, 30, 512)), (torch.bfloat16, (2, 8, 100, 17)),
+                                         (torch.bfloat16, (2, 8, 17, 100)), (torch.float32, (2, 8, 65, 40))])
 def test_attention_dropout_matches_explicit_mask(dtype, shape):
     B, heads, Lq, Lk = shape
     W, p, lo, hi = heads * 64, 0.25, 0xDEADBEEF, 0x0BADF00D

@@ -147,6 +147,15 @@ int b200f_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream)
 /* mean over L: x[B,L,H] -> y[B, H] written with row stride ldy (fusion_layers.py:166-168);
  * backward: dx[b,l,:] = dy[b,:] / L. */
 int b200f_meanpool_fwd(const void* x, void* y, int64_t ldy, int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream);
+/* Staging pass of the MulT engine, one read of x [B,L,H]: copy[b,l,:] = keep * x[b,l,:] and (mean != NULL) mean[b,:] = keep * mean_l x[b,l,:],
+ * keep = mask[b*3 + col] (mask NULL: 1) -- ModalityDropout's multiply (models/encoders.py:317-319) and the mean-pool that feeds the
+ * 2-D heads of HierarchicalFusion fused into the copy into the static buffers the captured chunk graphs read. */
+int b200f_stage_pool(const void* x, void* copy, void* mean, int64_t ldmean, const float* mask, int32_t col, int32_t B, int32_t L, int32_t H,
+                     int32_t dtype, void* stream);
+/* y[r,:] = a[r,:] + b[r,:] + c[r,:] + s * v[r / L, :] over `rows` rows of H (v: one row per sample with leading dimension ldv,
+ * broadcast over the sample's L tokens): the residual paths into a MulT input plus the gradient of its mean-pooled copy. */
+int b200f_add_rowbcast(const void* a, const void* b, const void* c, const void* v, int64_t ldv, float s, void* y, int64_t rows, int32_t L, int32_t H,
+                       int32_t dtype, void* stream);
 int b200f_meanpool_bwd(const void* dy, int64_t lddy, void* dx, int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream);
 /* weighted pooling over L: y[b,:] = sum_l w[b,l] * x[b,l,:], w fp32 [B,L].  With w = mask / max(sum_l mask, 1e-9)
  * it is the attention-mask mean pooling of the text encoder (models/encoders.py:89-93) applied to per-token projected features;

@@ -255,6 +255,8 @@ constexpr int NKB_ST = 3;
 constexpr int NKB_TILE = 64 * 128;                         // one operand tile: 64 rows x 128 B
 constexpr int NKB_STAGE = 3 * NKB_TILE;                    // Q, dO, O
 constexpr int NKB_SMEM = 2 * NARROW * 128 + NKB_ST * NKB_STAGE + 256;
+constexpr int NKB_RSTRIDE = HD + 8;                        // fp32 row stride of the per-warp dK / dV partials (bank spread)
+static_assert(4 * 2 * NARROW * NKB_RSTRIDE * 4 <= NKB_ST * NKB_STAGE, "the per-warp partials must fit in the ring");
 
 template <bool DROP>
 __global__ void __launch_bounds__(128, 2) attn_nk_bwd_kernel(const NarrowParams p) {
@@ -412,38 +414,49 @@ __global__ void __launch_bounds__(128, 2) attn_nk_bwd_kernel(const NarrowParams 
     store_tile(stg, r0, p.dQ, p.lddq, qtok, tok0, p.Lq, h, lane, p.dbq ? &dbq0 : nullptr, p.dbq ? &dbq1 : nullptr);
   }
   cp_wait<0>();
-  __syncthreads();                   // the ring is free: reuse it as the fp32 reduction buffer [2][32][64]
-  float* red = reinterpret_cast<float*>(ring);
-  for (int i = tid; i < 2 * NARROW * HD; i += 128) red[i] = 0.f;
-  __syncthreads();
+  __syncthreads();                   // the ring is free: per-warp partials [4 warps][dV | dK][32][NKB_RSTRIDE] fp32, summed in a FIXED order
+  float* red = reinterpret_cast<float*>(ring);          // (no atomics: dK / dV are bit-reproducible from run to run)
+  {
+    float* mine = red + warp * (2 * NARROW * NKB_RSTRIDE);
 #pragma unroll
-  for (int j = 0; j < 2; ++j)
+    for (int j = 0; j < 2; ++j)
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = j * 16 + g + (e >> 1) * 8, d = nt * 8 + 2 * t + (e & 1);
-        atomicAdd(&red[key * HD + d], dv[j][nt][e]);
-        atomicAdd(&red[NARROW * HD + key * HD + d], dk[j][nt][e]);
+      for (int nt = 0; nt < 8; ++nt) {
+        const int d = nt * 8 + 2 * t;
+        *reinterpret_cast<float2*>(mine + (j * 16 + g) * NKB_RSTRIDE + d) = make_float2(dv[j][nt][0], dv[j][nt][1]);
+        *reinterpret_cast<float2*>(mine + (j * 16 + g + 8) * NKB_RSTRIDE + d) = make_float2(dv[j][nt][2], dv[j][nt][3]);
+        *reinterpret_cast<float2*>(mine + (NARROW + j * 16 + g) * NKB_RSTRIDE + d) = make_float2(dk[j][nt][0], dk[j][nt][1]);
+        *reinterpret_cast<float2*>(mine + (NARROW + j * 16 + g + 8) * NKB_RSTRIDE + d) = make_float2(dk[j][nt][2], dk[j][nt][3]);
       }
+  }
   if (p.dbq) { atomicAdd(&dbq_s[2 * lane], dbq0); atomicAdd(&dbq_s[2 * lane + 1], dbq1); }
   __syncthreads();
   const long long ktok = (long long)b * p.Lk;
-  for (int i = tid; i < 2 * NARROW * 8; i += 128) {     // (tensor, key, 16-byte chunk)
-    const int which = i >> 8, key = (i >> 3) & 31, ch = i & 7;
-    if (key >= p.Lk) continue;
-    const float* src = red + which * NARROW * HD + key * HD + ch * 8;
+  for (int i = tid; i < 2 * NARROW * 8; i += 128) {     // (tensor, key, 16-byte chunk): sum the four warps, round, store, keep the rounded
+    const int which = i >> 8, key = (i >> 3) & 31, ch = i & 7;                                      // values for the column sums
+    float* src = red + (which * NARROW + key) * NKB_RSTRIDE + ch * 8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = src[e];
+#pragma unroll
+    for (int w = 1; w < 4; ++w)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += src[w * (2 * NARROW * NKB_RSTRIDE) + e];
     uint4 o;
-    o.x = pack_bf16(src[0], src[1]); o.y = pack_bf16(src[2], src[3]); o.z = pack_bf16(src[4], src[5]); o.w = pack_bf16(src[6], src[7]);
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) src[e] = key < p.Lk ? bf16_round(v[e]) : 0.f;
+    if (key >= p.Lk) continue;
     bf16* dst = which == 0 ? p.dV + (ktok + key) * p.lddv : p.dK + (ktok + key) * p.lddk;
     *reinterpret_cast<uint4*>(dst + h * HD + ch * 8) = o;
   }
+  __syncthreads();
   if (tid < 64) {                                        // bias gradients: column sums of the stored (bf16) values
     if (p.dbq) atomicAdd(p.dbq + h * HD + tid, dbq_s[tid]);
     float sv_ = 0.f, sk_ = 0.f;
     for (int key = 0; key < p.Lk; ++key) {
-      sv_ += bf16_round(red[key * HD + tid]);
-      sk_ += bf16_round(red[NARROW * HD + key * HD + tid]);
+      sv_ += red[key * NKB_RSTRIDE + tid];
+      sk_ += red[(NARROW + key) * NKB_RSTRIDE + tid];
     }
     if (p.dbv) atomicAdd(p.dbv + h * HD + tid, sv_);
     if (p.dbk) atomicAdd(p.dbk + h * HD + tid, sk_);
@@ -459,6 +472,7 @@ constexpr int NQ_STAGE = 2 * 64 * 128;                    // K, V
 constexpr int NQ_OSTRIDE = HD + 8;                        // fp32 row stride of the merge buffers (bank spread)
 constexpr int NQF_SMEM = NARROW * 128 + NQF_ST * NQ_STAGE + 256;
 static_assert(4 * NARROW * NQ_OSTRIDE * 4 + 2 * 4 * NARROW * 4 <= NQF_ST * NQ_STAGE, "merge buffers must fit in the ring");
+static_assert(4 * NARROW * NQ_OSTRIDE * 4 <= 3 * NQ_STAGE, "the backward's per-warp dQ partials must fit in its ring");
 
 template <bool DROP>
 __global__ void __launch_bounds__(128, 2) attn_nq_fwd_kernel(const NarrowParams p) {
@@ -676,7 +690,6 @@ __global__ void __launch_bounds__(128, 2) attn_nq_bwd_kernel(const NarrowParams 
   load_rows(smem_u32(Os), p.O, p.ldo, qtok, 0, p.Lq, NARROW, h, tid, 128);
   issue(0);
   issue(1);
-  for (int i = tid; i < NARROW * NQ_OSTRIDE; i += 128) red[i] = 0.f;
   for (int i = tid; i < 3 * HD; i += 128) dbs[i] = 0.f;
   cp_wait<1>();                      // the resident tiles + K/V tile 0 (one group may still be in flight)
   __syncthreads();
@@ -829,33 +842,43 @@ __global__ void __launch_bounds__(128, 2) attn_nq_bwd_kernel(const NarrowParams 
     store_tile(Kt, kw, p.dK, p.lddk, ktok, key0, p.Lk, h, lane, p.dbk ? &dbk0 : nullptr, p.dbk ? &dbk1 : nullptr);
   }
   cp_wait<0>();
-  // dQ: reduce the four warps' partials, then store the valid rows
+  __syncthreads();                   // the ring is free: per-warp dQ partials [4][32][NQ_OSTRIDE] fp32, summed in a FIXED order (no atomics:
+  float* part = reinterpret_cast<float*>(ring);          // dQ is bit-reproducible from run to run)
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        atomicAdd(&red[(mt * 16 + g + (e >> 1) * 8) * NQ_OSTRIDE + nt * 8 + 2 * t + (e & 1)], dq[mt][nt][e]);
+    for (int nt = 0; nt < 8; ++nt) {
+      *reinterpret_cast<float2*>(part + (warp * NARROW + mt * 16 + g) * NQ_OSTRIDE + nt * 8 + 2 * t) = make_float2(dq[mt][nt][0], dq[mt][nt][1]);
+      *reinterpret_cast<float2*>(part + (warp * NARROW + mt * 16 + g + 8) * NQ_OSTRIDE + nt * 8 + 2 * t) = make_float2(dq[mt][nt][2], dq[mt][nt][3]);
+    }
   if (p.dbv) { atomicAdd(&dbs[2 * HD + 2 * lane], dbv0); atomicAdd(&dbs[2 * HD + 2 * lane + 1], dbv1); }
   if (p.dbk) { atomicAdd(&dbs[HD + 2 * lane], dbk0); atomicAdd(&dbs[HD + 2 * lane + 1], dbk1); }
   __syncthreads();
   {
     const int row = tid >> 2, c0 = (tid & 3) * 16;
+    float v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = part[row * NQ_OSTRIDE + c0 + e];
+#pragma unroll
+    for (int w = 1; w < 4; ++w)
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] += part[(w * NARROW + row) * NQ_OSTRIDE + c0 + e];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) red[row * NQ_OSTRIDE + c0 + e] = row < p.Lq ? bf16_round(v[e]) : 0.f;
     if (row < p.Lq) {
-      const float* src = red + row * NQ_OSTRIDE + c0;
       uint4 o0, o1;
-      o0.x = pack_bf16(src[0], src[1]); o0.y = pack_bf16(src[2], src[3]); o0.z = pack_bf16(src[4], src[5]); o0.w = pack_bf16(src[6], src[7]);
-      o1.x = pack_bf16(src[8], src[9]); o1.y = pack_bf16(src[10], src[11]); o1.z = pack_bf16(src[12], src[13]); o1.w = pack_bf16(src[14], src[15]);
+      o0.x = pack_bf16(v[0], v[1]); o0.y = pack_bf16(v[2], v[3]); o0.z = pack_bf16(v[4], v[5]); o0.w = pack_bf16(v[6], v[7]);
+      o1.x = pack_bf16(v[8], v[9]); o1.y = pack_bf16(v[10], v[11]); o1.z = pack_bf16(v[12], v[13]); o1.w = pack_bf16(v[14], v[15]);
       bf16* dst = p.dQ + (qtok + row) * p.lddq + h * HD + c0;
       *reinterpret_cast<uint4*>(dst) = o0;
       *reinterpret_cast<uint4*>(dst + 8) = o1;
     }
   }
+  __syncthreads();
   if (tid < 64) {
     if (p.dbq) {
       float s_ = 0.f;
-      for (int row = 0; row < p.Lq; ++row) s_ += bf16_round(red[row * NQ_OSTRIDE + tid]);
+      for (int row = 0; row < p.Lq; ++row) s_ += red[row * NQ_OSTRIDE + tid];
       atomicAdd(p.dbq + h * HD + tid, s_);
     }
     if (p.dbk) atomicAdd(p.dbk + h * HD + tid, dbs[HD + tid]);

@@ -287,6 +287,26 @@ __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, con
   }
 }
 
+// y[r, :] = a[r, :] + b[r, :] + c[r, :] + s * v[r / L, :]   (rows of H; v: one row per sample, broadcast over its L tokens).
+// MulT backward: the three residual paths into a modality's input plus the gradient of the mean-pooled copy that feeds the 2-D heads.
+template <typename T>
+__global__ void add_rowbcast_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c, const T* __restrict__ v, long long ldv,
+                                    float s, T* __restrict__ y, long long rows, int L, int hv) {
+  constexpr int VN = Vec16<T>::N;
+  const long long nvec = rows * hv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / hv;
+    const int cv = int(i - r * hv);
+    Vec16<T> va, vb, vc, vv;
+    va.load(a + i * VN); vb.load(b + i * VN); vc.load(c + i * VN); vv.load(v + (r / L) * ldv + cv * VN);
+    float fa[VN], fb[VN], fc[VN], fv[VN];
+    va.unpack(fa); vb.unpack(fb); vc.unpack(fc); vv.unpack(fv);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) fa[j] = fa[j] + fb[j] + fc[j] + s * fv[j];
+    Vec16<T> o; o.pack(fa); o.store(y + i * VN);
+  }
+}
+
 template <typename T>
 __global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ ref, T* __restrict__ dx, long long nvec) {
   constexpr int VN = Vec16<T>::N;
@@ -320,9 +340,13 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __rest
 // CX column threads x RY row groups, each row group walks l = ry, ry + RY, ... with eight independent 16-byte loads in flight
 // (the one-thread-per-column loop it replaces kept 1 MB in flight over the whole GPU at B = 256: 1.9 TB/s); the row groups
 // are combined through shared memory.
+// Staging variant (copy != nullptr; the chunk-graph MulT engine): the same single read of x also writes the copy
+// copy[b,l,:] = keep * x[b,l,:] and y = keep * mean, keep = mask[b*3 + mcol] (mask == nullptr: 1) -- ModalityDropout's multiply
+// (reference models/encoders.py:317-319) and the mean-pool that feeds the 2-D heads ride on the copy into the static buffers.
 template <typename T>
 __global__ void __launch_bounds__(512) meanpool_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y, long long ldy, int L,
-                                                           int H, int CX) {   // w: nullptr = plain mean (1/L), else per-(b,l) weights [B,L]
+                                                           int H, int CX, T* __restrict__ copy = nullptr, const float* __restrict__ mask = nullptr,
+                                                           int mcol = 0) {   // w: nullptr = plain mean (1/L), else per-(b,l) weights [B,L]
   constexpr int VN = Vec16<T>::N;
   extern __shared__ float pool_red[];                 // [RY][CX * VN]
   const int RY = blockDim.x / CX;
@@ -331,6 +355,8 @@ __global__ void __launch_bounds__(512) meanpool_fwd_kernel(const T* __restrict__
   const bool col_ok = c0 < H && ry < RY;
   const long long b = blockIdx.x;
   const T* xb = x + b * (long long)L * H + c0;
+  T* cb = copy ? copy + b * (long long)L * H + c0 : nullptr;
+  const float keep = mask ? mask[b * 3 + mcol] : 1.f;
   float acc[VN];
 #pragma unroll
   for (int j = 0; j < VN; ++j) acc[j] = 0.f;
@@ -346,6 +372,14 @@ __global__ void __launch_bounds__(512) meanpool_fwd_kernel(const T* __restrict__
         const float wl = w ? __ldg(w + b * L + l + u * RY) : 1.f;
 #pragma unroll
         for (int j = 0; j < VN; ++j) acc[j] += wl * f[j];
+        if (cb) {
+          if (keep != 1.f) {
+#pragma unroll
+            for (int j = 0; j < VN; ++j) f[j] *= keep;
+            t[u].pack(f);
+          }
+          t[u].store(cb + (long long)(l + u * RY) * H);
+        }
       }
     }
     for (; l < L; l += RY) {
@@ -353,16 +387,24 @@ __global__ void __launch_bounds__(512) meanpool_fwd_kernel(const T* __restrict__
       const float wl = w ? __ldg(w + b * L + l) : 1.f;
 #pragma unroll
       for (int j = 0; j < VN; ++j) acc[j] += wl * f[j];
+      if (cb) {
+        if (keep != 1.f) {
+#pragma unroll
+          for (int j = 0; j < VN; ++j) f[j] *= keep;
+          t.pack(f);
+        }
+        t.store(cb + (long long)l * H);
+      }
     }
 #pragma unroll
     for (int j = 0; j < VN; ++j) pool_red[(ry * CX + cx) * VN + j] = acc[j];
   }
   __syncthreads();
-  if (col_ok && ry == 0) {
+  if (col_ok && ry == 0 && y) {
     for (int r = 1; r < RY; ++r)
 #pragma unroll
       for (int j = 0; j < VN; ++j) acc[j] += pool_red[(r * CX + cx) * VN + j];
-    const float inv = w ? 1.f : 1.f / L;
+    const float inv = (w ? 1.f : 1.f / L) * keep;
 #pragma unroll
     for (int j = 0; j < VN; ++j) acc[j] *= inv;
     Vec16<T> o; o.pack(acc); o.store(y + b * ldy + c0);
@@ -660,6 +702,21 @@ int b200f_add(const void* a, const void* b, const void* c, void* y, int64_t n, i
   return check_launch("add");
 }
 
+int b200f_add_rowbcast(const void* a, const void* b, const void* c, const void* v, int64_t ldv, float s, void* y, int64_t rows, int32_t L, int32_t H,
+                       int32_t dtype, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (rows == 0) return B200F_OK;
+  B200F_REQUIRE(a && b && c && v && y && L > 0 && rows % L == 0, B200F_ERR_SHAPE, "add_rowbcast: operands / shape");
+  DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec16<T>::N;
+    B200F_REQUIRE(H % VN == 0 && ldv % VN == 0, B200F_ERR_SHAPE, "add_rowbcast: H and ldv must be multiples of %d", VN);
+    B200F_REQUIRE(aligned16(a) && aligned16(b) && aligned16(c) && aligned16(v) && aligned16(y), B200F_ERR_ALIGN, "add_rowbcast: alignment");
+    add_rowbcast_kernel<T><<<ew_grid(rows * (H / VN), 256), 256, 0, st>>>(static_cast<const T*>(a), static_cast<const T*>(b), static_cast<const T*>(c),
+                                                                          static_cast<const T*>(v), ldv, s, static_cast<T*>(y), rows, L, H / VN);
+  })
+  return check_launch("add_rowbcast");
+}
+
 int b200f_relu_bwd(const void* dy, const void* ref, void* dx, int64_t n, int32_t dtype, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n == 0) return B200F_OK;
@@ -708,6 +765,24 @@ static int pool_bwd(const void* dy, int64_t lddy, const float* w, void* dx, int3
     meanpool_bwd_kernel<T><<<ew_grid((long long)B * L * (H / VN), 256), 256, 0, st>>>(static_cast<const T*>(dy), lddy, w, static_cast<T*>(dx), B, L, H);
   })
   return check_launch("meanpool_bwd");
+}
+
+int b200f_stage_pool(const void* x, void* copy, void* mean, int64_t ldmean, const float* mask, int32_t col, int32_t B, int32_t L, int32_t H,
+                     int32_t dtype, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B == 0) return B200F_OK;
+  B200F_REQUIRE(x && copy && L > 0 && col >= 0 && col < 3, B200F_ERR_SHAPE, "stage_pool: operands / shape");
+  DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec16<T>::N;
+    B200F_REQUIRE(H % VN == 0 && (!mean || ldmean % VN == 0), B200F_ERR_SHAPE, "stage_pool: shape");
+    B200F_REQUIRE(aligned16(x) && aligned16(copy) && aligned16(mean), B200F_ERR_ALIGN, "stage_pool: alignment");
+    const int hv = H / VN;
+    const int cx = hv < 64 ? hv : 64;
+    const int gy = (hv + cx - 1) / cx;
+    meanpool_fwd_kernel<T><<<dim3(B, gy), 512, 512 * VN * sizeof(float), st>>>(static_cast<const T*>(x), nullptr, static_cast<T*>(mean), ldmean, L, H, cx,
+                                                                              static_cast<T*>(copy), mask, col);
+  })
+  return check_launch("stage_pool");
 }
 
 int b200f_meanpool_fwd(const void* x, void* y, int64_t ldy, int32_t B, int32_t L, int32_t H, int32_t dtype, void* stream) {

@@ -224,7 +224,7 @@ class MultimodalTransformer(_FusionBase):
             self._engine.release()
         self._engine, self._engine_key = None, None
 
-    def _graph_engine(self, W, xs, need_dx, p_drop):
+    def _graph_engine(self, W, xs, need_dx, p_drop, want_mean=False):
         """ChunkGraphEngine for this step, or None when the step is issued eagerly: fp32 parity mode, inference, inside an outer
         CUDA-graph capture, tiny chunks, shapes that keep changing, or too little free memory to keep every chunk's stash."""
         t = xs[0]
@@ -233,7 +233,7 @@ class MultimodalTransformer(_FusionBase):
         B, Ls, chunk = t.size(0), [x.size(1) for x in xs], int(self.chunk_size)
         if min(B, chunk) * sum(Ls) < self.graph_min_tokens:
             return None
-        key = (B, tuple(Ls), chunk, t.device, float(p_drop), bool(need_dx), id(W))
+        key = (B, tuple(Ls), chunk, t.device, float(p_drop), bool(need_dx), bool(want_mean), id(W))
         if self._engine is not None and self._engine_key == key:
             return self._engine
         if self._engine_builds >= 4:                     # shapes keep changing: capturing each of them costs more than it saves
@@ -248,19 +248,20 @@ class MultimodalTransformer(_FusionBase):
         if B * stash > self.stash_fraction * free_bytes or need > 0.92 * free_bytes:
             return None                                      # not every chunk can stay resident: eager issue with recomputed chunks
         self._engine = mult_engine.ChunkGraphEngine(W, self._names, H, self.config.fusion_num_heads, chunk, B, Ls, t.dtype, t.device,
-                                                    p_drop, need_dx)
+                                                    p_drop, need_dx, want_mean)
         self._engine_key = key
         self._engine_builds += 1
         return self._engine
 
-    def _pooled(self, t, a, v, mask):
+    def _pooled(self, t, a, v, mask, want_mean=False):
+        """pooled attended features [B,3H]; with `want_mean` also the masked mean over L of the inputs ([B,3H], see MulTFn)"""
         if t.dim() == 2:                                     # fusion_layers.py:140-143
             t, a, v = t.unsqueeze(1), a.unsqueeze(1), v.unsqueeze(1)
         training_drop = self.training and self._p > 0.0
         H, heads = self.config.fusion_hidden_size, self.config.fusion_num_heads
         W, plist = self._operands(t.dtype)
         need_dx = torch.is_grad_enabled() and any(x.requires_grad for x in (t, a, v))
-        engine = self._graph_engine(W, (t, a, v), need_dx, self._p if training_drop else 0.0)
+        engine = self._graph_engine(W, (t, a, v), need_dx, self._p if training_drop else 0.0, want_mean)
         drop = None
         if engine is None and training_drop:
             drop = (self._p, *ops.next_drop_seed())          # one seed pair per call
@@ -273,7 +274,9 @@ class MultimodalTransformer(_FusionBase):
             free_bytes, _ = torch.cuda.mem_get_info(t.device)
             free_bytes += torch.cuda.memory_reserved(t.device) - torch.cuda.memory_allocated(t.device)
             budget = int(self.stash_fraction * free_bytes) if torch.is_grad_enabled() else 0
-        return mult_engine.MulTFn.apply(t, a, v, mask, H, heads, int(self.chunk_size), budget, drop, self._names, W, engine, *plist)
+        pooled, xmean = mult_engine.MulTFn.apply(t, a, v, mask, bool(want_mean), H, heads, int(self.chunk_size), budget, drop, self._names, W,
+                                                 engine, *plist)
+        return (pooled, xmean) if want_mean else pooled
 
     def forward(self, text_features, audio_features, video_features, mask=None) -> Dict[str, Tensor]:
         (t, a, v), mask, _ = self._prepare((text_features, audio_features, video_features), mask)
@@ -459,12 +462,18 @@ class HierarchicalFusion(_FusionBase):
                 raise B200FusionError("pooled_features must be three [B,H] tensors")
             pooled2d, _, _ = self._prepare(tuple(pooled_features), None)
         else:
-            pooled2d = [x if x.dim() == 2 else ops.MeanPoolFn.apply(x) for x in (t, a, v)]
-        cat = _masked_cat(*pooled2d, mask)                                   # shared by early / graph / contrastive / adaptive
-        feats = ops.Split3Fn.apply(cat) if mask is not None else pooled2d
-        early = self.early_fusion._run(cat)
+            pooled2d = None if t.dim() == 3 else [t, a, v]
         mt = self.mult_fusion
-        mult_pooled = mt._pooled(t, a, v, mask)
+        if pooled2d is None:
+            # [B,L,H] inputs and no pooled features given: the 2-D heads see the (masked) mean over L, which MulT's staging pass
+            # produces from the same read of the sequences; its gradient joins MulT's input gradient inside the chunk backward
+            mult_pooled, cat = mt._pooled(t, a, v, mask, want_mean=True)
+            feats = ops.Split3Fn.apply(cat)
+        else:
+            mult_pooled = mt._pooled(t, a, v, mask)
+            cat = _masked_cat(*pooled2d, mask)                               # shared by early / graph / contrastive / adaptive
+            feats = ops.Split3Fn.apply(cat) if mask is not None else pooled2d
+        early = self.early_fusion._run(cat)
         ff = mt.final_fusion[0]
         mult = ops.dropout(ops.linear(mult_pooled, ff.weight, ff.bias, relu=True), self._p, self.training)
         graph = self.graph_fusion._run(cat, dt)

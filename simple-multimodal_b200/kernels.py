@@ -200,6 +200,30 @@ def meanpool_fwd(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
     return out
 
 
+def stage_pool(x: Tensor, copy: Tensor, mean: Optional[Tensor], mask: Optional[Tensor], col: int) -> None:
+    """copy[b,l,:] = keep * x[b,l,:]; mean[b,:] = keep * mean_l x[b,l,:] (mean may be a column slice of a wider [B, *] tensor, or None);
+    keep = mask[b, col] (mask None: 1).  One read of x."""
+    require_cuda(x, copy, mean, mask)
+    B, Lx, H = x.shape
+    if copy.shape != x.shape or copy.dtype != x.dtype or not x.is_contiguous() or not copy.is_contiguous():
+        raise B200FusionError("stage_pool: x / copy must be contiguous [B,L,H] tensors of one dtype")
+    if mean is not None and (mean.shape != (B, H) or mean.dtype != x.dtype or mean.stride(1) != 1):
+        raise B200FusionError("stage_pool: mean must be [B,H] rows of the input dtype")
+    check(lib().b200f_stage_pool(ptr(x), ptr(copy), ptr(mean), C.c_int64(0 if mean is None else mean.stride(0)), ptr(mask), C.c_int32(col),
+                                 C.c_int32(B), C.c_int32(Lx), C.c_int32(H), dtype_code(x.dtype), stream_ptr()), "b200f_stage_pool")
+
+
+def add_rowbcast(a: Tensor, b: Tensor, c: Tensor, v: Tensor, scale: float, Lx: int, out: Optional[Tensor] = None) -> Tensor:
+    """out[r,:] = a[r,:] + b[r,:] + c[r,:] + scale * v[r // Lx, :]; a/b/c contiguous [rows, H], v [rows // Lx, H] rows (may be a column slice)."""
+    rows, H = a.shape
+    out = torch.empty_like(a) if out is None else out
+    if v.stride(1) != 1 or v.size(0) * Lx != rows or v.size(1) != H:
+        raise B200FusionError("add_rowbcast: v must hold one contiguous row of H per sample")
+    check(lib().b200f_add_rowbcast(ptr(a), ptr(b), ptr(c), ptr(v), C.c_int64(v.stride(0)), C.c_float(scale), ptr(out), C.c_int64(rows), C.c_int32(Lx),
+                                   C.c_int32(H), dtype_code(a.dtype), stream_ptr()), "b200f_add_rowbcast")
+    return out
+
+
 def meanpool_bwd(dy: Tensor, Lx: int) -> Tensor:
     B, H = dy.shape
     dx = torch.empty((B, Lx, H), device=dy.device, dtype=dy.dtype)

@@ -167,10 +167,11 @@ def _chunk_forward(xs, W: _Weights, H: int, heads: int, pooled_out: Tensor, keep
     return st
 
 
-def _chunk_backward(st, W: _Weights, H: int, heads: int, dpooled: Tensor, G: Dict[str, Tensor], dstack_w, dstack_b, dx_out, drop=None):
+def _chunk_backward(st, W: _Weights, H: int, heads: int, dpooled: Tensor, G: Dict[str, Tensor], dstack_w, dstack_b, dx_out, drop=None, dmean=None):
     """Backward of one chunk.  dpooled [Bc,3H]; G: fp32 gradient accumulators keyed like the parameters;
     dstack_w/dstack_b: accumulators of the stacked projections; dx_out: None, or the three contiguous [Bc,L,H] slices of the
-    input-gradient buffers this chunk's input gradients are written into (the last dgrad GEMM stores there directly)."""
+    input-gradient buffers this chunk's input gradients are written into (the last dgrad GEMM stores there directly);
+    dmean: None or [Bc,3H], the gradient of the mean-over-L of the inputs (MulTFn's second output) -- added to the residual paths."""
     need_dx = dx_out is not None
     scale = mha_scale(H, heads)
     x2, Ls, proj = st["x2"], st["Ls"], st["proj"]
@@ -222,7 +223,10 @@ def _chunk_backward(st, W: _Weights, H: int, heads: int, dpooled: Tensor, G: Dic
         K.linear_wgrad(dp2, x2[m], dstack_w[m])
         if need_dx:
             a_name, b_name = [n for n, qm, _ in BLOCKS if qm == m]
-            direct = K.add(d_enh[m], d_s1[a_name], d_s1[b_name])      # residual paths into the input
+            if dmean is None:
+                direct = K.add(d_enh[m], d_s1[a_name], d_s1[b_name])      # residual paths into the input
+            else:                                                         # ... plus dmean / L broadcast over the sample's tokens
+                direct = K.add_rowbcast(d_enh[m], d_s1[a_name], d_s1[b_name], dmean[:, m * H:(m + 1) * H], 1.0 / Ls[m], Ls[m])
             K.linear_dgrad(dp2, W.w_stack[m], residual=direct, out=dx_out[m].view(-1, H))
 
 
@@ -288,10 +292,12 @@ class ChunkGraphEngine:
 
     One forward may be in flight: a second forward overwrites the static buffers, and the first one's backward then raises."""
 
-    def __init__(self, W: _Weights, names, H: int, heads: int, chunk: int, B: int, Ls, dtype, dev, drop_p: float, need_dx: bool):
+    def __init__(self, W: _Weights, names, H: int, heads: int, chunk: int, B: int, Ls, dtype, dev, drop_p: float, need_dx: bool,
+                 want_mean: bool = False):
         from .ops import next_drop_seed
         self.W, self.names, self.H, self.heads, self.chunk, self.B, self.Ls = W, list(names), H, heads, chunk, B, list(Ls)
-        self.need_dx, self.drop_p = need_dx, drop_p
+        self.need_dx, self.drop_p, self.want_mean = need_dx, drop_p, want_mean
+        self.dmean = torch.zeros((B, 3 * H), device=dev, dtype=dtype) if (want_mean and need_dx) else None
         self.drop = (drop_p, *next_drop_seed()) if drop_p > 0.0 else None
         self.bounds = [(b0, min(B, b0 + chunk)) for b0 in range(0, B, chunk)]
         self.xs = [torch.empty((B, L, H), device=dev, dtype=dtype) for L in Ls]
@@ -311,7 +317,8 @@ class ChunkGraphEngine:
     def _bwd(self, ci, st):
         b0, b1 = self.bounds[ci]
         _chunk_backward(st, self.W, self.H, self.heads, self.dpooled[b0:b1], self.G, self.dstack_w, self.dstack_b,
-                        [d[b0:b1] for d in self.dx] if self.need_dx else None, drop=_chunk_drop(self.drop, ci))
+                        [d[b0:b1] for d in self.dx] if self.need_dx else None, drop=_chunk_drop(self.drop, ci),
+                        dmean=None if self.dmean is None else self.dmean[b0:b1])
 
     def _capture(self):
         from . import _lib
@@ -353,23 +360,32 @@ class ChunkGraphEngine:
         if self.drop is not None:
             K.dropout_epoch(delta & 0xFFFFFFFF, add=True)
 
-    def forward(self, xs, mask) -> Tensor:
+    def forward(self, xs, mask):
         self.W.refresh()
-        for m in range(3):
-            K.rowmask_copy(xs[m], self.xs[m], mask, m)
+        xmean = torch.empty((self.B, 3 * self.H), device=self.pooled.device, dtype=self.pooled.dtype) if self.want_mean else None
+        for m in range(3):                                  # one read of the inputs: masked copy into the static buffers (+ their mean over L)
+            if self.want_mean:
+                K.stage_pool(xs[m], self.xs[m], xmean[:, m * self.H:(m + 1) * self.H], mask, m)
+            else:
+                K.rowmask_copy(xs[m], self.xs[m], mask, m)
         self.step_no += 1
         self.live = self.step_no
         self._epoch(self.step_no)
         for g in self.fwd_graphs:
             g.replay()
         self._epoch(-self.step_no)
-        return self.pooled.clone(), self.step_no
+        return self.pooled.clone(), xmean, self.step_no
 
-    def backward(self, token: int, dpooled: Tensor, mask):
+    def backward(self, token: int, dpooled: Tensor, mask, dxmean=None):
         if token != self.live:
             raise B200FusionError("MulT chunk graphs: the static activation buffers of this forward were overwritten by a later forward "
                                     "(one forward may be in flight; set MultimodalTransformer.graph_chunks = False for several)")
         self.dpooled.copy_(dpooled)
+        if self.dmean is not None:
+            if dxmean is None:
+                self.dmean.zero_()
+            else:
+                self.dmean.copy_(dxmean)
         self.flat.zero_()
         self._epoch(token)
         for ci in reversed(range(len(self.bounds))):
@@ -388,49 +404,66 @@ class ChunkGraphEngine:
 
 
 class MulTFn(torch.autograd.Function):
-    """(text, audio, video [B,L,H]) [+ modality keep-mask [B,3]] + MulT parameters -> pooled attended features [B,3H].
+    """(text, audio, video [B,L,H]) [+ modality keep-mask [B,3]] + MulT parameters -> (pooled attended features [B,3H], xmean).
 
     The modality-dropout multiply (models/encoders.py:317-319) is applied here: on the copy into the engine's static input
-    buffers, or (eager path) by one masked copy; backward masks the input gradients in place.
+    buffers, or (eager path) by one masked copy; backward masks the input gradients in place.  With `want_mean` the second output
+    is [mask_t * mean_L(t) | mask_a * mean_L(a) | mask_v * mean_L(v)] ([B,3H]), the input of HierarchicalFusion's 2-D heads
+    (SURVEY F3), computed by the same single read of the inputs; its gradient joins the residual paths inside the last add of the
+    chunk backward instead of materialising a second [B,L,H] gradient.  Without `want_mean` it is an empty placeholder.
     `engine` (a ChunkGraphEngine for exactly this shape) replays captured chunk graphs; without it the batch runs in eagerly
     issued chunks of `chunk` samples: chunks whose activations fit in `stash_budget` bytes stay resident for backward, the
     remaining chunks are recomputed chunk by chunk in backward (bounded memory at any batch)."""
 
     @staticmethod
-    def forward(ctx, t, a, v, mask, H, heads, chunk, stash_budget, drop, names, W, engine, *params):
-        ctx.mask, ctx.engine = mask, engine
+    def forward(ctx, t, a, v, mask, want_mean, H, heads, chunk, stash_budget, drop, names, W, engine, *params):
+        ctx.mask, ctx.engine, ctx.want_mean = mask, engine, want_mean
         need_grad = any(ctx.needs_input_grad)
-        if engine is not None:
-            pooled, ctx.token = engine.forward([x.contiguous() for x in (t, a, v)], mask)
-            ctx.cfg = (H, heads, chunk, names, drop)
-            return pooled
-        if mask is None:
-            xs = [x.contiguous() for x in (t, a, v)]
-        else:
-            xs = [K.rowmask_copy(x.contiguous(), torch.empty(x.shape, device=x.device, dtype=x.dtype), mask, m) for m, x in enumerate((t, a, v))]
-        B = xs[0].size(0)
-        W.refresh(force=torch.cuda.is_current_stream_capturing())     # inside a captured step the casts must be part of the graph
-        pooled = torch.empty((B, 3 * H), device=t.device, dtype=t.dtype)
-        per_chunk = stash_bytes_per_sample([x.size(1) for x in xs], H, xs[0].element_size()) * min(chunk, B)
-        n_keep = int(stash_budget // max(per_chunk, 1)) if need_grad else 0
-        stash = {}
-        for ci, b0 in enumerate(range(0, B, chunk)):
-            b1 = min(B, b0 + chunk)
-            keep = ci < n_keep
-            st = _chunk_forward([x[b0:b1] for x in xs], W, H, heads, pooled[b0:b1], keep=keep, drop=_chunk_drop(drop, ci))
-            if keep:
-                stash[b0] = st
         ctx.cfg = (H, heads, chunk, names, drop)
-        ctx.W, ctx.stash, ctx.xs = (W if need_grad else None), stash, (xs if need_grad else None)
-        return pooled
+        if engine is not None:
+            pooled, xmean, ctx.token = engine.forward([x.contiguous() for x in (t, a, v)], mask)
+        else:
+            B = t.size(0)
+            xin = [x.contiguous() for x in (t, a, v)]
+            xmean = torch.empty((B, 3 * H), device=t.device, dtype=t.dtype) if want_mean else None
+            if mask is None:
+                xs = xin
+                if want_mean:
+                    for m in range(3):
+                        K.meanpool_fwd(xs[m], out=xmean[:, m * H:(m + 1) * H])
+            else:
+                xs = [torch.empty(x.shape, device=x.device, dtype=x.dtype) for x in xin]
+                for m in range(3):
+                    if want_mean:
+                        K.stage_pool(xin[m], xs[m], xmean[:, m * H:(m + 1) * H], mask, m)
+                    else:
+                        K.rowmask_copy(xin[m], xs[m], mask, m)
+            W.refresh(force=torch.cuda.is_current_stream_capturing())     # inside a captured step the casts must be part of the graph
+            pooled = torch.empty((B, 3 * H), device=t.device, dtype=t.dtype)
+            per_chunk = stash_bytes_per_sample([x.size(1) for x in xs], H, xs[0].element_size()) * min(chunk, B)
+            n_keep = int(stash_budget // max(per_chunk, 1)) if need_grad else 0
+            stash = {}
+            for ci, b0 in enumerate(range(0, B, chunk)):
+                b1 = min(B, b0 + chunk)
+                keep = ci < n_keep
+                st = _chunk_forward([x[b0:b1] for x in xs], W, H, heads, pooled[b0:b1], keep=keep, drop=_chunk_drop(drop, ci))
+                if keep:
+                    stash[b0] = st
+            ctx.W, ctx.stash, ctx.xs = (W if need_grad else None), stash, (xs if need_grad else None)
+        if xmean is None:
+            xmean = pooled.new_empty(0)
+            ctx.mark_non_differentiable(xmean)
+        return pooled, xmean
 
     @staticmethod
-    def backward(ctx, dpooled):
+    def backward(ctx, dpooled, dxmean):
         H, heads, chunk, names, drop = ctx.cfg
         need_dx = any(ctx.needs_input_grad[:3])
-        n_fixed = 12                                   # positional arguments before *params
+        n_fixed = 13                                   # positional arguments before *params
+        if not ctx.want_mean:
+            dxmean = None
         if ctx.engine is not None:
-            dxs, views = ctx.engine.backward(ctx.token, dpooled, ctx.mask)
+            dxs, views = ctx.engine.backward(ctx.token, dpooled, ctx.mask, dxmean)
             grads = [g if ctx.needs_input_grad[n_fixed + i] else None for i, g in enumerate(views)]
             dxs = dxs if need_dx else (None, None, None)
             return (dxs[0], dxs[1], dxs[2], *([None] * (n_fixed - 3)), *grads)
@@ -438,6 +471,8 @@ class MulTFn(torch.autograd.Function):
         B = xs[0].size(0)
         dev = xs[0].device
         dpooled = dpooled.contiguous()
+        if dxmean is not None:
+            dxmean = dxmean.contiguous()
         flat, G, dstack_w, dstack_b = _grad_buffers(W, names, dev)
         flat.zero_()
         dxs = [torch.empty_like(x) for x in xs] if need_dx else None
@@ -450,7 +485,7 @@ class MulTFn(torch.autograd.Function):
                     scratch = torch.empty((min(chunk, B), 3 * H), device=dev, dtype=xs[0].dtype)
                 st = _chunk_forward([x[b0:b1] for x in xs], W, H, heads, scratch[:b1 - b0], keep=True, drop=_chunk_drop(drop, b0 // chunk))
             _chunk_backward(st, W, H, heads, dpooled[b0:b1], G, dstack_w, dstack_b, [d[b0:b1] for d in dxs] if need_dx else None,
-                            drop=_chunk_drop(drop, b0 // chunk))
+                            drop=_chunk_drop(drop, b0 // chunk), dmean=None if dxmean is None else dxmean[b0:b1])
             del st
         ctx.stash = {}
         _scatter_stacked(W, H, G, dstack_w, dstack_b)

@@ -131,7 +131,7 @@ def test_engine_dropout_matches_eager_at_the_same_seeds_and_epoch():
         p.grad = None
     try:
         K.dropout_epoch(2)                                                # the epoch the engine raised around its second step
-        pooled = ME.MulTFn.apply(*ins, None, 512, 8, 2, 1 << 40, eng.drop, head._names, W, None, *plist)
+        pooled, _ = ME.MulTFn.apply(*ins, None, False, 512, 8, 2, 1 << 40, eng.drop, head._names, W, None, *plist)
         # (final_fusion's own elementwise dropout draws from the host-side counter stream: compare the pooled path only)
         pooled.float().pow(2).mean().backward()
         torch.cuda.synchronize()
@@ -143,7 +143,7 @@ def test_engine_dropout_matches_eager_at_the_same_seeds_and_epoch():
         p.grad = None
     ins2 = [x.detach().clone().requires_grad_(True) for x in xs]
     eng.step_no = 1                                                       # replay step 2 again
-    pooled2 = ME.MulTFn.apply(*ins2, None, 512, 8, 2, 0, None, head._names, W, eng, *plist)
+    pooled2, _ = ME.MulTFn.apply(*ins2, None, False, 512, 8, 2, 0, None, head._names, W, eng, *plist)
     pooled2.float().pow(2).mean().backward()
     torch.cuda.synchronize()
     assert torch.equal(pooled2, pooled)

@@ -39,6 +39,7 @@ extern uint32_t g_dbg_mn_lbo, g_dbg_mn_sbo, g_dbg_mn_kadv;
 extern bool g_dbg_disable_pair;
 extern bool g_dbg_six_stages;
 extern bool g_dbg_no_tma_store;
+extern bool g_dbg_no_tma_store_aux;
 extern bool g_dbg_no_ln_tma;
 extern int g_attn_fwd_variant;
 extern int g_attn_bwd_variant;
@@ -117,6 +118,7 @@ int b200f_debug_set(int key, unsigned value) {
     case 8: b200f::g_dbg_no_tma_store = value != 0; break;
     case 9: b200f::g_dbg_no_ln_tma = value != 0; break;
     case 10: b200f::g_attn_narrow = int(value); break;
+    case 11: b200f::g_dbg_no_tma_store_aux = value != 0; break;
     default: return b200f::fail(B200F_ERR_UNSUPPORTED, "unknown debug key %d", key);
   }
   return B200F_OK;

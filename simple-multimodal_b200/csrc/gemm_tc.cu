@@ -186,7 +186,9 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, const 
     const int col0 = n_base + c0;
     uint8_t* st = stage + (blk & 1) * p.epi_stride;
     if (p.tma_store) {                                        // the bulk store that last read this staging tile must be done reading it
-      if (lane == 0) { if (p.epi_stride) tma_store_wait_read1(); else tma_store_wait_read(); }
+      // ... and with an aux block, also the store that last read the OTHER tile, which the prefetch below is about to overwrite
+      const bool all = p.epi_stride == 0 || (has_aux && blk + 1 < NBLK);
+      if (lane == 0) { if (all) tma_store_wait_read(); else tma_store_wait_read1(); }
       __syncwarp();
     }
     if (blk + 1 < NBLK) {
@@ -350,6 +352,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, const CUten
   const int c_begin = col_half * (BN / 2);
   if (p.bias && et < BN) bias_tile[et] = (n_base + et < p.N) ? __ldg(p.bias + n_base + et) : 0.f;
   const bool staged16 = !out_f32 && p.vec_ok;
+  if (staged16 && p.tma_store && (p.residual || p.mask)) {
+    // the first staging tile receives this tile's first aux block: the bulk store that last read it (NBLK stores ago) must be done
+    if (lane == 0) { if (BN / 2 / 64 >= 2 && p.epi_stride) tma_store_wait_read1(); else tma_store_wait_read(); }
+    __syncwarp();
+  }
   if (staged16) epi_issue_aux(p, stage, row0, n_base + c_begin, lane);
   asm volatile("bar.sync 1, 256;" ::: "memory");             // bias slice visible to all epilogue warps
   mbar_wait(full_bar, full_phase);
@@ -698,6 +705,7 @@ uint32_t g_dbg_mn_lbo = 0, g_dbg_mn_sbo = 0, g_dbg_mn_kadv = 0;
 
 bool g_dbg_disable_pair = false;     // b200f_debug_set(3, 1): force the single-CTA kernel (A/B testing)
 bool g_dbg_no_tma_store = false;     // b200f_debug_set(8, 1): LDS + STG copy-out instead of bulk tensor stores (A/B testing)
+bool g_dbg_no_tma_store_aux = false; // b200f_debug_set(11, 1): launches with a residual / mask block keep the LDS + STG copy-out (A/B testing)
 bool g_dbg_six_stages = false;       // b200f_debug_set(7, 1): 6-stage / one-staging-tile pair kernel for launches without an aux block.
                                      // Measured no faster than 5 stages on any MulT shape (profiles/r01_e): the ring depth is not the limiter.
 
@@ -782,7 +790,10 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
   p.alpha = a.alpha; p.flags = a.flags;
   p.vec_ok = vec_ok ? 1 : 0;
   // bf16 output, nothing to prefetch into the staging tiles, full 64-column blocks: the epilogue stores through TMA
-  p.tma_store = (!out_f32 && vec_ok && !a.residual && !a.relu_mask && a.N % 64 == 0 && !g_dbg_no_tma_store) ? 1 : 0;
+  // (round 2: also with a residual / ReLU-mask block -- it is prefetched into the staging tile by cp.async, consumed into registers,
+  //  and the tile then leaves through the bulk store like a plain one; b200f_debug_set(11, 1) restores LDS + STG for those launches)
+  const bool has_aux = a.residual || a.relu_mask;
+  p.tma_store = (!out_f32 && vec_ok && (!has_aux || !g_dbg_no_tma_store_aux) && a.N % 64 == 0 && !g_dbg_no_tma_store) ? 1 : 0;
   CUtensorMap tc;
   memset(&tc, 0, sizeof(tc));
   if (p.tma_store) {

@@ -23,10 +23,13 @@ ap.add_argument("--only", default="")
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--filter", default="")
 ap.add_argument("--no-tma-store", action="store_true", help="A/B: LDS + STG copy-out instead of bulk tensor stores (b200f_debug_set(8, 1))")
+ap.add_argument("--no-tma-aux", action="store_true", help="A/B: GEMMs with a residual / ReLU-mask block keep the LDS + STG copy-out (b200f_debug_set(11, 1))")
 ap.add_argument("--six-stages", action="store_true", help="A/B: 6-stage pair GEMM for launches without an aux block (b200f_debug_set(7, 1))")
 args = ap.parse_args()
 if args.no_tma_store:
     pkg._lib.lib().b200f_debug_set(8, 1)
+if args.no_tma_aux:
+    pkg._lib.lib().b200f_debug_set(11, 1)
 if args.six_stages:
     pkg._lib.lib().b200f_debug_set(7, 1)
 dev = torch.device("cuda")
@@ -71,6 +74,15 @@ if args.only in ("", "gemm"):
         cases.append((f"{name}_dgrad M{M} N{k_in} K{n_out}", 2.0 * M * n_out * k_in,
                       lambda dy=dy, w=w, dxout=dxout: K.linear_dgrad(dy, w, out=dxout),
                       lambda dy=dy, w=w: torch.matmul(dy, w)))
+        if name == "ffn1":        # FFN1 input gradient + the residual path (K = 2048 -> N = 512, residual block in the epilogue)
+            cases.append((f"{name}_dgrad_res M{M} N{k_in} K{n_out}", 2.0 * M * n_out * k_in,
+                          lambda dy=dy, w=w, dxout=dxout: K.linear_dgrad(dy, w, out=dxout, residual=res512),
+                          lambda dy=dy, w=w: torch.matmul(dy, w)))
+        if name == "ffn2":        # FFN2 input gradient with the ReLU mask of the stored hidden layer in the epilogue (K = 512 -> N = 2048)
+            cs = torch.zeros(k_in, device=dev)
+            cases.append((f"{name}_dgrad_mask M{M} N{k_in} K{n_out}", 2.0 * M * n_out * k_in,
+                          lambda dy=dy, w=w, dxout=dxout, cs=cs: K.linear_dgrad(dy, w, out=dxout, relu_mask=x2048, colsum=cs),
+                          lambda dy=dy, w=w: torch.matmul(dy, w)))
         cases.append((f"{name}_wgrad M{n_out} N{k_in} K{M}", 2.0 * M * n_out * k_in,
                       lambda dy=dy, xin=xin, dw=dw: K.linear_wgrad(dy, xin, dw),
                       lambda dy=dy, xin=xin: torch.matmul(dy.t(), xin)))
@@ -111,5 +123,5 @@ if args.only in ("", "attn"):
         print(name, {k_: round(v_, 3) for k_, v_ in out[name].items()}, flush=True)
 
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-tag = args.only or "all"
+tag = (args.only or "all") + ("_no_tma_aux" if args.no_tma_aux else "")
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"microbench_{tag}.json"), "w"), indent=1)

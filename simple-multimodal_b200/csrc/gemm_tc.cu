@@ -152,6 +152,10 @@ __device__ __forceinline__ void red_add_v4(float* dst, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+__device__ __forceinline__ void red_add_v2(float* dst, float x, float y) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(x), "f"(y) : "memory");
+}
+
 // Prefetch the 32 x 64 aux (residual, else mask) block at (row0, col0) into `stage`; always commits one (maybe empty) group.
 __device__ __forceinline__ void epi_issue_aux(const GemmTcParams& p, uint8_t* stage, long long row0, int col0, int lane) {
   const bf16* aux = p.residual ? p.residual : p.mask;
@@ -283,15 +287,14 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, const 
     if (EXTRAS && p.colsum) {
       // bias gradient: column sums of the 32 x 64 block just staged (the rounded values that were stored).  A lane owns
       // columns 2*lane, 2*lane+1 (one conflict-free word per row); even lanes collect 4 columns and issue one vector RED.
-      float a0 = 0.f, a1 = 0.f;
+      // (round 2: on the warp-level tensor path -- ONES x tile -- instead of a 32-row LDS loop per lane; ptx.cuh)
       const int nr = p.M - row0 < 32 ? int(p.M - row0) : 32;
-      for (int rr = 0; rr < nr; ++rr) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(st + sw128_offset(rr, lane >> 2) + (lane & 3) * 4);
-        a0 += __uint_as_float(w << 16);
-        a1 += __uint_as_float(w & 0xFFFF0000u);
+      float cs[8][2];
+      colsum32x64_hmma(st, nr, lane, cs);
+      if (lane < 4) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) red_add_v2(p.colsum + col0 + nt * 8 + 2 * lane, cs[nt][0], cs[nt][1]);
       }
-      const float b0 = __shfl_down_sync(0xffffffffu, a0, 1), b1 = __shfl_down_sync(0xffffffffu, a1, 1);
-      if (!(lane & 1)) red_add_v4(p.colsum + col0 + 2 * lane, make_float4(a0, a1, b0, b1));
     }
     __syncwarp();
   }

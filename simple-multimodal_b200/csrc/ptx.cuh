@@ -254,6 +254,41 @@ __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
 }
 
 
+// ---------------------------------------------------------------- column sums of a staged bf16 tile on the warp-level tensor path
+// s[c] = sum_{r < rows_valid} T[r][c] for a [32 rows x 64 bf16] tile in the SWIZZLE_128B staging layout (sw128_offset), as
+// D = ONES(16x16) * T(16 rows x 8 cols) on mma.sync.m16n8k16 (fp32 accumulate: exact sums of the stored bf16 values) -- 8 ldmatrix +
+// 16 HMMA per tile instead of 32 LDS + 64 unpack/add per lane (the loop that made the bias-gradient epilogues issue-bound).
+// Returns, in lanes 0..3 (t = lane), out[nt][0..1] = the sums of columns 8*nt + 2*t, + 1; other lanes hold copies of other rows of D
+// (all rows of D are equal).  Rows >= rows_valid are excluded by zeroing their entries of the ONES operand.
+__device__ __forceinline__ void colsum32x64_hmma(const uint8_t* tile, int rows_valid, int lane, float (&out)[8][2]) {
+  const uint32_t base = smem_u32(tile);
+  const int t = lane & 3, mi = lane >> 3, r = lane & 7;
+  float acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    // A fragment of ONES restricted to valid rows: a0/a1 hold k = 2t, 2t+1; a2/a3 hold k = 2t+8, 2t+9 (k = row of the tile - 16*ks)
+    const int k0 = ks * 16 + 2 * t;
+    const uint32_t lo = (k0 < rows_valid ? 0x3F80u : 0u) | (k0 + 1 < rows_valid ? 0x3F800000u : 0u);
+    const uint32_t hi = (k0 + 8 < rows_valid ? 0x3F80u : 0u) | (k0 + 9 < rows_valid ? 0x3F800000u : 0u);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b0, b1, b2, b3;
+      const uint32_t addr = base + sw128_offset(uint32_t(ks * 16 + (mi & 1) * 8 + r), uint32_t(np * 2 + (mi >> 1)));
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+f"(acc[2 * np][0]), "+f"(acc[2 * np][1]), "+f"(acc[2 * np][2]), "+f"(acc[2 * np][3])
+                   : "r"(lo), "r"(lo), "r"(hi), "r"(hi), "r"(b0), "r"(b1));
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+f"(acc[2 * np + 1][0]), "+f"(acc[2 * np + 1][1]), "+f"(acc[2 * np + 1][2]), "+f"(acc[2 * np + 1][3])
+                   : "r"(lo), "r"(lo), "r"(hi), "r"(hi), "r"(b2), "r"(b3));
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) { out[nt][0] = acc[nt][0]; out[nt][1] = acc[nt][1]; }
+}
+
 // ---------------------------------------------------------------- register reallocation between warpgroups
 // All four warps of a warpgroup (warps 4g..4g+3) must execute the same one.  The softmax warpgroups of the attention kernels
 // keep a whole score row (128 fp32) in registers and need room to batch MUFU/FFMA2 work; the TMA / MMA warps need ~32.

@@ -346,12 +346,13 @@ class Runner:
         if sampler is not None:
             sampler.mark()
         e0.record()
-        t_host = time.perf_counter()
+        t_host, c_host = time.perf_counter(), time.process_time()
         for _ in range(steps):
             self.step(self.resident)
-        host_issue_ms = (time.perf_counter() - t_host) * 1e3 / steps     # host time to ISSUE a step (no sync inside): if it approaches
-        e1.record()                                                      # ms_per_step the run is launch-bound on the host, not GPU-bound
-        self.sync_all()
+        host_issue_ms = (time.perf_counter() - t_host) * 1e3 / steps     # wall time the host spent inside the issue loop (no sync inside):
+        self.host_cpu_ms = (time.process_time() - c_host) * 1e3 / steps  # it includes waiting on a full launch queue; the CPU time next to
+        e1.record()                                                      # it is what the host really works per step -- if THAT approaches
+        self.sync_all()                                                  # ms_per_step the run is launch-bound on the host, not GPU-bound
         counted = (self.pkg._lib.launch_count() - l0) // steps
         return e0.elapsed_time(e1) / steps, host_issue_ms, self.launches_per_step(counted)
 
@@ -483,7 +484,7 @@ def main():
     else:
         ms_prof, gemm_ms, gemm_flops, n_gemm = run.gemm_profile_leg(max(1, min(args.steps, 5)))
     ms, ms_e2e = reduce_max([ms, ms_e2e], world, dev)
-    issue, h2d_bytes = run.issue, run.h2d_bytes
+    issue, h2d_bytes, host_cpu_ms = run.issue, run.h2d_bytes, getattr(run, "host_cpu_ms", None)
     run.close()
 
     # ---- the other GPU-sized BASELINE configs, value + e2e only (never allowed to take the primary line down)
@@ -519,7 +520,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": args.workload, "head": kind, "batch_per_gpu": batch, "global_batch": b_global, "seq_lens": lens,
                        "hidden": H, "heads": HEADS, "dropout": args.dropout, "modality_dropout": 0.1 if kind == "hierarchical" else None,
-                       "parallelism": f"dp{world}", "warmup_steps_run": warm_done, "host_issue_ms_per_step": host_issue_ms, "issue": issue,
+                       "parallelism": f"dp{world}", "warmup_steps_run": warm_done, "host_issue_ms_per_step": host_issue_ms, "host_cpu_ms_per_step": host_cpu_ms, "issue": issue,
                        "collectives_per_step": (["all_gather(z)", "all_reduce(loss)", "all_gather(lse)", "all_reduce(grads, flat fp32 bucket)"]
                                                 if world > 1 and kind in ("contrastive", "hierarchical") else
                                                 (["all_reduce(grads, flat fp32 bucket)"] if world > 1 else [])),

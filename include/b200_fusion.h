@@ -118,6 +118,10 @@ typedef struct {
    * and backward (counter-based hash of (b, head, query, key), see csrc/common.cuh) -- pass the same values to both.
    * dropout_p = 0 disables it.  LSE is the log-sum-exp of the UNdropped scores. */
   float dropout_p; uint32_t drop_seed_lo, drop_seed_hi;
+  /* forward only, optional (nullable; bf16 / head dim 64 kernels): fp32 [B, H*D] accumulators, += the column sums over the Lq
+   * rows of each (b, head) of the O that is stored -- the numerator of `.mean(dim=1)` of the attended features
+   * (fusion_layers.py:166-168) straight out of the attention epilogue, so no separate pass re-reads O. */
+  float* pool_sum;
 } b200f_attn_args;
 int b200f_attn_fwd(const b200f_attn_args* args, void* stream);
 int b200f_attn_bwd(const b200f_attn_args* args, void* stream);

@@ -48,7 +48,8 @@ class AttnArgs(C.Structure):
                 ("dV", C.c_void_p), ("lddv", C.c_int64),
                 ("delta", C.c_void_p),
                 ("dbq", C.c_void_p), ("dbk", C.c_void_p), ("dbv", C.c_void_p),
-                ("dropout_p", C.c_float), ("drop_seed_lo", C.c_uint32), ("drop_seed_hi", C.c_uint32)]
+                ("dropout_p", C.c_float), ("drop_seed_lo", C.c_uint32), ("drop_seed_hi", C.c_uint32),
+                ("pool_sum", C.c_void_p)]
 
 
 _lib = None

@@ -154,6 +154,7 @@ int b200f_attn_fwd(const b200f_attn_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a->dtype == B200F_BF16 && a->D == 64 && !b200f::g_force_simt_attention)      // one side <= 32 rows: the HBM-bound narrow kernels
     return b200f::attn_narrow_kind(*a) ? b200f::attn_fwd_narrow(*a, st) : b200f::attn_fwd_tc(*a, st);
+  if (a->pool_sum) return b200f::fail(B200F_ERR_UNSUPPORTED, "attention: pool_sum needs the bf16 / head-dim-64 kernels");
   return b200f::attn_fwd_simt_dispatch(*a, st);
 }
 

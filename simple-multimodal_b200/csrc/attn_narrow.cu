@@ -42,6 +42,7 @@ struct NarrowParams {
   bf16* dK; long long lddk;
   bf16* dV; long long lddv;
   float* dbq; float* dbk; float* dbv;
+  float* pool;                          // forward, optional [B, H*64] fp32: += column sums of the stored O
   uint32_t drop_thr, drop_seed_lo, drop_seed_hi;
   float inv_keep;
 };
@@ -243,7 +244,13 @@ __global__ void __launch_bounds__(128) attn_nk_fwd_kernel(const NarrowParams p) 
     __syncwarp();
     stage_tile(Qs, r0, o, ik / l0, ik / l1, lane);      // this warp's own (already consumed) query rows
     __syncwarp();
-    store_tile(Qs, r0, p.O, p.ldo, (long long)b * p.Lq, q0 + r0, p.Lq, h, lane);
+    float ps0 = 0.f, ps1 = 0.f;
+    store_tile(Qs, r0, p.O, p.ldo, (long long)b * p.Lq, q0 + r0, p.Lq, h, lane, p.pool ? &ps0 : nullptr, p.pool ? &ps1 : nullptr);
+    if (p.pool) {
+      float* dst = p.pool + ((long long)b * p.H + h) * HD + 2 * lane;
+      atomicAdd(dst, ps0);
+      atomicAdd(dst + 1, ps1);
+    }
   }
 }
 
@@ -647,6 +654,11 @@ __global__ void __launch_bounds__(128, 2) attn_nq_fwd_kernel(const NarrowParams 
       *reinterpret_cast<uint4*>(dst) = o0;
       *reinterpret_cast<uint4*>(dst + 8) = o1;
       if ((tid & 3) == 0) p.LSE[((long long)b * p.H + h) * p.Lq + row] = mm * p.scale + logf(lt);
+      if (p.pool) {                                        // <= 32 rows per (b, h): a few atomics on the rounded values that were stored
+        float* pd = p.pool + ((long long)b * p.H + h) * HD + c0;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) atomicAdd(pd + e, bf16_round(acc[e] * inv));
+      }
     }
   }
 }
@@ -899,6 +911,7 @@ NarrowParams make_params(const b200f_attn_args& a) {
   p.dK = static_cast<bf16*>(a.dK); p.lddk = a.lddk;
   p.dV = static_cast<bf16*>(a.dV); p.lddv = a.lddv;
   p.dbq = a.dbq; p.dbk = a.dbk; p.dbv = a.dbv;
+  p.pool = a.pool_sum;
   p.drop_thr = drop_threshold(a.dropout_p); p.drop_seed_lo = a.drop_seed_lo; p.drop_seed_hi = a.drop_seed_hi;
   p.inv_keep = 1.f / (1.f - a.dropout_p);
   return p;

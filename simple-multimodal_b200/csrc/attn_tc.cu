@@ -39,6 +39,7 @@ struct AttnTcParams {
   bf16* dK; long long lddk;
   bf16* dV; long long lddv;
   float* dbq; float* dbk; float* dbv;   // optional [H*64] fp32 accumulators: column sums of dQ / dK / dV (in-proj bias gradients)
+  float* pool;                           // forward, optional [B, H*64] fp32: += column sums of the stored O over the queries of (b, h)
   // attention-probability dropout (persistent kernels, DROP = true instantiation): keep iff hash >= drop_thr, kept scaled by inv_keep
   uint32_t drop_thr, drop_seed_lo, drop_seed_hi;
   float inv_keep;
@@ -70,15 +71,16 @@ __device__ __forceinline__ void store_rows64(uint32_t taddr, uint8_t* stage, bf1
     if (r < rows_valid)
       *reinterpret_cast<uint4*>(gbase + (long long)r * ld + cchunk * 8) = *reinterpret_cast<const uint4*>(stage + sw128_offset(r, cchunk));
   }
-  if (colsum) {                          // lane owns columns 2*lane, 2*lane+1: one conflict-free 4-byte word per row
-    float a0 = 0.f, a1 = 0.f;
+  if (colsum) {                          // ONES x tile on the warp-level tensor path (ptx.cuh): lanes 0..3 hold columns 8*nt + 2*lane, +1
     const int nr = rows_valid < 32 ? rows_valid : 32;
-    for (int r = 0; r < nr; ++r) {
-      const uint32_t w = *reinterpret_cast<const uint32_t*>(stage + sw128_offset(r, lane >> 2) + (lane & 3) * 4);
-      a0 += __uint_as_float(w << 16);
-      a1 += __uint_as_float(w & 0xFFFF0000u);
+    if (nr > 0) {                        // warp-uniform
+      float cs[8][2];
+      colsum32x64_hmma(stage, nr, lane, cs);
+      if (lane < 4) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) { atomicAdd(colsum + nt * 8 + 2 * lane, cs[nt][0]); atomicAdd(colsum + nt * 8 + 2 * lane + 1, cs[nt][1]); }
+      }
     }
-    if (nr > 0) { atomicAdd(colsum + 2 * lane, a0); atomicAdd(colsum + 2 * lane + 1, a1); }
   }
   __syncwarp();
 }
@@ -263,7 +265,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     // O / l -> bf16 -> this warp's 32 x 128 B slice of the (now free) P tile -> full 128-byte lines to global
     if (qrow < p.Lq) p.LSE[((long long)b * p.H + h) * p.Lq + qrow] = m * p.scale + logf(l);
     store_rows64(t_o + lane_addr, smem + FwdSmem::P_OFF + grp * (32 * 128), p.O + ((long long)b * p.Lq + q0 + grp * 32) * p.ldo + h * HD, p.ldo,
-                 p.Lq - (q0 + grp * 32), lane, inv);
+                 p.Lq - (q0 + grp * 32), lane, inv, p.pool ? p.pool + ((long long)b * p.H + h) * HD : nullptr);
   }
 
   tc_fence_before();
@@ -540,7 +542,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       if (qrow < p.Lq) p.LSE[((long long)b * p.H + h) * p.Lq + qrow] = m * p.scale + logf(l);
       // O / l -> bf16 -> this warp's 32 x 128 B slice of the (now free) P_t tile -> full 128-byte lines to global
       store_rows64(t_o + lane_addr, prow + grp * (32 * 128), p.O + ((long long)b * p.Lq + q0 + grp * 32) * p.ldo + h * HD, p.ldo,
-                   p.Lq - (q0 + grp * 32), lane, (DROP ? p.inv_keep : 1.f) / l);
+                   p.Lq - (q0 + grp * 32), lane, (DROP ? p.inv_keep : 1.f) / l, p.pool ? p.pool + ((long long)b * p.H + h) * HD : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[t]);
@@ -578,6 +580,7 @@ int attn_fwd_tc(const b200f_attn_args& a, cudaStream_t st) {
   AttnTcParams p = {};
   p.B = a.B; p.H = a.H; p.Lq = a.Lq; p.Lk = a.Lk; p.scale = a.scale;
   p.O = static_cast<bf16*>(a.O); p.ldo = a.ldo; p.LSE = a.LSE;
+  p.pool = a.pool_sum;
   static bool configured = false;
   if (!configured) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));

@@ -183,7 +183,12 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, const 
   const int crow = lane >> 3, cchunk = lane & 7;             // coalesced phase: 4 rows x 8 chunks per instruction
   const bool has_aux = p.residual || p.mask;
   const uint32_t rk = (EXTRAS && p.drop_thr) ? drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, uint32_t(row)) : 0u;
-  const uint64_t al2 = f2_pack(p.alpha, p.alpha);
+  // dropout without a residual: 1/(1-p) rides on alpha and on the bias slice (pre-scaled by epilogue_tile), relu commutes with the
+  // positive scale -- the per-element work is then one select
+  const bool fold_keep = EXTRAS && p.drop_thr && !p.residual;
+  const float al = fold_keep ? p.alpha * p.inv_keep : p.alpha;
+  const uint64_t al2 = f2_pack(al, al);
+  const float keep_mul = fold_keep ? 1.f : p.inv_keep;
 #pragma unroll 1
   for (int blk = 0; blk < NBLK; ++blk) {
     const int c0 = c_begin + blk * 64;
@@ -252,7 +257,7 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, const 
         if (EXTRAS && p.drop_thr) {                          // nn.Dropout behind Linear(+ReLU): mask from (seed, row, column)
           const uint32_t cc = uint32_t(col0 + h * 32 + g * 8) * kDropColMul;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = drop_keep_c(rk, cc + uint32_t(j) * kDropColMul, p.drop_thr) ? v[j] * p.inv_keep : 0.f;
+          for (int j = 0; j < 8; ++j) v[j] = drop_keep_c(rk, cc + uint32_t(j) * kDropColMul, p.drop_thr) ? v[j] * keep_mul : 0.f;
         }
         if (p.mask) {
           if (p.residual) {                                  // both present: the mask comes straight from global
@@ -353,7 +358,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, const CUten
   const bool accum = (p.flags & B200F_EPI_ACCUM) != 0;
   const bool relu = (p.flags & B200F_EPI_RELU) != 0;
   const int c_begin = col_half * (BN / 2);
-  if (p.bias && et < BN) bias_tile[et] = (n_base + et < p.N) ? __ldg(p.bias + n_base + et) : 0.f;
+  const bool staged16_ = !((p.flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) != 0) && p.vec_ok;
+  const float bias_mul = (p.drop_thr && !p.residual && staged16_) ? p.inv_keep : 1.f;      // see fold_keep in epilogue_tile_bf16
+  if (p.bias && et < BN) bias_tile[et] = (n_base + et < p.N) ? __ldg(p.bias + n_base + et) * bias_mul : 0.f;
   const bool staged16 = !out_f32 && p.vec_ok;
   if (staged16 && p.tma_store && (p.residual || p.mask)) {
     // the first staging tile receives this tile's first aux block: the bulk store that last read it (NBLK stores ago) must be done

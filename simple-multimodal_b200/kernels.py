@@ -175,6 +175,10 @@ def relu_bwd(dy: Tensor, ref: Tensor) -> Tensor:
     return dx
 
 
+def zeros_f32(shape, device) -> Tensor:
+    return torch.zeros(shape, device=device, dtype=torch.float32)
+
+
 def cast_to_bf16(src: Tensor, scale: float = 1.0, out: Optional[Tensor] = None) -> Tensor:
     src = src.contiguous()
     dst = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16) if out is None else out
@@ -310,17 +314,27 @@ def _tokens(x: Tensor):
     return x.data_ptr(), x.stride(1)
 
 
-def attn_fwd(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float, out: Optional[Tensor] = None, dropout=None):
-    require_cuda(q, k, v)
+def attn_pool_supported(q: Tensor, heads: int) -> bool:
+    """whether attn_fwd can accumulate the pooled output (`pool_sum=`) for this operand: the bf16 / head-dim-64 kernels"""
+    return q.dtype == torch.bfloat16 and q.size(-1) // heads == 64
+
+
+def attn_fwd(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float, out: Optional[Tensor] = None, dropout=None,
+             pool_sum: Optional[Tensor] = None):
+    """`pool_sum` (optional, fp32 [B, H*D], contiguous): += sum over the Lq rows of the stored output per (batch, column)."""
+    require_cuda(q, k, v, pool_sum)
     B, Lq, W = q.shape
     Lk = k.size(1)
     D = W // heads
+    if pool_sum is not None and (pool_sum.dtype != torch.float32 or not pool_sum.is_contiguous() or pool_sum.shape != (B, W) or not attn_pool_supported(q, heads)):
+        raise B200FusionError("attn_fwd: pool_sum must be a contiguous float32 [B, H*D] accumulator (bf16, head dim 64 only)")
     if out is None:
         out = torch.empty((B, Lq, W), device=q.device, dtype=q.dtype)
     lse = torch.empty((B, heads, Lq), device=q.device, dtype=torch.float32)
     (qp, ldq), (kp, ldk), (vp, ldv), (op, ldo) = _tokens(q), _tokens(k), _tokens(v), _tokens(out)
     args = L.AttnArgs(B=B, H=heads, Lq=Lq, Lk=Lk, D=D, Q=qp, ldq=ldq, K=kp, ldk=ldk, V=vp, ldv=ldv, O=op, ldo=ldo,
-                      LSE=lse.data_ptr(), scale=scale, dtype=dtype_code(q.dtype), **_drop_fields(dropout))
+                      LSE=lse.data_ptr(), scale=scale, dtype=dtype_code(q.dtype), pool_sum=None if pool_sum is None else pool_sum.data_ptr(),
+                      **_drop_fields(dropout))
     check(lib().b200f_attn_fwd(C.byref(args), stream_ptr()), "b200f_attn_fwd")
     return out, lse
 

@@ -83,6 +83,16 @@ if args.only in ("", "gemm"):
             cases.append((f"{name}_dgrad_mask M{M} N{k_in} K{n_out}", 2.0 * M * n_out * k_in,
                           lambda dy=dy, w=w, dxout=dxout, cs=cs: K.linear_dgrad(dy, w, out=dxout, relu_mask=x2048, colsum=cs),
                           lambda dy=dy, w=w: torch.matmul(dy, w)))
+            cases.append((f"{name}_dgrad_maskonly M{M} N{k_in} K{n_out}", 2.0 * M * n_out * k_in,
+                          lambda dy=dy, w=w, dxout=dxout: K.linear_dgrad(dy, w, out=dxout, relu_mask=x2048),
+                          lambda dy=dy, w=w: torch.matmul(dy, w)))
+            cases.append((f"{name}_dgrad_colsumonly M{M} N{k_in} K{n_out}", 2.0 * M * n_out * k_in,
+                          lambda dy=dy, w=w, dxout=dxout, cs=cs: K.linear_dgrad(dy, w, out=dxout, colsum=cs),
+                          lambda dy=dy, w=w: torch.matmul(dy, w)))
+        if name == "ffn1":        # FFN1 forward with the hidden-layer dropout generated in the epilogue (the training configuration)
+            cases.append((f"{name}_fwd_dropout M{M} N{n_out} K{k_in}", 2.0 * M * n_out * k_in,
+                          lambda xin=xin, w=w, bias=bias, yout=yout: K.linear_fwd(xin, w, bias, relu=True, out=yout, dropout=(0.1, 11, 22)),
+                          lambda xin=xin, w=w: torch.matmul(xin, w.t())))
         cases.append((f"{name}_wgrad M{n_out} N{k_in} K{M}", 2.0 * M * n_out * k_in,
                       lambda dy=dy, xin=xin, dw=dw: K.linear_wgrad(dy, xin, dw),
                       lambda dy=dy, xin=xin: torch.matmul(dy.t(), xin)))

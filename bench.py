@@ -275,7 +275,8 @@ class Runner:
         if multi_chunk:
             self.issue = "per-chunk CUDA graphs inside the head (ChunkGraphEngine); small heads / collectives issued eagerly"
             return
-        if world > 1 and kind in ("contrastive", "hierarchical"):
+        if world > 1 and kind in ("contrastive", "hierarchical") and os.environ.get("B200F_GRAPH_COLLECTIVES", "0") != "1":
+            # (capturing the step's NCCL collectives into the graph is opt-in: B200F_GRAPH_COLLECTIVES=1)
             self.issue = "eager (NCCL all-gather inside the step)"
             return
         try:

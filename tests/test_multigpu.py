@@ -113,8 +113,8 @@ def _worker_hier(rank, port, Bl, dtype_name, ret):
         bucket.all_reduce()
         torch.cuda.synchronize()
         ret[rank] = dict(losses={k: float(v.detach()) for k, v in out["contrastive_losses"].items()},
-                         fused=out["fused_features"].float().cpu(), dx=[x.grad.float().cpu() for x in xs],
-                         pg={k: p.grad.float().cpu() for k, p in head.named_parameters()},
+                         fused=out["fused_features"].detach().float().cpu(), dx=[x.grad.detach().float().cpu() for x in xs],
+                         pg={k: p.grad.detach().float().cpu() for k, p in head.named_parameters()},
                          engine=head.mult_fusion._engine is not None)
     finally:
         dist.destroy_process_group()

@@ -402,7 +402,18 @@ class Runner:
             self.mult.release_graphs()
             torch.cuda.empty_cache()
         K.prealloc_profile_events(2 * 100 * max(1, self.batch // 256 + 1) * steps + 2048)
-        self.eager_step(self.resident)                    # untimed: the eager path's allocations happen here
+        self.profile_chunk = None if self.mult is None else int(self.mult.chunk_size)
+        try:
+            self.eager_step(self.resident)                # untimed: the eager path's allocations happen here
+        except torch.OutOfMemoryError:                    # the eager path keeps its temporaries outside any graph pool: retry with smaller chunks
+            if self.mult is None:
+                raise
+            for p in self.params:
+                p.grad = None
+            torch.cuda.empty_cache()
+            self.mult.chunk_size = self.profile_chunk = 256
+            self.bucket.attach()
+            self.eager_step(self.resident)
         K.GEMM_PROFILE = []
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.sync_all()
@@ -486,6 +497,7 @@ def main():
         ms_prof, gemm_ms, gemm_flops, n_gemm = run.gemm_profile_leg(max(1, min(args.steps, 5)))
     ms, ms_e2e = reduce_max([ms, ms_e2e], world, dev)
     issue, h2d_bytes, host_cpu_ms = run.issue, run.h2d_bytes, getattr(run, "host_cpu_ms", None)
+    profile_chunk = getattr(run, "profile_chunk", None)
     run.close()
 
     # ---- the other GPU-sized BASELINE configs, value + e2e only (never allowed to take the primary line down)
@@ -542,7 +554,8 @@ def main():
                                                                           f'{traffic["algorithmic_bytes_per_launch"]} ({traffic["source"]})',
                          "peak_source": pk["src"], "launches_per_step": n_gemm, "kernel_ms_per_step": gemm_ms,
                          "share_of_step": gemm_ms / ms_prof if ms_prof else None, "instrumented_ms_per_step": ms_prof,
-                         "note": "events around every tcgen05 GEMM launch in a separate eagerly issued pass of the same step"},
+                         "note": "events around every tcgen05 GEMM launch in a separate eagerly issued pass of the same step"
+                                 + (f" (MulT chunk {profile_chunk})" if profile_chunk else "")},
         }
         if secondary:
             line["secondary"] = secondary

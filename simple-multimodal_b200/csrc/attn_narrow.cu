@@ -471,6 +471,237 @@ __global__ void __launch_bounds__(128, 2) attn_nk_bwd_kernel(const NarrowParams 
 }
 
 // ==============================================================================================================================
+// NK backward, version 2 ("d-split", the default): the first version above keeps dK and dV (32 x 64 fp32 each) in every warp's
+// registers -- 255 registers per thread, two CTAs (8 warps) per SM, 45 % issue utilisation under ncu because nothing hides the
+// ldmatrix -> mma and exp latencies.  Here a tile is processed in two phases:
+//   A  warp w owns query rows 16w..16w+15 of the 64-row tile (as before): S, dP, Pd, dS in registers, dQ = dS K stored at once,
+//      and Pd / dS written as bf16 [64 rows x 32 keys] tiles to shared memory;
+//   B  warp w owns the 16-wide slice d = 16w..16w+15 of dK / dV: dV[:, slice] += Pd^T dO[:, slice] and dK[:, slice] += dS^T Q[:, slice]
+//      over ALL 64 rows of the tile (A operands = the shared Pd / dS tiles read transposed by ldmatrix, no movmatrix), 32 fp32
+//      accumulator registers per thread instead of 128.
+// Same number of HMMAs; ~150 registers -> three CTAs per SM with a 2-deep ring; no cross-warp reduction at the end (every warp owns
+// its own columns of dK / dV, summed in a fixed order: bit-reproducible).
+// ==============================================================================================================================
+constexpr int NKB2_ST = 2;
+constexpr int NKB2_PS = 64 * 64;                           // one [64 rows x 32 keys] bf16 tile (64-byte rows)
+constexpr int NKB2_SMEM = 2 * NARROW * 128 + NKB2_ST * NKB_STAGE + 2 * NKB2_PS + 256;
+
+__device__ __forceinline__ uint32_t swz64(int row, int chunk) {   // [rows x 64 B] tile, 16-byte chunks XOR-swizzled by (row / 2) % 4
+  return uint32_t(row) * 64u + (uint32_t((chunk ^ (row >> 1)) & 3) << 4);
+}
+
+template <bool DROP>
+__global__ void __launch_bounds__(128, 3) attn_nk_bwd2_kernel(const NarrowParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* Ks = smem;
+  uint8_t* Vs = smem + NARROW * 128;
+  uint8_t* ring = smem + 2 * NARROW * 128;
+  uint8_t* Pt = ring + NKB2_ST * NKB_STAGE;                // Pd  [64 x 32] bf16
+  uint8_t* St = Pt + NKB2_PS;                              // dS  [64 x 32] bf16
+  float* dbq_s = reinterpret_cast<float*>(St + NKB2_PS);   // 64 floats
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const uint32_t sk = smem_u32(Ks), sv = smem_u32(Vs), sring = smem_u32(ring), spt = smem_u32(Pt), sst = smem_u32(St);
+  const int n_tiles = (p.Lq + 63) / 64;
+  const long long qtok = (long long)b * p.Lq;
+  auto issue = [&](int i) {
+    if (i < n_tiles) {
+      const uint32_t st = sring + (i % NKB2_ST) * NKB_STAGE;
+      load_rows(st, p.Q, p.ldq, qtok, i * 64, p.Lq, 64, h, tid, 128);
+      load_rows(st + NKB_TILE, p.dO, p.lddo, qtok, i * 64, p.Lq, 64, h, tid, 128);
+      load_rows(st + 2 * NKB_TILE, p.O, p.ldo, qtok, i * 64, p.Lq, 64, h, tid, 128);
+    }
+    cp_commit();
+  };
+  load_rows(sk, p.K, p.ldk, (long long)b * p.Lk, 0, p.Lk, NARROW, h, tid, 128);
+  load_rows(sv, p.V, p.ldv, (long long)b * p.Lk, 0, p.Lk, NARROW, h, tid, 128);
+  issue(0);
+  if (tid < 64) dbq_s[tid] = 0.f;
+  float dv[2][2][4], dk[2][2][4];                          // [key m-tile][n-tile of this warp's d slice]
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { dv[mt][nt][e] = 0.f; dk[mt][nt][e] = 0.f; }
+  float dbq0 = 0.f, dbq1 = 0.f;
+  const float c = p.scale * LOG2E;
+  const long long lb = ((long long)b * p.H + h) * p.Lq;
+  const int r0 = warp * 16;
+#pragma unroll 1
+  for (int i = 0; i < n_tiles; ++i) {
+    cp_wait<0>();
+    __syncthreads();                 // tile i landed; every warp is done with phase B of tile i-1 (Pd / dS tiles and the other ring slot are free)
+    issue(i + 1);
+    uint8_t* stg = ring + (i % NKB2_ST) * NKB_STAGE;
+    const uint32_t sq = sring + (i % NKB2_ST) * NKB_STAGE, sdo = sq + NKB_TILE;
+    const uint8_t* dOt = stg + NKB_TILE;
+    uint8_t* Ot = stg + 2 * NKB_TILE;
+    // ---------------- phase A: this warp's 16 query rows (rows past Lq are zero-filled: they contribute exact zeros everywhere)
+    const int tok0 = i * 64 + r0;
+    const int row_a = tok0 + g, row_b = row_a + 8;
+    float dl0 = 0.f, dl1 = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      Vec16<bf16> x, y;
+      float fx[8], fy[8];
+      x.raw = *reinterpret_cast<const uint4*>(dOt + swz(r0 + g, 2 * t + cc));
+      y.raw = *reinterpret_cast<const uint4*>(Ot + swz(r0 + g, 2 * t + cc));
+      x.unpack(fx); y.unpack(fy);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dl0 = fmaf(fx[e], fy[e], dl0);
+      x.raw = *reinterpret_cast<const uint4*>(dOt + swz(r0 + g + 8, 2 * t + cc));
+      y.raw = *reinterpret_cast<const uint4*>(Ot + swz(r0 + g + 8, 2 * t + cc));
+      x.unpack(fx); y.unpack(fy);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dl1 = fmaf(fx[e], fy[e], dl1);
+    }
+    dl0 = quad_sum(dl0); dl1 = quad_sum(dl1);
+    const float nl0 = -(row_a < p.Lq ? p.LSE[lb + row_a] : 0.f) * LOG2E;
+    const float nl1 = -(row_b < p.Lq ? p.LSE[lb + row_b] : 0.f) * LOG2E;
+    uint32_t dsa[2][4];
+    {
+      float s[4][4], dp[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { s[nt][e] = 0.f; dp[nt][e] = 0.f; }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t a[4], a2[4], bb[4];
+        ld_a(a, sq, r0, kk, lane);
+        ld_a(a2, sdo, r0, kk, lane);
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+          ld_b_nk(bb, sk, np * 16, kk, lane);
+          mma16816(s[2 * np], a, bb[0], bb[1]);
+          mma16816(s[2 * np + 1], a, bb[2], bb[3]);
+          ld_b_nk(bb, sv, np * 16, kk, lane);
+          mma16816(dp[2 * np], a2, bb[0], bb[1]);
+          mma16816(dp[2 * np + 1], a2, bb[2], bb[3]);
+        }
+      }
+      const uint32_t rbase = uint32_t((b * p.H + h) * p.Lq);
+      const uint32_t rk0 = DROP ? drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, rbase + row_a) : 0u;
+      const uint32_t rk1 = DROP ? drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, rbase + row_b) : 0u;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float pd[4], ds[4];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = nt * 8 + 2 * t + e;
+          const bool valid = key < p.Lk;
+          const float p0 = valid ? ex2_approx(fmaf(s[nt][e], c, nl0)) : 0.f;
+          const float p1 = valid ? ex2_approx(fmaf(s[nt][2 + e], c, nl1)) : 0.f;
+          float k0 = 1.f, k1 = 1.f;
+          if (DROP) {
+            const uint32_t cm = uint32_t(key) * kDropColMul;
+            k0 = drop_keep_c(rk0, cm, p.drop_thr) ? p.inv_keep : 0.f;
+            k1 = drop_keep_c(rk1, cm, p.drop_thr) ? p.inv_keep : 0.f;
+          }
+          pd[e] = p0 * k0;
+          pd[2 + e] = p1 * k1;
+          ds[e] = p0 * (dp[nt][e] * k0 - dl0) * p.scale;
+          ds[2 + e] = p1 * (dp[nt][2 + e] * k1 - dl1) * p.scale;
+        }
+        const uint32_t plo = pack_bf16(pd[0], pd[1]), phi = pack_bf16(pd[2], pd[3]);
+        const uint32_t slo = pack_bf16(ds[0], ds[1]), shi = pack_bf16(ds[2], ds[3]);
+        dsa[nt >> 1][(nt & 1) * 2] = slo;
+        dsa[nt >> 1][(nt & 1) * 2 + 1] = shi;
+        // [row][key] bf16 tiles for phase B: this thread's two keys (4 bytes) of rows r0+g and r0+g+8
+        *reinterpret_cast<uint32_t*>(Pt + swz64(r0 + g, nt) + t * 4) = plo;
+        *reinterpret_cast<uint32_t*>(Pt + swz64(r0 + g + 8, nt) + t * 4) = phi;
+        *reinterpret_cast<uint32_t*>(St + swz64(r0 + g, nt) + t * 4) = slo;
+        *reinterpret_cast<uint32_t*>(St + swz64(r0 + g + 8, nt) + t * 4) = shi;
+      }
+    }
+    {                                // dQ = dS K for this warp's rows
+      float dq[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dq[nt][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int d4 = 0; d4 < 4; ++d4) {
+          uint32_t bb[4];
+          ld_b_kn(bb, sk, ks * 16, d4, lane);
+          mma16816(dq[2 * d4], dsa[ks], bb[0], bb[1]);
+          mma16816(dq[2 * d4 + 1], dsa[ks], bb[2], bb[3]);
+        }
+      __syncwarp();
+      stage_tile(Ot, r0, dq, 1.f, 1.f, lane);             // over this warp's own (consumed) O rows: phase B reads Q and dO of ALL rows
+      __syncwarp();
+      if (tok0 < p.Lq)
+        store_tile(Ot, r0, p.dQ, p.lddq, qtok, tok0, p.Lq, h, lane, p.dbq ? &dbq0 : nullptr, p.dbq ? &dbq1 : nullptr);
+    }
+    __syncthreads();                 // Pd / dS of all 64 rows are in shared memory
+    // ---------------- phase B: this warp's 16-wide slice of d, all 64 rows of the tile
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t bo[4], bq[4];
+      ld_b_kn(bo, sdo, ks * 16, warp, lane);              // dO[k = rows 16ks.., n = d slice]: two n-tiles
+      ld_b_kn(bq, sq, ks * 16, warp, lane);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        uint32_t ap[4], as[4];
+        const int mi = lane >> 3, r = lane & 7;
+        const int row = ks * 16 + (mi >> 1) * 8 + r, chunk = mt * 2 + (mi & 1);
+        ldsm4t(ap, spt + swz64(row, chunk));              // A = Pd^T (m = keys 16mt.., k = rows 16ks..)
+        ldsm4t(as, sst + swz64(row, chunk));
+        mma16816(dv[mt][0], ap, bo[0], bo[1]);
+        mma16816(dv[mt][1], ap, bo[2], bo[3]);
+        mma16816(dk[mt][0], as, bq[0], bq[1]);
+        mma16816(dk[mt][1], as, bq[2], bq[3]);
+      }
+    }
+  }
+  cp_wait<0>();
+  if (p.dbq) { atomicAdd(&dbq_s[2 * lane], dbq0); atomicAdd(&dbq_s[2 * lane + 1], dbq1); }
+  // dV / dK: warp w owns columns 16w..16w+15 of both; rows = keys
+  const long long ktok = (long long)b * p.Lk;
+  float csv[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, csk[2][2] = {{0.f, 0.f}, {0.f, 0.f}};     // column sums of the stored (rounded) values
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int col = h * HD + warp * 16 + nt * 8 + 2 * t;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int key = mt * 16 + g + hf * 8;
+        if (key < p.Lk) {
+          const uint32_t wv = pack_bf16(dv[mt][nt][2 * hf], dv[mt][nt][2 * hf + 1]);
+          const uint32_t wk = pack_bf16(dk[mt][nt][2 * hf], dk[mt][nt][2 * hf + 1]);
+          *reinterpret_cast<uint32_t*>(p.dV + (ktok + key) * p.lddv + col) = wv;
+          *reinterpret_cast<uint32_t*>(p.dK + (ktok + key) * p.lddk + col) = wk;
+          csv[nt][0] += __uint_as_float(wv << 16); csv[nt][1] += __uint_as_float(wv & 0xFFFF0000u);
+          csk[nt][0] += __uint_as_float(wk << 16); csk[nt][1] += __uint_as_float(wk & 0xFFFF0000u);
+        }
+      }
+    }
+  if (p.dbv || p.dbk) {
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {                 // over the 8 row groups g (lanes with equal t)
+          csv[nt][e] += __shfl_xor_sync(0xffffffffu, csv[nt][e], o);
+          csk[nt][e] += __shfl_xor_sync(0xffffffffu, csk[nt][e], o);
+        }
+        if (g == 0) {
+          const int col = h * HD + warp * 16 + nt * 8 + 2 * t + e;
+          if (p.dbv) atomicAdd(p.dbv + col, csv[nt][e]);
+          if (p.dbk) atomicAdd(p.dbk + col, csk[nt][e]);
+        }
+      }
+  }
+  __syncthreads();
+  if (p.dbq && tid < 64) atomicAdd(p.dbq + h * HD + tid, dbq_s[tid]);
+}
+
+// ==============================================================================================================================
 // NQ forward: Lq <= 32.  grid (H, B), 128 threads; 64-key tiles of {K, V} through a 4-deep ring, warp w owns keys 16w..16w+15 of
 // every tile and keeps its own running (max, sum, O[32 x 64]); the four partials are merged at the end.
 // ==============================================================================================================================
@@ -969,6 +1200,16 @@ int attn_bwd_narrow(const b200f_attn_args& a, cudaStream_t st) {
   const bool drop = p.drop_thr != 0;
   dim3 grid(a.H, a.B);
   if (attn_narrow_kind(a) == 1) {
+    if (g_attn_narrow != 2) {                              // default: the d-split kernel; b200f_debug_set(10, 2) = the first version (A/B)
+      if (drop) {
+        B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_nk_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NKB2_SMEM));
+        attn_nk_bwd2_kernel<true><<<grid, 128, NKB2_SMEM, st>>>(p);
+      } else {
+        B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_nk_bwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NKB2_SMEM));
+        attn_nk_bwd2_kernel<false><<<grid, 128, NKB2_SMEM, st>>>(p);
+      }
+      return check_launch("attn_nk_bwd2_kernel");
+    }
     if (drop) {
       B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_nk_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NKB_SMEM));
       attn_nk_bwd_kernel<true><<<grid, 128, NKB_SMEM, st>>>(p);

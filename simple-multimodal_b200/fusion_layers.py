@@ -180,8 +180,9 @@ class CrossModalTransformer(_FusionBase):
 class MultimodalTransformer(_FusionBase):
     """reference models/fusion_layers.py:93-179, executed by mult_engine.MulTFn (chunked, fused schedule)."""
 
-    chunk_size = 512            # samples per MulT chunk (~15 GB of bf16 activations at L=512/512/30, H=512; measured on the B=4096 step:
-                                # 256 -> 324.3 ms, 512 -> 318.1 ms -- fewer, larger launches: shorter GEMM tails, more items per persistent CTA)
+    chunk_size = 1024           # samples per MulT chunk (~30 GB of bf16 activations at L=512/512/30, H=512; measured on the B=4096 step:
+                                # 256 -> 324.3 ms, 512 -> 318.1 ms, 1024 -> 314.7 ms: fewer, larger launches -- shorter GEMM tails, more items
+                                # per persistent CTA; the graph engine halves it by itself when memory is short)
     stash_fraction = 0.72       # share of the currently free device memory that forward may keep resident for backward
     graph_chunks = True         # bf16 training steps replay captured per-chunk CUDA graphs (mult_engine.ChunkGraphEngine)
     graph_min_tokens = 16384    # ... when a chunk is big enough for launch overhead to matter (tokens per chunk, all modalities)
@@ -245,10 +246,16 @@ class MultimodalTransformer(_FusionBase):
         free_bytes, _ = torch.cuda.mem_get_info(t.device)
         stash = mult_engine.stash_bytes_per_sample(Ls, H, t.element_size())
         static = (2 if need_dx else 1) * B * sum(Ls) * H * t.element_size()        # masked inputs (+ input gradients)
-        need = B * stash + static + 4 * min(B, chunk) * stash // 5     # + backward temporaries of the chunk in flight (~0.55 x its stash, measured)
-        if B * stash > self.stash_fraction * free_bytes or need > 0.92 * free_bytes:
+        if B * stash > self.stash_fraction * free_bytes:
             return None                                      # not every chunk can stay resident: eager issue with recomputed chunks
-        self._engine = mult_engine.ChunkGraphEngine(W, self._names, H, self.config.fusion_num_heads, chunk, B, Ls, t.dtype, t.device,
+        # the backward temporaries of the chunk in flight (~0.55 x its stash, measured) must fit next to the resident stash: halve the
+        # engine's chunk until they do (larger chunks are faster -- B = 4096: 256 -> 324 ms, 512 -> 318 ms, 1024 -> 315 ms per step)
+        eng_chunk = min(B, chunk)
+        while B * stash + static + 4 * eng_chunk * stash // 5 > 0.92 * free_bytes and eng_chunk > 128:
+            eng_chunk //= 2
+        if B * stash + static + 4 * eng_chunk * stash // 5 > 0.92 * free_bytes:
+            return None
+        self._engine = mult_engine.ChunkGraphEngine(W, self._names, H, self.config.fusion_num_heads, eng_chunk, B, Ls, t.dtype, t.device,
                                                     p_drop, need_dx, want_mean)
         self._engine_key = key
         self._engine_builds += 1

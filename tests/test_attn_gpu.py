@@ -135,6 +135,19 @@ def test_narrow_attention(shape):
     finally:
         lib.b200f_debug_set(10, 1)
     assert rel(o, o2) < 1e-2 and float((lse - lse2).abs().max()) < 2e-2
+    # and so does the first-generation narrow-key backward (b200f_debug_set(10, 2)); both are bit-reproducible run to run
+    lib.b200f_debug_set(10, 2)
+    try:
+        dpq2, dpkv2 = torch.zeros_like(pq), torch.zeros_like(pkv)
+        K.attn_bwd(do, q, k, v, o, lse, heads, scale, dpq2[:, :, W:], dpkv2[:, :, :W], dpkv2[:, :, 2 * W:])
+        torch.cuda.synchronize()
+    finally:
+        lib.b200f_debug_set(10, 1)
+    assert rel(dpq2, dpq) < 1e-2 and rel(dpkv2, dpkv) < 1e-2
+    dpq3, dpkv3 = torch.zeros_like(pq), torch.zeros_like(pkv)
+    K.attn_bwd(do, q, k, v, o, lse, heads, scale, dpq3[:, :, W:], dpkv3[:, :, :W], dpkv3[:, :, 2 * W:])
+    torch.cuda.synchronize()
+    assert torch.equal(dpq3, dpq) and torch.equal(dpkv3, dpkv)
 
 
 def test_attention_tc_matches_cuda_core_path():

@@ -1129,6 +1129,241 @@ __global__ void __launch_bounds__(128, 2) attn_nq_bwd_kernel(const NarrowParams 
   }
 }
 
+// ==============================================================================================================================
+// NQ backward, version 2 ("d-split", the default; same idea as attn_nk_bwd2_kernel): phase A -- warp w owns keys 16w..16w+15 of the
+// 64-key tile: S^T, dP^T, Pd^T, dS^T in registers, dV and dK of its keys stored at once (both staged over the warp's own V rows),
+// dS^T written as a bf16 [64 keys x 32 queries] tile to shared memory; phase B -- warp w owns the slice d = 16w..16w+15 of dQ:
+// dQ[:, slice] += dS K[:, slice] over ALL 64 keys of the tile (A = the shared dS^T tile read transposed).  16 instead of 64
+// accumulator registers for dQ, three CTAs per SM, no cross-warp reduction at the end.
+// ==============================================================================================================================
+constexpr int NQB2_SMEM = NQB_FIXED + NQB_ST * NQ_STAGE + NKB2_PS + 2 * NARROW * 4 + 3 * HD * 4 + 128;
+
+template <bool DROP>
+__global__ void __launch_bounds__(128, 3) attn_nq_bwd2_kernel(const NarrowParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* Qs = smem;
+  uint8_t* dOs = smem + NARROW * 128;
+  uint8_t* Os = smem + 2 * NARROW * 128;
+  uint8_t* ring = smem + NQB_FIXED;
+  uint8_t* DSt = ring + NQB_ST * NQ_STAGE;                               // dS^T [64 keys x 32 queries] bf16 (64-byte rows)
+  float* nl2s = reinterpret_cast<float*>(DSt + NKB2_PS);                 // -lse * log2e   per query
+  float* ndls = nl2s + NARROW;                                           // -delta * scale per query
+  float* dbs = ndls + NARROW;                                            // [3][64]: (unused), dbk, dbv partial sums
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const uint32_t sq = smem_u32(Qs), sdo = smem_u32(dOs), sring = smem_u32(ring), sds = smem_u32(DSt);
+  const int n_tiles = (p.Lk + 63) / 64;
+  const long long ktok = (long long)b * p.Lk, qtok = (long long)b * p.Lq;
+  auto issue = [&](int i) {
+    if (i < n_tiles) {
+      const uint32_t st = sring + (i % NQB_ST) * NQ_STAGE;
+      load_rows(st, p.K, p.ldk, ktok, i * 64, p.Lk, 64, h, tid, 128);
+      load_rows(st + 64 * 128, p.V, p.ldv, ktok, i * 64, p.Lk, 64, h, tid, 128);
+    }
+    cp_commit();
+  };
+  load_rows(sq, p.Q, p.ldq, qtok, 0, p.Lq, NARROW, h, tid, 128);
+  load_rows(sdo, p.dO, p.lddo, qtok, 0, p.Lq, NARROW, h, tid, 128);
+  load_rows(smem_u32(Os), p.O, p.ldo, qtok, 0, p.Lq, NARROW, h, tid, 128);
+  issue(0);
+  issue(1);
+  for (int i = tid; i < 3 * HD; i += 128) dbs[i] = 0.f;
+  cp_wait<1>();
+  __syncthreads();
+  {                                  // per-query statistics: thread -> (row = tid / 4, 16 of its 64 columns)
+    const int row = tid >> 2, cq = (tid & 3) * 2;
+    float dl = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      Vec16<bf16> x, y;
+      float fx[8], fy[8];
+      x.raw = *reinterpret_cast<const uint4*>(dOs + swz(row, cq + cc));
+      y.raw = *reinterpret_cast<const uint4*>(Os + swz(row, cq + cc));
+      x.unpack(fx); y.unpack(fy);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dl = fmaf(fx[e], fy[e], dl);
+    }
+    dl = quad_sum(dl);
+    if ((tid & 3) == 0) {
+      ndls[row] = -dl * p.scale;
+      nl2s[row] = -(row < p.Lq ? p.LSE[((long long)b * p.H + h) * p.Lq + row] : 0.f) * LOG2E;
+    }
+  }
+  __syncthreads();
+  float nl2[4][2], ndl[4][2];
+  uint32_t rk[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int q = nt * 8 + 2 * t + e;
+      nl2[nt][e] = nl2s[q];
+      ndl[nt][e] = ndls[q];
+      rk[nt][e] = DROP ? drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, uint32_t((b * p.H + h) * p.Lq + q)) : 0u;
+    }
+  float dq[2][2][4];                                       // [query m-tile][n-tile of this warp's d slice]
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dq[mt][nt][e] = 0.f;
+  float dbv0 = 0.f, dbv1 = 0.f, dbk0 = 0.f, dbk1 = 0.f;
+  const float c = p.scale * LOG2E;
+  const float sck = p.scale * (DROP ? p.inv_keep : 1.f);
+  const int kw = warp * 16;
+#pragma unroll 1
+  for (int i = 0; i < n_tiles; ++i) {
+    cp_wait<1>();
+    __syncthreads();                 // tile i landed; every warp is done with phase B of tile i-1 (the dS^T tile and a ring slot are free)
+    issue(i + 2);
+    uint8_t* Vt = ring + (i % NQB_ST) * NQ_STAGE + 64 * 128;
+    const uint32_t skt = sring + (i % NQB_ST) * NQ_STAGE, svt = skt + 64 * 128;
+    const int key0 = i * 64 + kw;
+    // ---------------- phase A: this warp's 16 keys (keys past Lk are zero-filled and forced to P = 0: exact zeros everywhere)
+    uint32_t pa[2][4], dsa[2][4];
+    {
+      float st[4][4], dpt[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { st[nt][e] = 0.f; dpt[nt][e] = 0.f; }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t a[4], a2[4], bb[4];
+        ld_a(a, skt, kw, kk, lane);
+        ld_a(a2, svt, kw, kk, lane);
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+          ld_b_nk(bb, sq, np * 16, kk, lane);
+          mma16816(st[2 * np], a, bb[0], bb[1]);
+          mma16816(st[2 * np + 1], a, bb[2], bb[3]);
+          ld_b_nk(bb, sdo, np * 16, kk, lane);
+          mma16816(dpt[2 * np], a2, bb[0], bb[1]);
+          mma16816(dpt[2 * np + 1], a2, bb[2], bb[3]);
+        }
+      }
+      const bool va = key0 + g < p.Lk, vb = key0 + g + 8 < p.Lk;
+      const uint32_t cma = uint32_t(key0 + g) * kDropColMul, cmb = uint32_t(key0 + g + 8) * kDropColMul;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float pd[4], ds[4];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float p0 = va ? ex2_approx(fmaf(st[nt][e], c, nl2[nt][e])) : 0.f;
+          const float p1 = vb ? ex2_approx(fmaf(st[nt][2 + e], c, nl2[nt][e])) : 0.f;
+          bool k0 = true, k1 = true;
+          if (DROP) {
+            k0 = drop_keep_c(rk[nt][e], cma, p.drop_thr);
+            k1 = drop_keep_c(rk[nt][e], cmb, p.drop_thr);
+          }
+          pd[e] = k0 ? p0 * (DROP ? p.inv_keep : 1.f) : 0.f;
+          pd[2 + e] = k1 ? p1 * (DROP ? p.inv_keep : 1.f) : 0.f;
+          ds[e] = p0 * fmaf(dpt[nt][e], k0 ? sck : 0.f, ndl[nt][e]);
+          ds[2 + e] = p1 * fmaf(dpt[nt][2 + e], k1 ? sck : 0.f, ndl[nt][e]);
+        }
+        pa[nt >> 1][(nt & 1) * 2] = pack_bf16(pd[0], pd[1]);
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(pd[2], pd[3]);
+        const uint32_t slo = pack_bf16(ds[0], ds[1]), shi = pack_bf16(ds[2], ds[3]);
+        dsa[nt >> 1][(nt & 1) * 2] = slo;
+        dsa[nt >> 1][(nt & 1) * 2 + 1] = shi;
+        // dS^T tile for phase B: this thread's two queries (4 bytes) of key rows kw+g and kw+g+8
+        *reinterpret_cast<uint32_t*>(DSt + swz64(kw + g, nt) + t * 4) = slo;
+        *reinterpret_cast<uint32_t*>(DSt + swz64(kw + g + 8, nt) + t * 4) = shi;
+      }
+    }
+    {
+      float acc[8][4];
+      // dV = Pd^T dO over all (<= 32) queries: complete for these 16 keys
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int d4 = 0; d4 < 4; ++d4) {
+          uint32_t bb[4];
+          ld_b_kn(bb, sdo, ks * 16, d4, lane);
+          mma16816(acc[2 * d4], pa[ks], bb[0], bb[1]);
+          mma16816(acc[2 * d4 + 1], pa[ks], bb[2], bb[3]);
+        }
+      __syncwarp();
+      stage_tile(Vt, kw, acc, 1.f, 1.f, lane);             // over this warp's own (consumed) V rows; the K rows stay intact for phase B
+      __syncwarp();
+      store_tile(Vt, kw, p.dV, p.lddv, ktok, key0, p.Lk, h, lane, p.dbv ? &dbv0 : nullptr, p.dbv ? &dbv1 : nullptr);
+      // dK = dS^T Q
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int d4 = 0; d4 < 4; ++d4) {
+          uint32_t bb[4];
+          ld_b_kn(bb, sq, ks * 16, d4, lane);
+          mma16816(acc[2 * d4], dsa[ks], bb[0], bb[1]);
+          mma16816(acc[2 * d4 + 1], dsa[ks], bb[2], bb[3]);
+        }
+      __syncwarp();                                        // the dV rows above have been read back by this warp's store_tile
+      stage_tile(Vt, kw, acc, 1.f, 1.f, lane);
+      __syncwarp();
+      store_tile(Vt, kw, p.dK, p.lddk, ktok, key0, p.Lk, h, lane, p.dbk ? &dbk0 : nullptr, p.dbk ? &dbk1 : nullptr);
+    }
+    __syncthreads();                 // dS^T of all 64 keys is in shared memory
+    // ---------------- phase B: this warp's 16-wide slice of d, all 64 keys of the tile
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t bk[4];
+      ld_b_kn(bk, skt, ks * 16, warp, lane);               // K[k = keys 16ks.., n = d slice]: two n-tiles
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        uint32_t as[4];
+        const int mi = lane >> 3, r = lane & 7;
+        ldsm4t(as, sds + swz64(ks * 16 + (mi >> 1) * 8 + r, mt * 2 + (mi & 1)));     // A = dS (m = queries 16mt.., k = keys 16ks..)
+        mma16816(dq[mt][0], as, bk[0], bk[1]);
+        mma16816(dq[mt][1], as, bk[2], bk[3]);
+      }
+    }
+  }
+  cp_wait<0>();
+  if (p.dbv) { atomicAdd(&dbs[2 * HD + 2 * lane], dbv0); atomicAdd(&dbs[2 * HD + 2 * lane + 1], dbv1); }
+  if (p.dbk) { atomicAdd(&dbs[HD + 2 * lane], dbk0); atomicAdd(&dbs[HD + 2 * lane + 1], dbk1); }
+  // dQ: warp w owns columns 16w..16w+15; rows = queries
+  float csq[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int col = h * HD + warp * 16 + nt * 8 + 2 * t;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int q = mt * 16 + g + hf * 8;
+        if (q < p.Lq) {
+          const uint32_t w = pack_bf16(dq[mt][nt][2 * hf], dq[mt][nt][2 * hf + 1]);
+          *reinterpret_cast<uint32_t*>(p.dQ + (qtok + q) * p.lddq + col) = w;
+          csq[nt][0] += __uint_as_float(w << 16); csq[nt][1] += __uint_as_float(w & 0xFFFF0000u);
+        }
+      }
+    }
+  if (p.dbq) {
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) csq[nt][e] += __shfl_xor_sync(0xffffffffu, csq[nt][e], o);
+        if (g == 0) atomicAdd(p.dbq + h * HD + warp * 16 + nt * 8 + 2 * t + e, csq[nt][e]);
+      }
+  }
+  __syncthreads();
+  if (tid < 64) {
+    if (p.dbk) atomicAdd(p.dbk + h * HD + tid, dbs[HD + tid]);
+    if (p.dbv) atomicAdd(p.dbv + h * HD + tid, dbs[2 * HD + tid]);
+  }
+}
+
 NarrowParams make_params(const b200f_attn_args& a) {
   NarrowParams p = {};
   p.B = a.B; p.H = a.H; p.Lq = a.Lq; p.Lk = a.Lk; p.scale = a.scale;
@@ -1218,6 +1453,16 @@ int attn_bwd_narrow(const b200f_attn_args& a, cudaStream_t st) {
       attn_nk_bwd_kernel<false><<<grid, 128, NKB_SMEM, st>>>(p);
     }
     return check_launch("attn_nk_bwd_kernel");
+  }
+  if (g_attn_narrow != 2) {                                // default: the d-split kernel; b200f_debug_set(10, 2) = the first version (A/B)
+    if (drop) {
+      B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_nq_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQB2_SMEM));
+      attn_nq_bwd2_kernel<true><<<grid, 128, NQB2_SMEM, st>>>(p);
+    } else {
+      B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_nq_bwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQB2_SMEM));
+      attn_nq_bwd2_kernel<false><<<grid, 128, NQB2_SMEM, st>>>(p);
+    }
+    return check_launch("attn_nq_bwd2_kernel");
   }
   if (drop) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_nq_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NQB_SMEM));

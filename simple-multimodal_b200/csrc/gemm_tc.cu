@@ -194,17 +194,13 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, const 
     const int c0 = c_begin + blk * 64;
     const int col0 = n_base + c0;
     uint8_t* st = stage + (blk & 1) * p.epi_stride;
-    if (p.tma_store) {                                        // the bulk store that last read this staging tile must be done reading it
-      // ... and with an aux block, also the store that last read the OTHER tile, which the prefetch below is about to overwrite
-      const bool all = p.epi_stride == 0 || (has_aux && blk + 1 < NBLK);
-      if (lane == 0) { if (all) tma_store_wait_read(); else tma_store_wait_read1(); }
-      __syncwarp();
-    }
-    if (blk + 1 < NBLK) {
-      epi_issue_aux(p, stage + ((blk + 1) & 1) * p.epi_stride, row0, col0 + 64, lane);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
+    if (has_aux) {
+      // the aux (residual / ReLU-mask) blocks of ALL of this warp's column blocks were prefetched by epilogue_tile before it waited
+      // for the accumulator (one cp.async group per block, NBLK <= 2 = the number of staging tiles): their global-memory latency
+      // hides under the mainloop instead of under one block of epilogue work
+      if (blk + 1 < NBLK) cp_async_wait<1>(); else cp_async_wait<0>();
+    } else if (p.tma_store) {                                 // the bulk store that last read this staging tile must be done reading it
+      if (lane == 0) { if (p.epi_stride) tma_store_wait_read1(); else tma_store_wait_read(); }
     }
     __syncwarp();
     if (col0 >= p.N) continue;                                // warp-uniform
@@ -362,12 +358,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, const CUten
   const float bias_mul = (p.drop_thr && !p.residual && staged16_) ? p.inv_keep : 1.f;      // see fold_keep in epilogue_tile_bf16
   if (p.bias && et < BN) bias_tile[et] = (n_base + et < p.N) ? __ldg(p.bias + n_base + et) * bias_mul : 0.f;
   const bool staged16 = !out_f32 && p.vec_ok;
-  if (staged16 && p.tma_store && (p.residual || p.mask)) {
-    // the first staging tile receives this tile's first aux block: the bulk store that last read it (NBLK stores ago) must be done
-    if (lane == 0) { if (BN / 2 / 64 >= 2 && p.epi_stride) tma_store_wait_read1(); else tma_store_wait_read(); }
-    __syncwarp();
+  if (staged16 && (p.residual || p.mask)) {
+    static_assert(BN / 2 / 64 <= 2, "one staging tile per column block of a warp");
+    if (p.tma_store) {                                         // both staging tiles are about to be overwritten: every bulk store of the
+      if (lane == 0) tma_store_wait_read();                    // previous tile must be done reading them (it has had the whole mainloop)
+      __syncwarp();
+    }
+#pragma unroll
+    for (int blk = 0; blk < BN / 2 / 64; ++blk)
+      epi_issue_aux(p, stage + (blk & 1) * p.epi_stride, row0, n_base + c_begin + blk * 64, lane);
   }
-  if (staged16) epi_issue_aux(p, stage, row0, n_base + c_begin, lane);
   asm volatile("bar.sync 1, 256;" ::: "memory");             // bias slice visible to all epilogue warps
   mbar_wait(full_bar, full_phase);
   tc_fence_after();

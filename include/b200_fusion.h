@@ -118,11 +118,15 @@ typedef struct {
    * and backward (counter-based hash of (b, head, query, key), see csrc/common.cuh) -- pass the same values to both.
    * dropout_p = 0 disables it.  LSE is the log-sum-exp of the UNdropped scores. */
   float dropout_p; uint32_t drop_seed_lo, drop_seed_hi;
-  /* forward only, optional (nullable; bf16 / head dim 64 kernels): fp32 [B, H*D] accumulators, += the column sums over the Lq
-   * rows of each (b, head) of the O that is stored -- the numerator of `.mean(dim=1)` of the attended features
-   * (fusion_layers.py:166-168) straight out of the attention epilogue, so no separate pass re-reads O. */
+  /* forward only, optional (nullable; bf16 / head dim 64 kernels): fp32 [B, parts, H*D] PARTIAL column sums of the O that is stored,
+   * parts = b200f_attn_pool_parts(args): partial p of (b, head) covers a fixed group of query rows and is written (not added) by
+   * exactly one warp, so the result is bit-reproducible; b200f_pool_finish sums the parts in order and scales -- the `.mean(dim=1)`
+   * of the attended features (fusion_layers.py:166-168) straight out of the attention epilogue, no separate pass re-reads O. */
   float* pool_sum;
 } b200f_attn_args;
+int32_t b200f_attn_pool_parts(const b200f_attn_args* args);   /* 0: the kernel family serving this shape / dtype has no pooled output */
+/* out[b, c] = scale * sum_p partial[b, p, c]  (p ascending; out bf16 or fp32 by `dtype`, leading dimension ldo) */
+int b200f_pool_finish(const float* partial, void* out, int64_t ldo, int64_t B, int32_t parts, int32_t W, float scale, int32_t dtype, void* stream);
 int b200f_attn_fwd(const b200f_attn_args* args, void* stream);
 int b200f_attn_bwd(const b200f_attn_args* args, void* stream);
 

@@ -57,7 +57,7 @@ _lib = None
 # Optional live per-entry-point profile (tools/step_profile.py): when CALL_PROFILE is a list, every compute entry point is
 # bracketed by CUDA events on the launching stream and (name, start, stop) is appended.  Off (None) in normal use.
 CALL_PROFILE = None
-_NOT_KERNELS = ("b200f_last_error", "b200f_launch_count", "b200f_infonce_workspace_bytes", "b200f_version", "b200f_debug_set")
+_NOT_KERNELS = ("b200f_last_error", "b200f_launch_count", "b200f_infonce_workspace_bytes", "b200f_version", "b200f_debug_set", "b200f_attn_pool_parts")
 
 
 class _ProfiledLib:
@@ -90,6 +90,7 @@ def lib():
         _lib.b200f_last_error.restype = C.c_char_p
         _lib.b200f_launch_count.restype = C.c_ulonglong
         _lib.b200f_infonce_workspace_bytes.restype = C.c_size_t
+        _lib.b200f_attn_pool_parts.restype = C.c_int32
     return _lib if CALL_PROFILE is None else _ProfiledLib()
 
 

@@ -40,6 +40,7 @@ extern bool g_dbg_disable_pair;
 extern bool g_dbg_six_stages;
 extern bool g_dbg_no_tma_store;
 extern bool g_dbg_no_tma_store_aux;
+extern bool g_dbg_late_aux;
 extern bool g_dbg_no_ln_tma;
 extern int g_attn_fwd_variant;
 extern int g_attn_bwd_variant;
@@ -119,6 +120,7 @@ int b200f_debug_set(int key, unsigned value) {
     case 9: b200f::g_dbg_no_ln_tma = value != 0; break;
     case 10: b200f::g_attn_narrow = int(value); break;
     case 11: b200f::g_dbg_no_tma_store_aux = value != 0; break;
+    case 12: b200f::g_dbg_late_aux = value != 0; break;
     default: return b200f::fail(B200F_ERR_UNSUPPORTED, "unknown debug key %d", key);
   }
   return B200F_OK;
@@ -132,6 +134,7 @@ int attn_bwd_simt_dispatch(const b200f_attn_args& a, cudaStream_t st);
 int attn_fwd_tc(const b200f_attn_args& a, cudaStream_t st);
 int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st);
 int attn_narrow_kind(const b200f_attn_args& a);
+int attn_narrow_pool_parts(const b200f_attn_args& a);
 int attn_fwd_narrow(const b200f_attn_args& a, cudaStream_t st);
 int attn_bwd_narrow(const b200f_attn_args& a, cudaStream_t st);
 bool g_force_simt_attention = false;
@@ -147,6 +150,12 @@ static int attn_check(const b200f_attn_args* a) {
 }  // namespace b200f
 
 extern "C" {
+
+int32_t b200f_attn_pool_parts(const b200f_attn_args* a) {
+  if (!a || a->dtype != B200F_BF16 || a->D != 64 || b200f::g_force_simt_attention) return 0;
+  const int n = b200f::attn_narrow_pool_parts(*a);
+  return n ? n : (a->Lq + 31) / 32;                       // tcgen05 kernels: one partial per 32-row tile
+}
 
 int b200f_attn_fwd(const b200f_attn_args* a, void* stream) {
   int rc = b200f::attn_check(a);

@@ -42,7 +42,8 @@ struct NarrowParams {
   bf16* dK; long long lddk;
   bf16* dV; long long lddv;
   float* dbq; float* dbk; float* dbv;
-  float* pool;                          // forward, optional [B, H*64] fp32: += column sums of the stored O
+  float* pool;                          // forward, optional [B, parts, H*64] fp32: partial column sums of the stored O (NK: one part per 16 query
+                                        // rows; NQ: one part), each written by exactly one warp / thread set
   uint32_t drop_thr, drop_seed_lo, drop_seed_hi;
   float inv_keep;
 };
@@ -246,11 +247,8 @@ __global__ void __launch_bounds__(128) attn_nk_fwd_kernel(const NarrowParams p) 
     __syncwarp();
     float ps0 = 0.f, ps1 = 0.f;
     store_tile(Qs, r0, p.O, p.ldo, (long long)b * p.Lq, q0 + r0, p.Lq, h, lane, p.pool ? &ps0 : nullptr, p.pool ? &ps1 : nullptr);
-    if (p.pool) {
-      float* dst = p.pool + ((long long)b * p.H + h) * HD + 2 * lane;
-      atomicAdd(dst, ps0);
-      atomicAdd(dst + 1, ps1);
-    }
+    if (p.pool)                                           // this 16-row group's own slot of the partial sums: a plain store
+      *reinterpret_cast<float2*>(p.pool + (((long long)b * ((p.Lq + 15) / 16) + (q0 + r0) / 16) * p.H + h) * HD + 2 * lane) = make_float2(ps0, ps1);
   }
 }
 
@@ -709,7 +707,7 @@ constexpr int NQF_ST = 4;
 constexpr int NQ_STAGE = 2 * 64 * 128;                    // K, V
 constexpr int NQ_OSTRIDE = HD + 8;                        // fp32 row stride of the merge buffers (bank spread)
 constexpr int NQF_SMEM = NARROW * 128 + NQF_ST * NQ_STAGE + 256;
-static_assert(4 * NARROW * NQ_OSTRIDE * 4 + 2 * 4 * NARROW * 4 <= NQF_ST * NQ_STAGE, "merge buffers must fit in the ring");
+static_assert(4 * NARROW * NQ_OSTRIDE * 4 + 2 * 4 * NARROW * 4 + NARROW * HD * 4 <= NQF_ST * NQ_STAGE, "merge buffers (+ the pooled-output tile) must fit in the ring");
 static_assert(4 * NARROW * NQ_OSTRIDE * 4 <= 3 * NQ_STAGE, "the backward's per-warp dQ partials must fit in its ring");
 
 template <bool DROP>
@@ -885,11 +883,20 @@ __global__ void __launch_bounds__(128, 2) attn_nq_fwd_kernel(const NarrowParams 
       *reinterpret_cast<uint4*>(dst) = o0;
       *reinterpret_cast<uint4*>(dst + 8) = o1;
       if ((tid & 3) == 0) p.LSE[((long long)b * p.H + h) * p.Lq + row] = mm * p.scale + logf(lt);
-      if (p.pool) {                                        // <= 32 rows per (b, h): a few atomics on the rounded values that were stored
-        float* pd = p.pool + ((long long)b * p.H + h) * HD + c0;
+      if (p.pool) {                                        // the rounded values that were stored -> a [32][64] fp32 tile behind the merge buffers
+        float* pf = lw + 4 * NARROW + row * HD + c0;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) atomicAdd(pd + e, bf16_round(acc[e] * inv));
+        for (int e = 0; e < 16; ++e) pf[e] = bf16_round(acc[e] * inv);
       }
+    }
+  }
+  if (p.pool) {                                            // column sums over the (<= 32) query rows in a fixed order: one part per (b, h)
+    __syncthreads();
+    if (tid < HD) {
+      const float* pf = lw + 4 * NARROW + tid;
+      float s_ = 0.f;
+      for (int row = 0; row < p.Lq; ++row) s_ += pf[row * HD];
+      p.pool[((long long)b * p.H + h) * HD + tid] = s_;
     }
   }
 }
@@ -1385,6 +1392,8 @@ NarrowParams make_params(const b200f_attn_args& a) {
 
 }  // namespace
 
+// number of partial-sum slots per (batch, head) the forward kernel serving this shape writes into pool_sum (0: none)
+int attn_narrow_pool_parts(const b200f_attn_args& a);
 int g_attn_narrow = 1;           // b200f_debug_set(10, 0) routes the narrow shapes back to the 128-wide tcgen05 tiles (A/B)
 
 // which narrow kernel family serves this shape: 1 = NK (Lk <= 32), 2 = NQ (Lq <= 32 < Lk), 0 = none
@@ -1394,6 +1403,11 @@ int attn_narrow_kind(const b200f_attn_args& a) {
   if (a.Lk <= NARROW) return 1;
   if (a.Lq <= NARROW) return 2;
   return 0;
+}
+
+int attn_narrow_pool_parts(const b200f_attn_args& a) {
+  const int kind = attn_narrow_kind(a);
+  return kind == 1 ? (a.Lq + 15) / 16 : (kind == 2 ? 1 : 0);
 }
 
 static int narrow_check(const b200f_attn_args& a, bool bwd) {

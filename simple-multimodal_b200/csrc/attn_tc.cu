@@ -39,7 +39,7 @@ struct AttnTcParams {
   bf16* dK; long long lddk;
   bf16* dV; long long lddv;
   float* dbq; float* dbk; float* dbv;   // optional [H*64] fp32 accumulators: column sums of dQ / dK / dV (in-proj bias gradients)
-  float* pool;                           // forward, optional [B, H*64] fp32: += column sums of the stored O over the queries of (b, h)
+  float* pool;                           // forward, optional [B, ceil(Lq/32), H*64] fp32: partial column sums of the stored O, one per 32-row tile
   // attention-probability dropout (persistent kernels, DROP = true instantiation): keep iff hash >= drop_thr, kept scaled by inv_keep
   uint32_t drop_thr, drop_seed_lo, drop_seed_hi;
   float inv_keep;
@@ -51,7 +51,7 @@ struct AttnTcParams {
 // `colsum` (optional, 64 floats for this head): += the column sums of the rows stored (the bf16-rounded values, so it
 // equals a column sum over the stored tensor) -- the bias gradient of the projection that produced Q / K / V.
 __device__ __forceinline__ void store_rows64(uint32_t taddr, uint8_t* stage, bf16* gbase, long long ld, int rows_valid, int lane, float mul,
-                                             float* colsum = nullptr) {
+                                             float* colsum = nullptr, float* colpart = nullptr) {
 #pragma unroll
   for (int cc = 0; cc < HD; cc += 16) {
     uint32_t r[16];
@@ -71,14 +71,19 @@ __device__ __forceinline__ void store_rows64(uint32_t taddr, uint8_t* stage, bf1
     if (r < rows_valid)
       *reinterpret_cast<uint4*>(gbase + (long long)r * ld + cchunk * 8) = *reinterpret_cast<const uint4*>(stage + sw128_offset(r, cchunk));
   }
-  if (colsum) {                          // ONES x tile on the warp-level tensor path (ptx.cuh): lanes 0..3 hold columns 8*nt + 2*lane, +1
+  if (colsum || colpart) {               // ONES x tile on the warp-level tensor path (ptx.cuh): lanes 0..3 hold columns 8*nt + 2*lane, +1
     const int nr = rows_valid < 32 ? rows_valid : 32;
     if (nr > 0) {                        // warp-uniform
       float cs[8][2];
       colsum32x64_hmma(stage, nr, lane, cs);
       if (lane < 4) {
+        if (colpart) {                   // this tile's own slot: a plain store, bit-reproducible
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) { atomicAdd(colsum + nt * 8 + 2 * lane, cs[nt][0]); atomicAdd(colsum + nt * 8 + 2 * lane + 1, cs[nt][1]); }
+          for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<float2*>(colpart + nt * 8 + 2 * lane) = make_float2(cs[nt][0], cs[nt][1]);
+        } else {
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) { atomicAdd(colsum + nt * 8 + 2 * lane, cs[nt][0]); atomicAdd(colsum + nt * 8 + 2 * lane + 1, cs[nt][1]); }
+        }
       }
     }
   }
@@ -265,7 +270,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     // O / l -> bf16 -> this warp's 32 x 128 B slice of the (now free) P tile -> full 128-byte lines to global
     if (qrow < p.Lq) p.LSE[((long long)b * p.H + h) * p.Lq + qrow] = m * p.scale + logf(l);
     store_rows64(t_o + lane_addr, smem + FwdSmem::P_OFF + grp * (32 * 128), p.O + ((long long)b * p.Lq + q0 + grp * 32) * p.ldo + h * HD, p.ldo,
-                 p.Lq - (q0 + grp * 32), lane, inv, p.pool ? p.pool + ((long long)b * p.H + h) * HD : nullptr);
+                 p.Lq - (q0 + grp * 32), lane, inv, nullptr,
+                 p.pool ? p.pool + (((long long)b * ((p.Lq + 31) / 32) + (q0 + grp * 32) / 32) * p.H + h) * HD : nullptr);
   }
 
   tc_fence_before();
@@ -542,7 +548,8 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       if (qrow < p.Lq) p.LSE[((long long)b * p.H + h) * p.Lq + qrow] = m * p.scale + logf(l);
       // O / l -> bf16 -> this warp's 32 x 128 B slice of the (now free) P_t tile -> full 128-byte lines to global
       store_rows64(t_o + lane_addr, prow + grp * (32 * 128), p.O + ((long long)b * p.Lq + q0 + grp * 32) * p.ldo + h * HD, p.ldo,
-                   p.Lq - (q0 + grp * 32), lane, (DROP ? p.inv_keep : 1.f) / l, p.pool ? p.pool + ((long long)b * p.H + h) * HD : nullptr);
+                   p.Lq - (q0 + grp * 32), lane, (DROP ? p.inv_keep : 1.f) / l, nullptr,
+                   p.pool ? p.pool + (((long long)b * ((p.Lq + 31) / 32) + (q0 + grp * 32) / 32) * p.H + h) * HD : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[t]);

@@ -39,6 +39,7 @@ struct GemmTcParams {
   uint32_t drop_thr, drop_seed_lo, drop_seed_hi;   // inverted dropout on the output (staged bf16 epilogue only); 0 = off
   float inv_keep;
   int tma_store;   // bf16 output without residual / mask: staged tiles leave through cp.async.bulk.tensor stores (tensor map of C)
+  int late_aux;    // debug (b200f_debug_set(12, 1)): prefetch the aux block one column block ahead instead of all at tile start
   int epi_stride;  // byte distance of a warp's two epilogue staging tiles (EPI_STAGE_BYTES), or 0 when the launch has a single tile per warp
 };
 
@@ -194,13 +195,26 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, const 
     const int c0 = c_begin + blk * 64;
     const int col0 = n_base + c0;
     uint8_t* st = stage + (blk & 1) * p.epi_stride;
-    if (has_aux) {
+    if (has_aux && !p.late_aux) {
       // the aux (residual / ReLU-mask) blocks of ALL of this warp's column blocks were prefetched by epilogue_tile before it waited
       // for the accumulator (one cp.async group per block, NBLK <= 2 = the number of staging tiles): their global-memory latency
       // hides under the mainloop instead of under one block of epilogue work
       if (blk + 1 < NBLK) cp_async_wait<1>(); else cp_async_wait<0>();
-    } else if (p.tma_store) {                                 // the bulk store that last read this staging tile must be done reading it
-      if (lane == 0) { if (p.epi_stride) tma_store_wait_read1(); else tma_store_wait_read(); }
+    } else {
+      if (p.tma_store) {                                      // the bulk store that last read this staging tile must be done reading it
+        // ... and with an aux block, also the store that last read the OTHER tile, which the prefetch below is about to overwrite
+        const bool all = p.epi_stride == 0 || (has_aux && blk + 1 < NBLK);
+        if (lane == 0) { if (all) tma_store_wait_read(); else tma_store_wait_read1(); }
+        __syncwarp();
+      }
+      if (has_aux) {                                          // b200f_debug_set(12, 1): the round-1 schedule, one block ahead (A/B)
+        if (blk + 1 < NBLK) {
+          epi_issue_aux(p, stage + ((blk + 1) & 1) * p.epi_stride, row0, col0 + 64, lane);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+      }
     }
     __syncwarp();
     if (col0 >= p.N) continue;                                // warp-uniform
@@ -364,9 +378,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, const CUten
       if (lane == 0) tma_store_wait_read();                    // previous tile must be done reading them (it has had the whole mainloop)
       __syncwarp();
     }
+    if (p.late_aux) {
+      epi_issue_aux(p, stage, row0, n_base + c_begin, lane);
+    } else {
 #pragma unroll
-    for (int blk = 0; blk < BN / 2 / 64; ++blk)
-      epi_issue_aux(p, stage + (blk & 1) * p.epi_stride, row0, n_base + c_begin + blk * 64, lane);
+      for (int blk = 0; blk < BN / 2 / 64; ++blk)
+        epi_issue_aux(p, stage + (blk & 1) * p.epi_stride, row0, n_base + c_begin + blk * 64, lane);
+    }
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");             // bias slice visible to all epilogue warps
   mbar_wait(full_bar, full_phase);
@@ -715,6 +733,7 @@ uint32_t g_dbg_mn_lbo = 0, g_dbg_mn_sbo = 0, g_dbg_mn_kadv = 0;
 
 bool g_dbg_disable_pair = false;     // b200f_debug_set(3, 1): force the single-CTA kernel (A/B testing)
 bool g_dbg_no_tma_store = false;     // b200f_debug_set(8, 1): LDS + STG copy-out instead of bulk tensor stores (A/B testing)
+bool g_dbg_late_aux = false;         // b200f_debug_set(12, 1): aux blocks prefetched one column block ahead (round-1 schedule) instead of at tile start
 bool g_dbg_no_tma_store_aux = false; // b200f_debug_set(11, 1): launches with a residual / mask block keep the LDS + STG copy-out (A/B testing)
 bool g_dbg_six_stages = false;       // b200f_debug_set(7, 1): 6-stage / one-staging-tile pair kernel for launches without an aux block.
                                      // Measured no faster than 5 stages on any MulT shape (profiles/r01_e): the ring depth is not the limiter.
@@ -813,6 +832,7 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
     if (rc) return rc;
   }
   p.epi_stride = EPI_STAGE_BYTES;
+  p.late_aux = g_dbg_late_aux ? 1 : 0;
   p.colsum = a.colsum;
   p.drop_thr = drop_threshold(a.dropout_p); p.drop_seed_lo = a.drop_seed_lo; p.drop_seed_hi = a.drop_seed_hi;
   p.inv_keep = 1.f / (1.f - a.dropout_p);

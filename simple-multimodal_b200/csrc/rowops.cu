@@ -522,6 +522,19 @@ __global__ void rowmask_copy_kernel(const T* __restrict__ src, T* __restrict__ d
   }
 }
 
+// out[b, c] = scale * sum_p partial[b, p, c], p ascending (fixed order: bit-reproducible); one thread per (b, c)
+template <typename T>
+__global__ void pool_finish_kernel(const float* __restrict__ partial, T* __restrict__ out, long long ldo, long long B, int parts, int W, float scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * W) return;
+  const long long b = i / W;
+  const int c = int(i - b * W);
+  const float* src = partial + b * parts * (long long)W + c;
+  float s_ = 0.f;
+  for (int p = 0; p < parts; ++p) s_ += src[(long long)p * W];
+  out[b * ldo + c] = from_f32<T>(s_ * scale);
+}
+
 // L2 row normalisation: one warp per row.
 template <typename T, int NV>
 __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const T* __restrict__ y, T* __restrict__ z, float* __restrict__ norm_out,
@@ -838,6 +851,16 @@ int b200f_rowmask_apply(void* x, const float* mask, int32_t col, int64_t B, int6
     rowmask_kernel<T><<<ew_grid(B * L * (H / VN), 256), 256, 0, st>>>(static_cast<T*>(x), mask, col, B, L, H);
   })
   return check_launch("rowmask");
+}
+
+int b200f_pool_finish(const float* partial, void* out, int64_t ldo, int64_t B, int32_t parts, int32_t W, float scale, int32_t dtype, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B == 0) return B200F_OK;
+  B200F_REQUIRE(partial && out && parts > 0 && W > 0, B200F_ERR_SHAPE, "pool_finish: operands / shape");
+  DISPATCH_DTYPE(dtype, T, {
+    pool_finish_kernel<T><<<unsigned((B * W + 255) / 256), 256, 0, st>>>(partial, static_cast<T*>(out), ldo, B, parts, W, scale);
+  })
+  return check_launch("pool_finish");
 }
 
 int b200f_rowmask_copy(const void* src, void* dst, const float* mask, int32_t col, int64_t B, int64_t L, int32_t H, int32_t dtype, void* stream) {

@@ -315,27 +315,37 @@ def _tokens(x: Tensor):
 
 
 def attn_pool_supported(q: Tensor, heads: int) -> bool:
-    """whether attn_fwd can accumulate the pooled output (`pool_sum=`) for this operand: the bf16 / head-dim-64 kernels"""
+    """whether attn_fwd can produce the pooled output (`pooled=`) for this operand: the bf16 / head-dim-64 kernels"""
     return q.dtype == torch.bfloat16 and q.size(-1) // heads == 64
 
 
 def attn_fwd(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float, out: Optional[Tensor] = None, dropout=None,
-             pool_sum: Optional[Tensor] = None):
-    """`pool_sum` (optional, fp32 [B, H*D], contiguous): += sum over the Lq rows of the stored output per (batch, column)."""
-    require_cuda(q, k, v, pool_sum)
+             pooled: Optional[Tensor] = None):
+    """`pooled` (optional, [B, H*D] in q's dtype or fp32): receives mean over the Lq rows of the stored output, computed from partial
+    column sums the attention epilogue writes (one slot per row group, no atomics: bit-reproducible) + one small finishing kernel."""
+    require_cuda(q, k, v, pooled)
     B, Lq, W = q.shape
     Lk = k.size(1)
     D = W // heads
-    if pool_sum is not None and (pool_sum.dtype != torch.float32 or not pool_sum.is_contiguous() or pool_sum.shape != (B, W) or not attn_pool_supported(q, heads)):
-        raise B200FusionError("attn_fwd: pool_sum must be a contiguous float32 [B, H*D] accumulator (bf16, head dim 64 only)")
+    if pooled is not None and (pooled.shape != (B, W) or pooled.stride(1) != 1 or not attn_pool_supported(q, heads)):
+        raise B200FusionError("attn_fwd: pooled must be [B, H*D] rows (bf16, head dim 64 only)")
     if out is None:
         out = torch.empty((B, Lq, W), device=q.device, dtype=q.dtype)
     lse = torch.empty((B, heads, Lq), device=q.device, dtype=torch.float32)
     (qp, ldq), (kp, ldk), (vp, ldv), (op, ldo) = _tokens(q), _tokens(k), _tokens(v), _tokens(out)
     args = L.AttnArgs(B=B, H=heads, Lq=Lq, Lk=Lk, D=D, Q=qp, ldq=ldq, K=kp, ldk=ldk, V=vp, ldv=ldv, O=op, ldo=ldo,
-                      LSE=lse.data_ptr(), scale=scale, dtype=dtype_code(q.dtype), pool_sum=None if pool_sum is None else pool_sum.data_ptr(),
-                      **_drop_fields(dropout))
+                      LSE=lse.data_ptr(), scale=scale, dtype=dtype_code(q.dtype), **_drop_fields(dropout))
+    partial = None
+    if pooled is not None:
+        parts = int(lib().b200f_attn_pool_parts(C.byref(args)))
+        if parts <= 0:
+            raise B200FusionError("attn_fwd: no pooled output for this shape / dtype")
+        partial = torch.empty((B, parts, W), device=q.device, dtype=torch.float32)
+        args.pool_sum = partial.data_ptr()
     check(lib().b200f_attn_fwd(C.byref(args), stream_ptr()), "b200f_attn_fwd")
+    if pooled is not None:
+        check(lib().b200f_pool_finish(ptr(partial), ptr(pooled), C.c_int64(pooled.stride(0)), C.c_int64(B), C.c_int32(parts), C.c_int32(W),
+                                      C.c_float(1.0 / Lq), dtype_code(pooled.dtype), stream_ptr()), "b200f_pool_finish")
     return out, lse
 
 

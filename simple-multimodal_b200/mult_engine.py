@@ -162,9 +162,10 @@ def _chunk_forward(xs, W: _Weights, H: int, heads: int, pooled_out: Tensor, keep
         q_ = qkv[:, :, :H]
         # the mean over L of the attended features comes out of the attention epilogue (column sums of the stored O) where the
         # kernel family supports it, instead of a pass that re-reads [Bc, L, H]
-        pool = K.zeros_f32((Bc, H), q_.device) if K.attn_pool_supported(q_, heads) else None
-        att, lse = K.attn_fwd(q_, qkv[:, :, H:2 * H], qkv[:, :, 2 * H:], heads, scale, dropout=_site(drop, 12 + m), pool_sum=pool)
-        pooled_ctx = K.meanpool_fwd(att) if pool is None else K.cast_to_bf16(pool, scale=1.0 / Ls[m])
+        pooled_ctx = torch.empty((Bc, H), device=q_.device, dtype=q_.dtype) if K.attn_pool_supported(q_, heads) else None
+        att, lse = K.attn_fwd(q_, qkv[:, :, H:2 * H], qkv[:, :, 2 * H:], heads, scale, dropout=_site(drop, 12 + m), pooled=pooled_ctx)
+        if pooled_ctx is None:
+            pooled_ctx = K.meanpool_fwd(att)
         K.linear_fwd(pooled_ctx, W.w(pre + "out_proj.weight"), W.f32(pre + "out_proj.bias"), out=pooled_out[:, m * H:(m + 1) * H])
         if keep:
             st[mod] = dict(enh=enhanced[m], qkv=qkv, att=att, lse=lse, pooled_ctx=pooled_ctx)

@@ -101,6 +101,8 @@ def check(rc: int, what: str) -> None:
 
 
 def stream_ptr() -> C.c_void_p:
+    """the CURRENT device's current stream: every entry point launches in the current CUDA context, so callers working on another
+    device than the current one must switch first (`require_cuda` checks that operands live on the current device)"""
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -117,9 +119,17 @@ def ptr(t) -> C.c_void_p:
 
 
 def require_cuda(*tensors) -> None:
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise B200FusionError("b200 fusion kernels need CUDA tensors (no CPU fallback exists)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise B200FusionError(f"operand on cuda:{t.device.index} but the current device is cuda:{cur}: the kernels launch on the current "
+                                  "device's stream -- wrap the call in torch.cuda.device(tensor.device)")
 
 
 def launch_count() -> int:

@@ -588,12 +588,11 @@ int attn_fwd_tc(const b200f_attn_args& a, cudaStream_t st) {
   p.B = a.B; p.H = a.H; p.Lq = a.Lq; p.Lk = a.Lk; p.scale = a.scale;
   p.O = static_cast<bf16*>(a.O); p.ldo = a.ldo; p.LSE = a.LSE;
   p.pool = a.pool_sum;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::TOTAL));
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::TOTAL));
-    configured = true;
   }
   // a single 128-query tile per (batch, head) leaves the second softmax warpgroup of the two-tile kernel idle: use the
   // one-tile-per-CTA kernel there (measured Lq=30, Lk=512: 0.094 ms vs 0.122 ms).  b200f_debug_set(4, 1|2) forces either.
@@ -1454,15 +1453,14 @@ int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st) {
     attn_delta_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(static_cast<const bf16*>(a.dO), a.lddo, static_cast<const bf16*>(a.O), a.ldo, a.delta, a.B, a.H, a.Lq);
     if ((rc = check_launch("attn_delta_kernel"))) return rc;
   }
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::TOTAL));
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem::TOTAL));
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dq2Smem::TOTAL));
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dkv2Smem::TOTAL));
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dq2Smem::TOTAL));
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dkv2Smem::TOTAL));
-    configured = true;
   }
   CUtensorMap tq, tdo, tk, tv, to;
   if (g_attn_bwd_variant == 0) {

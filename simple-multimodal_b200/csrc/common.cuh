@@ -39,6 +39,19 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 int num_sms();
 
+// cudaFuncSetAttribute is per device: "configured once" flags are kept per device ordinal (one process may drive several GPUs)
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 // ---------------------------------------------------------------- dtype helpers
 typedef __nv_bfloat16 bf16;
 

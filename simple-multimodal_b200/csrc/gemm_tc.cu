@@ -743,10 +743,9 @@ static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   using S = PairSmem<BN, STAGES, EB>;
   auto kern = gemm_tc_pair_kernel<BN, STAGES, A_MN, B_MN, EB>;
   p.epi_stride = (EB - 1) * EPI_STAGE_BYTES;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    configured = true;
   }
   kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, tc, p);
   return check_launch("gemm_tc_pair_kernel");
@@ -756,10 +755,9 @@ template <int BN, int STAGES, int A_MN, int B_MN>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmTcParams& p, int grid, cudaStream_t st) {
   using S = GemmSmem<BN, STAGES>;
   auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    configured = true;
   }
   kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, tc, p);
   return check_launch("gemm_tc_kernel");

@@ -402,11 +402,10 @@ int infonce_lse_tc(const void* x, const void* y, float* lse, float* diag, int64_
   p.diag_off = diag_off; p.inv_tau = inv_tau; p.diag = diag;
   p.part_m = static_cast<float*>(workspace);
   p.part_l = p.part_m + size_t(grid.y) * Bl;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(infonce_lse_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NceSmem::TOTAL_LSE));
     B200F_CHECK_CUDA(cudaFuncSetAttribute(infonce_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NceSmem::TOTAL));
-    configured = true;
   }
   infonce_lse_tc_kernel<<<grid, NCE_THREADS, NceSmem::TOTAL_LSE, st>>>(tx, ty, p);
   if ((rc = check_launch("infonce_lse_tc_kernel"))) return rc;
@@ -423,11 +422,10 @@ int infonce_grad_tc(const void* x, const void* y, const float* lse_x, const floa
   if (rc) return rc;
   p.diag_off = diag_off; p.inv_tau = inv_tau;
   p.lse_x = lse_x; p.lse_y = lse_y; p.gscale = gscale_dev; p.coef = coef; p.dx = dx;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(infonce_lse_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NceSmem::TOTAL_LSE));
     B200F_CHECK_CUDA(cudaFuncSetAttribute(infonce_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NceSmem::TOTAL));
-    configured = true;
   }
   infonce_grad_tc_kernel<<<grid, NCE_THREADS, NceSmem::TOTAL, st>>>(tx, ty, p);
   return check_launch("infonce_grad_tc_kernel");

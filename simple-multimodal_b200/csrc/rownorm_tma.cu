@@ -309,10 +309,9 @@ static int launch_fwd(const T* x, const float* gamma, const float* beta, const T
   stages = stages > 8 ? 8 : stages;
   B200F_REQUIRE(stages >= 2, B200F_ERR_SHAPE, "layernorm (TMA): H=%d does not fit two stages", H);
   const size_t bytes = stages * stage + 2 * stages * sizeof(uint64_t);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024));
-    configured = true;
   }
   const long long tiles = (rows + CW * R - 1) / (CW * R);
   const int grid = int(tiles < num_sms() ? tiles : num_sms());
@@ -331,10 +330,9 @@ static int launch_bwd(const T* dy, const T* x, const float* mean, const float* r
   stages = stages > 8 ? 8 : stages;
   B200F_REQUIRE(stages >= 2, B200F_ERR_SHAPE, "layernorm backward (TMA): H=%d does not fit two stages", H);
   const size_t bytes = stages * stage + 2 * stages * sizeof(uint64_t) + tail;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024));
-    configured = true;
   }
   const long long tiles = (rows + CW - 1) / CW;
   const int grid = int(tiles < num_sms() ? tiles : num_sms());

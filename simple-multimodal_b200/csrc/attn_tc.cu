@@ -1115,6 +1115,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           for (int e = 0; e < 8; ++e) dl = fmaf(fo[e], fg[e], dl);
         }
       }
+      fence_proxy_async_smem();                      // generic reads of the TMA-loaded dO / O tiles before the TMA refill (WAR across proxies)
       __syncwarp();
       if (lane == 0) mbar_arrive(q_empty);           // this warp is done with the item's dO / O tiles
       if (qrow < p.Lq) p.delta[ri] = dl;             // the dKdV kernel (next launch on the stream) reads it

@@ -105,6 +105,10 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) layernorm_fwd_tma_kernel(con
           if (NIN >= 3) p2[NIN >= 3 ? r : 0][NIN >= 3 ? i : 0].load(sp2 + off);
         }
       }
+    // WAR across proxies: the generic-proxy reads above must be ordered before the async-proxy (TMA) write that refills this stage.
+    // An mbarrier arrive alone does not order them (round 2: one row in ~1e4 launches was read after the refill had begun, always in
+    // a CTA's first tiles where the memory pipe is most congested -- tools/repro_full_stash.py); the proxy fence does.
+    fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + s);           // the stage is in registers: hand it back to the producer
     if (++s == stages) { s = 0; ph ^= 1; }
@@ -228,6 +232,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) layernorm_bwd_tma_kernel(con
           if (NIN >= 3) rres[NIN >= 3 ? i : 0].load(sres + vi * VN);
         }
       }
+      fence_proxy_async_smem();                       // generic reads of the stage before the TMA refill (see the forward kernel)
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
       if (++s == stages) { s = 0; ph ^= 1; }

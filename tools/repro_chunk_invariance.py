@@ -46,8 +46,13 @@ def where(a, b, name):
     return f"{name}: {int((d > 0).sum())} elements differ, max abs {float(d.max()):.3e} (ref max {float(a.float().abs().max()):.3e}), samples {rows[:12]}{'...' if len(rows) > 12 else ''} ({len(rows)} samples)"
 
 
+for kv in os.environ.get("KNOBS", "").split(","):
+    if kv:
+        k_, v_ = kv.split("=")
+        lib.b200f_debug_set(int(k_), int(v_))
+print("knobs:", os.environ.get("KNOBS", "(default)"), flush=True)
 ref = run(1024, True)
-for trial in range(8):
+for trial in range(int(os.environ.get("TRIALS", "8"))):
     r = run(64, False)
     msgs = [where(ref[0], r[0], "fused"), where(ref[2][:, :H], r[2][:, :H], "pooled_text"), where(ref[2][:, H:2 * H], r[2][:, H:2 * H], "pooled_audio"),
             where(ref[2][:, 2 * H:], r[2][:, 2 * H:], "pooled_video")] + [where(a, b, f"dx{i}") for i, (a, b) in enumerate(zip(ref[1], r[1]))]

@@ -49,3 +49,32 @@ def test_fused_adamw_refuses_cpu_and_half():
     p.grad = torch.zeros(4)
     with pytest.raises(pkg.B200FusionError):
         pkg.FusedAdamW([p]).step()
+
+
+def test_fused_adamw_resumes_a_torch_adamw_checkpoint_and_bumps_versions():
+    """the reference trainer checkpoints torch.optim.AdamW's state_dict (training/advanced_trainer.py): its `step` entries are
+    tensors; FusedAdamW must resume from it and continue exactly like torch.  Also: the kernel writes parameters through raw pointers,
+    so it must bump their version counters (operand caches such as mult_engine._Weights key on them)."""
+    pa, pb = _models()
+    ref = torch.optim.AdamW(pa, lr=1e-3, weight_decay=0.01)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for _ in range(3):
+        for x in pa:
+            x.grad = torch.randn(x.shape, device="cuda", generator=g)
+        ref.step()
+    with torch.no_grad():
+        for x, y in zip(pa, pb):
+            y.copy_(x)
+    ours = pkg.FusedAdamW(pb, lr=1e-3, weight_decay=0.01)
+    ours.load_state_dict(ref.state_dict())
+    assert all(torch.is_tensor(st["step"]) for st in ours.state.values())        # what torch saved
+    v0 = [y._version for y in pb]
+    for _ in range(2):
+        for x, y in zip(pa, pb):
+            grad = torch.randn(x.shape, device="cuda", generator=g)
+            x.grad, y.grad = grad.clone(), grad.clone()
+        ref.step(); ours.step()
+    for x, y in zip(pa, pb):
+        assert float((x - y).abs().max()) / max(float(x.abs().max()), 1e-12) < 2e-6
+    assert all(st["step"] == 5 for st in ours.state.values())
+    assert all(y._version > v for y, v in zip(pb, v0))

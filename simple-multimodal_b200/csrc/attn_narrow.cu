@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(128) attn_nk_fwd_kernel(const NarrowParams p) 
       if (DROP) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const uint32_t cm = uint32_t(nt * 8 + 2 * t + e) * kDropColMul;
+          const uint32_t cm = drop_col_attn(uint32_t(nt * 8 + 2 * t + e));
           if (!drop_keep_c(rk0, cm, p.drop_thr)) pv[e] = 0.f;
           if (!drop_keep_c(rk1, cm, p.drop_thr)) pv[2 + e] = 0.f;
         }
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(128, 2) attn_nk_bwd_kernel(const NarrowParams 
         const float p1 = valid ? ex2_approx(fmaf(s[nt][2 + e], c, nl1)) : 0.f;
         float k0 = 1.f, k1 = 1.f;
         if (DROP) {
-          const uint32_t cm = uint32_t(key) * kDropColMul;
+          const uint32_t cm = drop_col_attn(uint32_t(key));
           k0 = drop_keep_c(rk0, cm, p.drop_thr) ? p.inv_keep : 0.f;
           k1 = drop_keep_c(rk1, cm, p.drop_thr) ? p.inv_keep : 0.f;
         }
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(128, 3) attn_nk_bwd2_kernel(const NarrowParams
           const float p1 = valid ? ex2_approx(fmaf(s[nt][2 + e], c, nl1)) : 0.f;
           float k0 = 1.f, k1 = 1.f;
           if (DROP) {
-            const uint32_t cm = uint32_t(key) * kDropColMul;
+            const uint32_t cm = drop_col_attn(uint32_t(key));
             k0 = drop_keep_c(rk0, cm, p.drop_thr) ? p.inv_keep : 0.f;
             k1 = drop_keep_c(rk1, cm, p.drop_thr) ? p.inv_keep : 0.f;
           }
@@ -804,7 +804,7 @@ __global__ void __launch_bounds__(128, 2) attn_nq_fwd_kernel(const NarrowParams 
         if (DROP) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const uint32_t cm = uint32_t(key0 + nt * 8 + 2 * t + e) * kDropColMul;
+            const uint32_t cm = drop_col_attn(uint32_t(key0 + nt * 8 + 2 * t + e));
             if (!drop_keep_c(rk[mt][0], cm, p.drop_thr)) pv[e] = 0.f;
             if (!drop_keep_c(rk[mt][1], cm, p.drop_thr)) pv[2 + e] = 0.f;
           }
@@ -1017,7 +1017,7 @@ __global__ void __launch_bounds__(128, 2) attn_nq_bwd_kernel(const NarrowParams 
       }
     }
     const bool va = key0 + g < p.Lk, vb = key0 + g + 8 < p.Lk;
-    const uint32_t cma = uint32_t(key0 + g) * kDropColMul, cmb = uint32_t(key0 + g + 8) * kDropColMul;
+    const uint32_t cma = drop_col_attn(uint32_t(key0 + g)), cmb = drop_col_attn(uint32_t(key0 + g + 8));
     uint32_t pa[2][4], dsa[2][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
@@ -1251,7 +1251,7 @@ __global__ void __launch_bounds__(128, 3) attn_nq_bwd2_kernel(const NarrowParams
         }
       }
       const bool va = key0 + g < p.Lk, vb = key0 + g + 8 < p.Lk;
-      const uint32_t cma = uint32_t(key0 + g) * kDropColMul, cmb = uint32_t(key0 + g + 8) * kDropColMul;
+      const uint32_t cma = drop_col_attn(uint32_t(key0 + g)), cmb = drop_col_attn(uint32_t(key0 + g + 8));
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         float pd[4], ds[4];

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(128) attn_fwd_simt(const AttnP p) {
   sum = warp_sum(sum);
   if (p.drop_thr) {                                  // mask what multiplies V; the row sum stays that of the undropped scores
     const uint32_t rk = drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, uint32_t(gw));
-    for (int j = lane; j < p.Lk; j += 32) sc[j] = drop_keep(rk, uint32_t(j), p.drop_thr) ? sc[j] * p.inv_keep : 0.f;
+    for (int j = lane; j < p.Lk; j += 32) sc[j] = drop_keep_attn(rk, uint32_t(j), p.drop_thr) ? sc[j] * p.inv_keep : 0.f;
   }
   __syncwarp();
   const float inv = 1.f / sum;
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_simt(const AttnP p) {
       s = fmaf(qs[d], to_f32(k[d]), s);
       dp = fmaf(gs[d], to_f32(v[d]), dp);
     }
-    if (p.drop_thr) dp = drop_keep(drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, uint32_t(gw)), uint32_t(j), p.drop_thr) ? dp * p.inv_keep : 0.f;
+    if (p.drop_thr) dp = drop_keep_attn(drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, uint32_t(gw)), uint32_t(j), p.drop_thr) ? dp * p.inv_keep : 0.f;
     ds[j] = expf(s - lse) * (dp - dl);
   }
   __syncwarp();
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_simt(const AttnP p) {
     const float pij = expf(s * p.scale - p.LSE[ri]);
     float pd = pij;                                  // dropped + rescaled probability (multiplies dO in dV)
     if (p.drop_thr) {
-      const bool keep = drop_keep(drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, uint32_t(ri)), uint32_t(j), p.drop_thr);
+      const bool keep = drop_keep_attn(drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, uint32_t(ri)), uint32_t(j), p.drop_thr);
       dp = keep ? dp * p.inv_keep : 0.f;
       pd = keep ? pij * p.inv_keep : 0.f;
     }

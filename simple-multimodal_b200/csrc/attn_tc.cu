@@ -490,6 +490,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const float nmc = -m_use * c;
         const uint64_t nmc2 = f2_pack(nmc, nmc);
         uint64_t lsum2 = 0ull;
+        const uint32_t rkh[2] = {rk ^ (uint32_t(2 * j) * kDropColMulHi), rk ^ (uint32_t(2 * j + 1) * kDropColMulHi)};   // dropout: row key ^ 64-key group term
         if (j > 0) {                                   // PV_t(j-1) must have retired before P_t is overwritten / O_t rescaled
           mbar_wait(&pv_done[t], pv_cnt & 1);          // (holding all of P_t in registers to wait later spills at 216 registers: measured slower)
           ++pv_cnt;
@@ -505,10 +506,9 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
               f2_unpack(f2_fma(f2_pack_u(r[q][i], r[q][i + 1]), c2, nmc2), x0, x1);
               float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
               lsum2 = f2_add(lsum2, f2_pack(e0, e1));
-              if (DROP) {
-                const uint32_t cc = uint32_t(j * TK + q * 32 + i) * kDropColMul;
-                e0 = drop_keep_c(rk, cc, p.drop_thr) ? e0 : 0.f;
-                e1 = drop_keep_c(rk, cc + kDropColMul, p.drop_thr) ? e1 : 0.f;
+              if (DROP) {                            // key = j*128 + q*32 + i: 64-key group 2j + q/2 (hoisted xor), offset (q%2)*32 + i (immediate)
+                e0 = drop_keep_c(rkh[q >> 1], uint32_t((q & 1) * 32 + i) * kDropColMul, p.drop_thr) ? e0 : 0.f;
+                e1 = drop_keep_c(rkh[q >> 1], uint32_t((q & 1) * 32 + i + 1) * kDropColMul, p.drop_thr) ? e1 : 0.f;
               }
               pk[i >> 1] = pack_bf16(e0, e1);
             }
@@ -1137,6 +1137,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sdp_free[t]);      // the next S_t / dP_t may be computed under this tile's exp work
+        const uint32_t rkh = rk ^ (uint32_t(j) * kDropColMulHi);
         uint32_t pk[2][16];                            // all of dS_t(j) in registers first: the wait for the smem tile comes after the math
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -1145,9 +1146,9 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             float x0, x1, d0, d1;
             f2_unpack(f2_fma(f2_pack_u(rs[hf][i], rs[hf][i + 1]), c2, nlse22), x0, x1);
             uint64_t m2 = sc2;
-            if (DROP) {
-              const uint32_t cc = uint32_t(j * BT + hf * 32 + i) * kDropColMul;
-              m2 = f2_pack(drop_keep_c(rk, cc, p.drop_thr) ? sck : 0.f, drop_keep_c(rk, cc + kDropColMul, p.drop_thr) ? sck : 0.f);
+            if (DROP) {                            // key = j*64 + hf*32 + i: 64-key group j (hoisted xor), offset hf*32 + i (immediate)
+              m2 = f2_pack(drop_keep_c(rkh, uint32_t(hf * 32 + i) * kDropColMul, p.drop_thr) ? sck : 0.f,
+                           drop_keep_c(rkh, uint32_t(hf * 32 + i + 1) * kDropColMul, p.drop_thr) ? sck : 0.f);
             }
             const uint64_t t2 = f2_fma(f2_pack_u(rp[hf][i], rp[hf][i + 1]), m2, ndl2);
             f2_unpack(f2_mul(f2_pack(ex2_approx(x0), ex2_approx(x1)), t2), d0, d1);
@@ -1339,7 +1340,7 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       const int k0 = kb * 2 * TK + t * TK;
       if (k0 >= p.Lk) continue;
       const long long stat_base = ((long long)b * p.H + h) * p.Lq;
-      const uint32_t jc = uint32_t(k0 + row) * kDropColMul;       // dropout: this thread's key column
+      const uint32_t jc = drop_col_attn(uint32_t(k0 + row));      // dropout: this thread's key column
       const float sck = p.scale * p.inv_keep;
       // per-query statistics of a tile: thread t128 < 64 fetches LSE, the others delta; the NEXT tile's value is requested one
       // iteration ahead so the global-load latency hides under this tile's exp work

@@ -135,6 +135,15 @@ __host__ __device__ __forceinline__ bool drop_keep_c(uint32_t row_key, uint32_t 
 __host__ __device__ __forceinline__ bool drop_keep(uint32_t row_key, uint32_t col, uint32_t thr32) {
   return drop_keep_c(row_key, col * kDropColMul, thr32);
 }
+// Attention-probability sites: the column term decomposes by XOR at 64-key granularity, term(col) = (col / 64) * MulHi ^ (col % 64) * Mul
+// (== col * Mul for col < 64).  The softmax loops walk a row in 64- / 128-key tiles with the in-tile offsets known at compile time, so
+// `row_key ^ tile term` is hoisted per tile and the element costs LOP3 (xor with an immediate) + IMAD + ISETP -- the integer add that
+// `(tile base + offset) * Mul` needed per element is gone (1 of ~11.5 instructions per score in the issue-bound forward / dQ kernels).
+constexpr uint32_t kDropColMulHi = 0xC2B2AE35u;
+__host__ __device__ __forceinline__ uint32_t drop_col_attn(uint32_t col) { return ((col >> 6) * kDropColMulHi) ^ ((col & 63u) * kDropColMul); }
+__host__ __device__ __forceinline__ bool drop_keep_attn(uint32_t row_key, uint32_t col, uint32_t thr32) {
+  return drop_keep_c(row_key, drop_col_attn(col), thr32);
+}
 // Dropout epoch: a device-side word mixed into the row key by every kernel that generates a mask.  It exists for CUDA graphs:
 // kernel arguments (the seeds) are frozen at capture, so a captured training step starts with a one-thread kernel that
 // advances the epoch -- every replay then draws fresh masks, and forward / backward of one replay still agree.  Eager use

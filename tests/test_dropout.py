@@ -40,10 +40,14 @@ def threshold(p):
     return 0 if t <= 0 else min(int(t), 4294967295)
 
 
-def keep_mask(lo, hi, rows, cols, p, epoch=0):
-    """[len(rows), len(cols)] bool: element kept"""
+def keep_mask(lo, hi, rows, cols, p, epoch=0, attn=False):
+    """[len(rows), len(cols)] bool: element kept.  attn: the attention-probability sites' column term (drop_col_attn: XOR-decomposed at
+    64-key granularity, equal to the plain col * Mul below 64); otherwise col * Mul (GEMM epilogue, GAT, 3-token attention)."""
     rk = row_key(lo, hi, rows, epoch)[:, None]
-    cm = (np.asarray(cols, dtype=np.uint64) * np.uint64(0x9E3779B1)) & M32
+    cols = np.asarray(cols, dtype=np.uint64)
+    cm = (cols * np.uint64(0x9E3779B1)) & M32
+    if attn:
+        cm = (((cols >> np.uint64(6)) * np.uint64(0xC2B2AE35)) & M32) ^ (((cols & np.uint64(63)) * np.uint64(0x9E3779B1)) & M32)
     h = ((rk ^ cm[None, :]) * np.uint64(0x85EBCA6B)) & M32
     return h >= np.uint64(threshold(p))
 
@@ -53,9 +57,10 @@ def inv_keep(p):
 
 
 # ---- CPU: statistics of the mask ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("attn", [False, True], ids=["plain", "attention"])
 @pytest.mark.parametrize("p", [0.1, 0.5])
-def test_mask_rate_and_independence(p):
-    m = keep_mask(0x1234ABCD, 0x9876FEDC, np.arange(4096), np.arange(512), p).astype(np.float64)
+def test_mask_rate_and_independence(p, attn):
+    m = keep_mask(0x1234ABCD, 0x9876FEDC, np.arange(4096), np.arange(512), p, attn=attn).astype(np.float64)
     n = m.size
     assert abs(m.mean() - (1 - p)) < 4 * math.sqrt(p * (1 - p) / n)
     assert np.abs(m.mean(0) - (1 - p)).max() < 6 * math.sqrt(p * (1 - p) / m.shape[0])      # every column
@@ -64,7 +69,9 @@ def test_mask_rate_and_independence(p):
     var = (c * c).mean()
     for a, b in ((c[:, :-1], c[:, 1:]), (c[:-1, :], c[1:, :]), (c[:-1, :-1], c[1:, 1:]), (c[:, :-2], c[:, 2:])):
         assert abs((a * b).mean() / var) < 5 / math.sqrt(a.size)                              # neighbours uncorrelated
-    other = keep_mask(0x1234ABCE, 0x9876FEDC, np.arange(4096), np.arange(512), p).astype(np.float64)
+    for d in (64, 128, 192):                                                                  # across the 64-key groups of the attention term
+        assert abs((c[:, :-d] * c[:, d:]).mean() / var) < 5 / math.sqrt(c[:, d:].size)
+    other = keep_mask(0x1234ABCE, 0x9876FEDC, np.arange(4096), np.arange(512), p, attn=attn).astype(np.float64)
     assert abs(((other - other.mean()) * c).mean() / var) < 5 / math.sqrt(n)                 # a new seed is a new mask
 
 
@@ -114,7 +121,7 @@ def test_attention_dropout_matches_explicit_mask(dtype, shape):
     db = torch.zeros(3, W, device="cuda")
     K.attn_bwd(do, q, k, v, o, lse, heads, 0.125, dq, dk, dv, dbq=db[0], dbk=db[1], dbv=db[2], dropout=(p, lo, hi))
     torch.cuda.synchronize()
-    mask = torch.from_numpy(keep_mask(lo, hi, np.arange(B * heads * Lq), np.arange(Lk), p)).view(B, heads, Lq, Lk).double()
+    mask = torch.from_numpy(keep_mask(lo, hi, np.arange(B * heads * Lq), np.arange(Lk), p, attn=True)).view(B, heads, Lq, Lk).double()
     qd, kd, vd = (t.detach().double().cpu().requires_grad_(True) for t in (q, k, v))
     split = lambda t, L: t.view(B, L, heads, 64).transpose(1, 2)
     s = split(qd, Lq) @ split(kd, Lk).transpose(-1, -2) * 0.125
@@ -281,7 +288,7 @@ def test_attention_dropout_mask_at_nonzero_epoch(shape):
         torch.cuda.synchronize()
     finally:
         K.dropout_epoch(0)
-    mask = torch.from_numpy(keep_mask(lo, hi, np.arange(B * heads * Lq), np.arange(Lk), p, epoch=5)).view(B, heads, Lq, Lk).double()
+    mask = torch.from_numpy(keep_mask(lo, hi, np.arange(B * heads * Lq), np.arange(Lk), p, epoch=5, attn=True)).view(B, heads, Lq, Lk).double()
     qd, kd, vd = (t.detach().double().cpu().requires_grad_(True) for t in (q, k, v))
     split = lambda t, L: t.view(B, L, heads, 64).transpose(1, 2)
     s_ = split(qd, Lq) @ split(kd, Lk).transpose(-1, -2) * 0.125

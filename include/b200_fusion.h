@@ -58,7 +58,7 @@ int b200f_device_supported(int device);
  * GEMM with fused epilogue:  C[m,n] = epi( alpha * sum_k A(m,k) * B(n,k) )
  *   a_layout 0: A stored [M,K] (K contiguous)   1: A stored [K,M] (M contiguous)
  *   b_layout 0: B stored [N,K] (K contiguous)   1: B stored [K,N] (N contiguous)
- *   epi(x) = [relu]( x + bias[n] + residual[m,n] ) * (relu_mask[m,n] > 0 ? 1 : 0)
+ *   epi(x) = [relu]( x + bias[n] + residual[m,n] ) * (relu_mask[m,n] > 0 ? 1 : 0)      (relu_mask or its 1-bit form sign_bits)
  * Replaces every nn.Linear on the path (fusion_layers.py:21-28,55-57,124-128,195-200,238,
  * 304-327,395-412,471-476 and the packed in/out projections of nn.MultiheadAttention,
  * torch/nn/functional.py:5833-5860,6653) in forward (layouts 0/0), input-gradient (0/1) and
@@ -84,6 +84,13 @@ typedef struct {
                                            stored C (the bias gradient of the Linear whose output
                                            gradient C is, e.g. ffn.0.bias from the FFN2 input-gradient
                                            GEMM); summed in the epilogue of the tcgen05 kernels      */
+  /* The ReLU' mask as ONE BIT per element instead of the stored activation (round 2): the Linear+ReLU(+Dropout) forward GEMM
+   * writes `sign_bits_out` (bit set <=> the stored C element is > 0, i.e. passed the ReLU and was kept by the dropout), the
+   * input-gradient GEMM of the next Linear reads it as `sign_bits` in place of `relu_mask` -- 1/16 of the bytes (the FFN2
+   * input-gradient GEMM of fusion_layers.py:195-200 was half HBM-bound on re-reading the [M, 2048] hidden layer).  Layout:
+   * [M, ldsb] 32-bit words, word c of a row covers columns 32c .. 32c+31 in the library's own bit order (opaque: only valid
+   * between these two fields).  bf16 tcgen05 path only, N % 64 == 0, ldsb even and >= N / 32, 8-byte aligned; NULL = off.   */
+  uint32_t* sign_bits_out; const uint32_t* sign_bits; int64_t ldsb;
 } b200f_gemm_args;
 int b200f_gemm(const b200f_gemm_args* args, void* stream);
 

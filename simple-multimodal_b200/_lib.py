@@ -32,7 +32,8 @@ class GemmArgs(C.Structure):
                 ("relu_mask", C.c_void_p), ("ldm", C.c_int64),
                 ("alpha", C.c_float), ("flags", C.c_int32), ("dtype", C.c_int32), ("split_k", C.c_int32),
                 ("dropout_p", C.c_float), ("drop_seed_lo", C.c_uint32), ("drop_seed_hi", C.c_uint32),
-                ("colsum", C.c_void_p)]
+                ("colsum", C.c_void_p),
+                ("sign_bits_out", C.c_void_p), ("sign_bits", C.c_void_p), ("ldsb", C.c_int64)]
 
 
 class AttnArgs(C.Structure):

@@ -42,6 +42,8 @@ extern bool g_dbg_six_stages;
 extern bool g_dbg_no_tma_store;
 extern bool g_dbg_no_tma_store_aux;
 extern bool g_dbg_late_aux;
+extern int g_dbg_colsum;
+extern bool g_dbg_no_spec_epi;
 extern bool g_dbg_no_ln_tma;
 extern int g_attn_fwd_variant;
 extern int g_attn_bwd_variant;
@@ -77,7 +79,10 @@ int b200f_gemm(const b200f_gemm_args* a, void* stream) {
   if (a->colsum && (a->flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) && a->dtype == B200F_BF16)
     return b200f::fail(B200F_ERR_UNSUPPORTED, "gemm: colsum needs the output in the operand dtype");
   if (!(a->dropout_p >= 0.f && a->dropout_p < 1.f)) return b200f::fail(B200F_ERR_SHAPE, "gemm: dropout_p=%f not in [0,1)", a->dropout_p);
-  const bool extras = a->colsum || a->dropout_p > 0.f;
+  const bool bits = a->sign_bits_out || a->sign_bits;
+  if (bits && !(a->dtype == B200F_BF16 && b200f::gemm_tc_eligible(*a) && b200f::gemm_tc_colsum_fused(*a)))
+    return b200f::fail(B200F_ERR_UNSUPPORTED, "gemm: sign_bits / sign_bits_out exist on the bf16 tcgen05 path only (bf16 output, N %% 64 == 0, aligned rows)");
+  const bool extras = a->colsum || a->dropout_p > 0.f || bits;
   if (a->dropout_p > 0.f && (a->flags & (B200F_EPI_OUT_F32 | B200F_EPI_ACCUM)) && a->dtype == B200F_BF16)
     return b200f::fail(B200F_ERR_UNSUPPORTED, "gemm: dropout needs the output in the operand dtype");
   if (a->dtype == B200F_BF16 && b200f::gemm_tc_eligible(*a) && (!extras || b200f::gemm_tc_colsum_fused(*a)))
@@ -122,6 +127,8 @@ int b200f_debug_set(int key, unsigned value) {
     case 10: b200f::g_attn_narrow = int(value); break;
     case 11: b200f::g_dbg_no_tma_store_aux = value != 0; break;
     case 12: b200f::g_dbg_late_aux = value != 0; break;
+    case 13: b200f::g_dbg_colsum = int(value); break;
+    case 14: b200f::g_dbg_no_spec_epi = value != 0; break;
     default: return b200f::fail(B200F_ERR_UNSUPPORTED, "unknown debug key %d", key);
   }
   return B200F_OK;

@@ -39,8 +39,14 @@ struct GemmTcParams {
   uint32_t drop_thr, drop_seed_lo, drop_seed_hi;   // inverted dropout on the output (staged bf16 epilogue only); 0 = off
   float inv_keep;
   int tma_store;   // bf16 output without residual / mask: staged tiles leave through cp.async.bulk.tensor stores (tensor map of C)
+  int dbg_colsum;  // debug (b200f_debug_set(13, v)): 1 = column sums computed but the REDs skipped, 2 = column sums skipped (timing experiments only)
   int late_aux;    // debug (b200f_debug_set(12, 1)): prefetch the aux block one column block ahead instead of all at tile start
   int epi_stride;  // byte distance of a warp's two epilogue staging tiles (EPI_STAGE_BYTES), or 0 when the launch has a single tile per warp
+  // one-bit ReLU' mask (b200f_gemm_args::sign_bits*): [M, ldsb] words, word c of a row = columns 32c..32c+31, element e of the word at
+  // bit 8*(e % 4) + e / 4 (the order the PRMT-based packing below produces)
+  uint32_t* sbits_out;
+  const uint32_t* sbits;
+  long long ldsb;
 };
 
 template <int BN, int STAGES>
@@ -176,9 +182,16 @@ __device__ __forceinline__ void epi_issue_aux(const GemmTcParams& p, uint8_t* st
 // columns [col_base, col_base + NCOLS) of rows [row0, row0 + 32).  Block 0's aux prefetch was issued by the caller.
 // EXTRAS = dropout and/or column sums requested: a separate instantiation, so the plain epilogue (which bounds the K = 512
 // GEMMs) carries none of their instructions or registers (measured: the runtime-flag version cost those GEMMs 10-15 %).
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+__host__ __device__ constexpr int sbit_pos(int e) { return 8 * (e & 3) + (e >> 2); }   // element e (0..31) of a 32-column word
+
 template <int NCOLS, bool EXTRAS>
 __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, const CUtensorMap* tmc, uint8_t* stage, const float* bias_s, uint32_t t_row,
-                                                   long long row0, int lane, int n_base, int c_begin, bool relu) {
+                                                   long long row0, int lane, int n_base, int c_begin, bool relu, uint2 sb0, uint2 sb1) {
   constexpr int NBLK = NCOLS / 64;
   const long long row = row0 + lane;
   const int crow = lane >> 3, cchunk = lane & 7;             // coalesced phase: 4 rows x 8 chunks per instruction
@@ -230,6 +243,7 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, const 
     uint32_t r[2][32];
     tmem_ld32(t_row + c0, r[0]);
     tmem_ld32(t_row + c0 + 32, r[1]);
+    const uint2 sbw = blk ? sb1 : sb0;                        // this block's two words of the one-bit mask (if any)
     uint4 aux[8];
     if (has_aux) {
 #pragma unroll
@@ -276,9 +290,28 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, const 
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = f[j] > 0.f ? v[j] : 0.f;
         }
+        if (EXTRAS && p.sbits) {                             // the same mask, one bit per element (loaded before the accumulator wait)
+          const uint32_t w = h ? sbw.y : sbw.x;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = (w & (1u << sbit_pos(g * 8 + j))) ? v[j] : 0.f;
+        }
         Vec16<bf16> ov; ov.pack(v);
         outv[h * 4 + g] = ov.raw;
       }
+    }
+    if (EXTRAS && p.sbits_out) {
+      // One bit per stored element: set <=> the bf16 value is > 0.  The outputs are ReLU'd (halves in [+0, +inf] -- max(-0, +0) = +0 --
+      // or NaN), so half + 0x7FFF carries into its top bit exactly when the half is non-zero, without crossing into the other half;
+      // PRMT in sign-replicate mode spreads the two top bits of two words over four bytes, one LOP3 drops them at this group's bit
+      // position: 1 integer instruction per element.
+      uint32_t wb[2] = {0u, 0u};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t t0 = outv[q].x + 0x7FFF7FFFu, t1 = outv[q].y + 0x7FFF7FFFu, t2 = outv[q].z + 0x7FFF7FFFu, t3 = outv[q].w + 0x7FFF7FFFu;
+        wb[q >> 2] |= prmt(t0, t1, 0xFDB9u) & (0x01010101u << (2 * (q & 3)));
+        wb[q >> 2] |= prmt(t2, t3, 0xFDB9u) & (0x01010101u << (2 * (q & 3) + 1));
+      }
+      if (row < p.M) *reinterpret_cast<uint2*>(p.sbits_out + row * p.ldsb + (col0 >> 5)) = make_uint2(wb[0], wb[1]);
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(st + sw128_offset(lane, q)) = outv[q];   // the cells this lane consumed
@@ -299,14 +332,14 @@ __device__ __forceinline__ void epilogue_tile_bf16(const GemmTcParams& p, const 
         if (row0 + rr < p.M) *reinterpret_cast<uint4*>(cbase + (long long)rr * p.ldc) = outv[it];
       }
     }
-    if (EXTRAS && p.colsum) {
+    if (EXTRAS && p.colsum && p.dbg_colsum != 2) {
       // bias gradient: column sums of the 32 x 64 block just staged (the rounded values that were stored).  A lane owns
       // columns 2*lane, 2*lane+1 (one conflict-free word per row); even lanes collect 4 columns and issue one vector RED.
       // (round 2: on the warp-level tensor path -- ONES x tile -- instead of a 32-row LDS loop per lane; ptx.cuh)
       const int nr = p.M - row0 < 32 ? int(p.M - row0) : 32;
       float cs[8][2];
       colsum32x64_hmma(st, nr, lane, cs);
-      if (lane < 4) {
+      if (lane < 4 && (p.dbg_colsum != 1 || cs[0][0] == 12345.678f)) {
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) red_add_v2(p.colsum + col0 + nt * 8 + 2 * lane, cs[nt][0], cs[nt][1]);
       }
@@ -386,16 +419,158 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, const CUten
         epi_issue_aux(p, stage + (blk & 1) * p.epi_stride, row0, n_base + c_begin + blk * 64, lane);
     }
   }
+  uint2 sb0 = make_uint2(0u, 0u), sb1 = sb0;                   // one-bit mask words of this lane's row: fetched before the accumulator wait
+  if (staged16 && p.sbits && row0 + lane < p.M) {
+    const uint32_t* sp = p.sbits + (row0 + lane) * p.ldsb + ((n_base + c_begin) >> 5);
+    if (n_base + c_begin + 64 <= p.N) sb0 = __ldg(reinterpret_cast<const uint2*>(sp));
+    if (BN / 2 > 64 && n_base + c_begin + 128 <= p.N) sb1 = __ldg(reinterpret_cast<const uint2*>(sp + 2));
+  }
   asm volatile("bar.sync 1, 256;" ::: "memory");             // bias slice visible to all epilogue warps
   mbar_wait(full_bar, full_phase);
   tc_fence_after();
   if (staged16)
-    if (p.drop_thr || p.colsum) epilogue_tile_bf16<BN / 2, true>(p, tmc, stage, bias_tile + c_begin, t_row, row0, lane, n_base, c_begin, relu);
-    else epilogue_tile_bf16<BN / 2, false>(p, tmc, stage, bias_tile + c_begin, t_row, row0, lane, n_base, c_begin, relu);
+    if (p.drop_thr || p.colsum || p.sbits || p.sbits_out) epilogue_tile_bf16<BN / 2, true>(p, tmc, stage, bias_tile + c_begin, t_row, row0, lane, n_base, c_begin, relu, sb0, sb1);
+    else epilogue_tile_bf16<BN / 2, false>(p, tmc, stage, bias_tile + c_begin, t_row, row0, lane, n_base, c_begin, relu, sb0, sb1);
   else if (out_f32 && p.vec_ok)
     epilogue_tile_f32<BN / 2>(p, stage, bias_tile + c_begin, t_row, row0, lane, n_base, c_begin, accum, relu);
   else
     epilogue_columns(p, t_row, row0 + lane, row0 + lane < p.M, n_base, c_begin, c_begin + BN / 2, out_f32, accum, relu);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Specialised epilogues (round 2).  The generic epilogue above decides every feature at run time inside fully unrolled code; ncu on the
+// K = 512 -> N = 2048 GEMMs of a MulT block showed what that costs once any "extra" is on: the two epilogue warps of a scheduler run
+// a serial chain (6-7 clk per instruction), so every instruction is on the critical path, the kernel's 200 KB of SASS misses the
+// instruction cache (15 % of the samples stalled on `no_inst`), and the 168-register cap (3 warps per scheduler) spills.  The hot
+// feature sets therefore get their own kernel instantiation with the features as template constants (EPI bit set): no runtime branch,
+// no dead registers, a fraction of the code.  Preconditions checked by the host: bf16 output, 16-byte aligned rows, N % 64 == 0 (a
+// 64-column block is inside the matrix or skipped), bulk tensor stores, two staging tiles per warp.
+// ------------------------------------------------------------------------------------------------
+enum : int { E_SPEC = 1, E_BIAS = 2, E_RES = 4, E_RELU = 8, E_DROP = 16, E_SBOUT = 32, E_SBIN = 64, E_COLSUM = 128 };
+
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile_spec(const GemmTcParams& p, const CUtensorMap* tmc, uint8_t* stage, float* bias_tile, uint64_t* full_bar,
+                                                   uint32_t full_phase, uint32_t t_row, long long row0, int lane, int et, int n_base, int col_half) {
+  constexpr bool BIAS = (EPI & E_BIAS) != 0, RES = (EPI & E_RES) != 0, RELU = (EPI & E_RELU) != 0, DROP = (EPI & E_DROP) != 0;
+  constexpr bool SBOUT = (EPI & E_SBOUT) != 0, SBIN = (EPI & E_SBIN) != 0, COLSUM = (EPI & E_COLSUM) != 0;
+  constexpr int NBLK = BN / 2 / 64;
+  static_assert(NBLK == 2, "two 64-column blocks per warp, one staging tile each");
+  static_assert(!(DROP && RES), "dropout rides on alpha and the bias slice: not combined with a residual here");
+  const int c_begin = col_half * (BN / 2);
+  const long long row = row0 + lane;
+  if (BIAS && et < BN) bias_tile[et] = (n_base + et < p.N) ? __ldg(p.bias + n_base + et) * (DROP ? p.inv_keep : 1.f) : 0.f;
+  if (RES) {                                                  // both staging tiles are about to receive the residual blocks: the bulk stores of
+    if (lane == 0) tma_store_wait_read();                     // the previous tile must be done reading them (they have had the whole mainloop)
+    __syncwarp();
+#pragma unroll
+    for (int blk = 0; blk < NBLK; ++blk) epi_issue_aux(p, stage + blk * EPI_STAGE_BYTES, row0, n_base + c_begin + blk * 64, lane);
+  }
+  uint2 sb[NBLK];
+  if (SBIN) {                                                 // one-bit mask words of this lane's row, in flight across the accumulator wait
+#pragma unroll
+    for (int blk = 0; blk < NBLK; ++blk) {
+      sb[blk] = make_uint2(0u, 0u);
+      if (row < p.M && n_base + c_begin + blk * 64 + 64 <= p.N)
+        sb[blk] = __ldg(reinterpret_cast<const uint2*>(p.sbits + row * p.ldsb + ((n_base + c_begin + blk * 64) >> 5)));
+    }
+  }
+  if (BIAS) asm volatile("bar.sync 1, 256;" ::: "memory");    // bias slice visible to all epilogue warps
+  mbar_wait(full_bar, full_phase);
+  tc_fence_after();
+  const float* bias_s = bias_tile + c_begin;
+  const uint32_t rk = DROP ? drop_row_key_e(p.drop_seed_lo, p.drop_seed_hi, uint32_t(row)) : 0u;
+  const float al = DROP ? p.alpha * p.inv_keep : p.alpha;     // 1/(1-p) folded into alpha and the bias slice; relu commutes with it
+  const uint64_t al2 = f2_pack(al, al);
+#pragma unroll
+  for (int blk = 0; blk < NBLK; ++blk) {
+    const int c0 = c_begin + blk * 64;
+    const int col0 = n_base + c0;
+    uint8_t* st = stage + blk * EPI_STAGE_BYTES;
+    if (RES) {
+      if (blk + 1 < NBLK) cp_async_wait<1>(); else cp_async_wait<0>();
+    } else {
+      if (lane == 0) tma_store_wait_read1();                  // the bulk store that last read THIS staging tile (two blocks ago) is done with it
+    }
+    __syncwarp();
+    if (col0 >= p.N) continue;                                // warp-uniform; N % 64 == 0: a block is never ragged
+    uint32_t r[2][32];
+    tmem_ld32(t_row + c0, r[0]);
+    tmem_ld32(t_row + c0 + 32, r[1]);
+    uint4 aux[RES ? 8 : 1];
+    if (RES) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) aux[q] = *reinterpret_cast<const uint4*>(st + sw128_offset(lane, q));
+    }
+    tmem_ld_wait();
+    uint4 outv[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float v[8];
+        const uint32_t* a = &r[h][g * 8];
+        if (BIAS) {
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + blk * 64 + h * 32 + g * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias_s + blk * 64 + h * 32 + g * 8 + 4);
+          f2_unpack(f2_fma(f2_pack_u(a[0], a[1]), al2, f2_pack(b0.x, b0.y)), v[0], v[1]);
+          f2_unpack(f2_fma(f2_pack_u(a[2], a[3]), al2, f2_pack(b0.z, b0.w)), v[2], v[3]);
+          f2_unpack(f2_fma(f2_pack_u(a[4], a[5]), al2, f2_pack(b1.x, b1.y)), v[4], v[5]);
+          f2_unpack(f2_fma(f2_pack_u(a[6], a[7]), al2, f2_pack(b1.z, b1.w)), v[6], v[7]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) f2_unpack(f2_mul(f2_pack_u(a[2 * j], a[2 * j + 1]), al2), v[2 * j], v[2 * j + 1]);
+        }
+        if (RES) {
+          float f[8];
+          Vec16<bf16> av; av.raw = aux[h * 4 + g]; av.unpack(f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += f[j];
+        }
+        if (RELU) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (DROP) {
+          const uint32_t cc = uint32_t(col0 + h * 32 + g * 8) * kDropColMul;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = drop_keep_c(rk, cc + uint32_t(j) * kDropColMul, p.drop_thr) ? v[j] : 0.f;
+        }
+        if (SBIN) {
+          const uint32_t w = h ? sb[blk].y : sb[blk].x;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = (w & (1u << sbit_pos(g * 8 + j))) ? v[j] : 0.f;
+        }
+        Vec16<bf16> ov; ov.pack(v);
+        outv[h * 4 + g] = ov.raw;
+      }
+    }
+    if (SBOUT) {                                              // see the generic epilogue for the bit arithmetic
+      uint32_t wb[2] = {0u, 0u};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t t0 = outv[q].x + 0x7FFF7FFFu, t1 = outv[q].y + 0x7FFF7FFFu, t2 = outv[q].z + 0x7FFF7FFFu, t3 = outv[q].w + 0x7FFF7FFFu;
+        wb[q >> 2] |= prmt(t0, t1, 0xFDB9u) & (0x01010101u << (2 * (q & 3)));
+        wb[q >> 2] |= prmt(t2, t3, 0xFDB9u) & (0x01010101u << (2 * (q & 3) + 1));
+      }
+      if (row < p.M) *reinterpret_cast<uint2*>(p.sbits_out + row * p.ldsb + (col0 >> 5)) = make_uint2(wb[0], wb[1]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(st + sw128_offset(lane, q)) = outv[q];
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) { tma_store_2d(tmc, st, col0, int(row0)); tma_store_commit(); }
+    if (COLSUM) {
+      const int nr = p.M - row0 < 32 ? int(p.M - row0) : 32;
+      float cs[8][2];
+      colsum32x64_hmma(st, nr, lane, cs);
+      if (lane < 4) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) red_add_v2(p.colsum + col0 + nt * 8 + 2 * lane, cs[nt][0], cs[nt][1]);
+      }
+      __syncwarp();
+    }
+  }
 }
 
 template <int BN, int STAGES, int A_MN, int B_MN>
@@ -554,7 +729,7 @@ struct PairSmem {
   static_assert(TOTAL <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 };
 
-template <int BN, int STAGES, int A_MN, int B_MN, int EB>
+template <int BN, int STAGES, int A_MN, int B_MN, int EB, int EPI = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_c,
                     const GemmTcParams p) {
@@ -680,7 +855,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const uint32_t acc_phase = (it >> 1) & 1;
       const long long row0 = (long long)m_blk * 2 * BM + (long long)rank * BM + lane_grp * 32;
       const uint32_t t_row = tmem_base + (uint32_t(lane_grp * 32) << 16) + acc * BN;
-      epilogue_tile<BN>(p, &tma_c, stage, bias_s + acc * BN, &tmem_full[acc], acc_phase, t_row, row0, lane, threadIdx.x - 64, n_blk * BN, col_half);
+      if constexpr (EPI != 0)
+        epilogue_tile_spec<BN, EPI>(p, &tma_c, stage, bias_s + acc * BN, &tmem_full[acc], acc_phase, t_row, row0, lane, threadIdx.x - 64, n_blk * BN, col_half);
+      else
+        epilogue_tile<BN>(p, &tma_c, stage, bias_s + acc * BN, &tmem_full[acc], acc_phase, t_row, row0, lane, threadIdx.x - 64, n_blk * BN, col_half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
@@ -733,15 +911,17 @@ uint32_t g_dbg_mn_lbo = 0, g_dbg_mn_sbo = 0, g_dbg_mn_kadv = 0;
 
 bool g_dbg_disable_pair = false;     // b200f_debug_set(3, 1): force the single-CTA kernel (A/B testing)
 bool g_dbg_no_tma_store = false;     // b200f_debug_set(8, 1): LDS + STG copy-out instead of bulk tensor stores (A/B testing)
+int g_dbg_colsum = 0;                // b200f_debug_set(13, v): see GemmTcParams::dbg_colsum
+bool g_dbg_no_spec_epi = false;      // b200f_debug_set(14, 1): every launch through the generic (run-time flag) epilogue (A/B testing)
 bool g_dbg_late_aux = false;         // b200f_debug_set(12, 1): aux blocks prefetched one column block ahead (round-1 schedule) instead of at tile start
 bool g_dbg_no_tma_store_aux = false; // b200f_debug_set(11, 1): launches with a residual / mask block keep the LDS + STG copy-out (A/B testing)
 bool g_dbg_six_stages = false;       // b200f_debug_set(7, 1): 6-stage / one-staging-tile pair kernel for launches without an aux block.
                                      // Measured no faster than 5 stages on any MulT shape (profiles/r01_e): the ring depth is not the limiter.
 
-template <int BN, int STAGES, int A_MN, int B_MN, int EB>
+template <int BN, int STAGES, int A_MN, int B_MN, int EB, int EPI = 0>
 static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, GemmTcParams p, int grid, cudaStream_t st) {
   using S = PairSmem<BN, STAGES, EB>;
-  auto kern = gemm_tc_pair_kernel<BN, STAGES, A_MN, B_MN, EB>;
+  auto kern = gemm_tc_pair_kernel<BN, STAGES, A_MN, B_MN, EB, EPI>;
   p.epi_stride = (EB - 1) * EPI_STAGE_BYTES;
   static PerDeviceOnce configured;
   if (configured.first()) {
@@ -831,11 +1011,20 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
   }
   p.epi_stride = EPI_STAGE_BYTES;
   p.late_aux = g_dbg_late_aux ? 1 : 0;
+  p.dbg_colsum = g_dbg_colsum;
   p.colsum = a.colsum;
   p.drop_thr = drop_threshold(a.dropout_p); p.drop_seed_lo = a.drop_seed_lo; p.drop_seed_hi = a.drop_seed_hi;
   p.inv_keep = 1.f / (1.f - a.dropout_p);
   if (a.colsum || p.drop_thr)
     B200F_REQUIRE(gemm_tc_colsum_fused(a), B200F_ERR_UNSUPPORTED, "gemm(tcgen05): fused colsum / dropout need bf16 output, N %% 64 == 0 and aligned rows");
+  p.sbits_out = a.sign_bits_out; p.sbits = a.sign_bits; p.ldsb = a.ldsb;
+  if (a.sign_bits_out || a.sign_bits) {
+    B200F_REQUIRE(gemm_tc_colsum_fused(a), B200F_ERR_UNSUPPORTED, "gemm(tcgen05): sign_bits need bf16 output, N %% 64 == 0 and aligned rows");
+    B200F_REQUIRE(a.ldsb % 2 == 0 && a.ldsb * 32 >= a.N && (reinterpret_cast<uintptr_t>(a.sign_bits_out) & 7) == 0 && (reinterpret_cast<uintptr_t>(a.sign_bits) & 7) == 0,
+                  B200F_ERR_ALIGN, "gemm: sign_bits rows must be 8-byte aligned (ldsb even, ldsb * 32 >= N)");
+    B200F_REQUIRE(!a.sign_bits_out || (a.flags & B200F_EPI_RELU), B200F_ERR_UNSUPPORTED, "gemm: sign_bits_out is the mask of a ReLU output (B200F_EPI_RELU)");
+    B200F_REQUIRE(!(a.sign_bits && a.relu_mask), B200F_ERR_UNSUPPORTED, "gemm: relu_mask and sign_bits are two forms of the same mask; pass one");
+  }
   // K-major SW128: rows of 128 B, 8-row groups 1024 B apart, +32 B per K=16 step inside the swizzle row.
   // MN-major SW128: 64-element (128 B) MN chunks, k rows 128 B apart, 8-k-row groups 1024 B apart (SBO),
   //                 MN chunks BK*128 B apart (LBO), +16 k rows = 2048 B per K=16 step.
@@ -855,6 +1044,17 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
         case 2: return launch_pair<256, 6, 1, 0, 1>(ta, tb, tc, p, 2 * clusters, st);
         default: return launch_pair<256, 6, 1, 1, 1>(ta, tb, tc, p, 2 * clusters, st);
       }
+    }
+    // the hot feature sets of the MulT schedule run kernels whose epilogue has them as template constants (epilogue_tile_spec)
+    if (p.tma_store && vec_ok && a.N % 64 == 0 && split == 1 && !g_dbg_no_spec_epi && !g_dbg_late_aux && !g_dbg_colsum && !a.relu_mask) {
+      const int feat = E_SPEC | (a.bias ? E_BIAS : 0) | (a.residual ? E_RES : 0) | ((a.flags & B200F_EPI_RELU) ? E_RELU : 0) | (p.drop_thr ? E_DROP : 0) |
+                       (a.sign_bits_out ? E_SBOUT : 0) | (a.sign_bits ? E_SBIN : 0) | (a.colsum ? E_COLSUM : 0);
+      if (pkey == 0 && feat == (E_SPEC | E_BIAS | E_RES)) return launch_pair<256, 5, 0, 0, 2, E_SPEC | E_BIAS | E_RES>(ta, tb, tc, p, 2 * clusters, st);
+      if (pkey == 0 && feat == (E_SPEC | E_BIAS | E_RELU | E_DROP | E_SBOUT))
+        return launch_pair<256, 5, 0, 0, 2, E_SPEC | E_BIAS | E_RELU | E_DROP | E_SBOUT>(ta, tb, tc, p, 2 * clusters, st);
+      if (pkey == 0 && feat == (E_SPEC | E_BIAS | E_RELU | E_SBOUT)) return launch_pair<256, 5, 0, 0, 2, E_SPEC | E_BIAS | E_RELU | E_SBOUT>(ta, tb, tc, p, 2 * clusters, st);
+      if (pkey == 1 && feat == (E_SPEC | E_SBIN | E_COLSUM)) return launch_pair<256, 5, 0, 1, 2, E_SPEC | E_SBIN | E_COLSUM>(ta, tb, tc, p, 2 * clusters, st);
+      if (pkey == 1 && feat == (E_SPEC | E_RES)) return launch_pair<256, 5, 0, 1, 2, E_SPEC | E_RES>(ta, tb, tc, p, 2 * clusters, st);
     }
     switch (pkey) {
       case 0: return launch_pair<256, 5, 0, 0, 2>(ta, tb, tc, p, 2 * clusters, st);

@@ -46,10 +46,15 @@ GEMM_PROFILE = None          # None, or a list collecting (start_event, stop_eve
 def gemm(a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_layout: int = 0, b_layout: int = 0,
          out: Optional[Tensor] = None, bias: Optional[Tensor] = None, residual: Optional[Tensor] = None,
          relu_mask: Optional[Tensor] = None, relu: bool = False, alpha: float = 1.0, accumulate: bool = False,
-         out_f32: bool = False, split_k: int = 1, colsum: Optional[Tensor] = None, dropout=None) -> Tensor:
+         out_f32: bool = False, split_k: int = 1, colsum: Optional[Tensor] = None, dropout=None,
+         sign_bits_out: Optional[Tensor] = None, sign_bits: Optional[Tensor] = None) -> Tensor:
     """C[M,N] = epi(alpha * sum_k A(m,k) B(n,k)); see b200f_gemm in include/b200_fusion.h.
-    `a`/`b` are 2-D views (row stride = leading dimension)."""
-    require_cuda(a, b, out, bias, residual, relu_mask)
+    `a`/`b` are 2-D views (row stride = leading dimension).  `sign_bits_out` / `sign_bits`: int32 [M, >= N/32], the one-bit form of
+    `relu_mask` written by the ReLU forward GEMM and read by the next Linear's input-gradient GEMM (`sign_bits_for`)."""
+    require_cuda(a, b, out, bias, residual, relu_mask, sign_bits_out, sign_bits)
+    for name, t in (("sign_bits_out", sign_bits_out), ("sign_bits", sign_bits)):
+        if t is not None and (t.dtype != torch.int32 or t.dim() != 2 or t.size(0) != M or t.stride(1) != 1 or t.size(1) * 32 < N):
+            raise B200FusionError(f"gemm: {name} must be an int32 [M, >= N/32] tensor with contiguous rows")
     dt = a.dtype
     if b.dtype != dt:
         raise B200FusionError(f"gemm operand dtypes differ: {dt} vs {b.dtype}")
@@ -85,7 +90,11 @@ def gemm(a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_layout: int = 0, b_l
                       relu_mask=None if relu_mask is None else relu_mask.data_ptr(),
                       ldm=0 if relu_mask is None else relu_mask.stride(0),
                       alpha=alpha, flags=flags, dtype=dtype_code(dt), split_k=split_k,
-                      colsum=None if colsum is None else colsum.data_ptr(), **_drop_fields(dropout))
+                      colsum=None if colsum is None else colsum.data_ptr(),
+                      sign_bits_out=None if sign_bits_out is None else sign_bits_out.data_ptr(),
+                      sign_bits=None if sign_bits is None else sign_bits.data_ptr(),
+                      ldsb=(sign_bits_out if sign_bits_out is not None else sign_bits).stride(0) if (sign_bits_out is not None or sign_bits is not None) else 0,
+                      **_drop_fields(dropout))
     if GEMM_PROFILE is None:
         check(lib().b200f_gemm(C.byref(args), stream_ptr()), "b200f_gemm")
         return out
@@ -114,18 +123,28 @@ def _wgrad_split(tokens: int, n_out: int, k_in: int) -> int:
     return max(1, min(want, tokens // 512 if tokens >= 512 else 1))
 
 
-def linear_fwd(x2: Tensor, w: Tensor, bias: Optional[Tensor], *, relu=False, residual=None, out=None, dropout=None) -> Tensor:
-    """y[M,N] = dropout(relu(x2[M,K] w[N,K]^T + bias (+ residual)))  (relu / dropout optional)."""
+def sign_bits_for(x2: Tensor, n_out: int) -> Optional[Tensor]:
+    """An int32 [M, n_out/32] buffer for the one-bit ReLU' mask of `linear_fwd(x2, w[n_out, K], relu=True)`, or None where the
+    tcgen05 epilogue that writes it does not apply (fp32 parity mode, ragged widths): the caller then keeps `relu_mask=`."""
+    if x2.dtype != torch.bfloat16 or n_out % 64 or x2.size(1) % 8 or x2.stride(0) % 8 or x2.data_ptr() % 16:
+        return None
+    return torch.empty((x2.size(0), n_out // 32), device=x2.device, dtype=torch.int32)
+
+
+def linear_fwd(x2: Tensor, w: Tensor, bias: Optional[Tensor], *, relu=False, residual=None, out=None, dropout=None, sign_bits_out=None) -> Tensor:
+    """y[M,N] = dropout(relu(x2[M,K] w[N,K]^T + bias (+ residual)))  (relu / dropout optional).
+    `sign_bits_out` (from `sign_bits_for`): also write bit (m, n) = [y > 0] for the backward of the ReLU (and dropout)."""
     M, K = x2.shape
-    return gemm(x2, w, M=M, N=w.size(0), K=K, out=out, bias=bias, residual=residual, relu=relu, dropout=dropout)
+    return gemm(x2, w, M=M, N=w.size(0), K=K, out=out, bias=bias, residual=residual, relu=relu, dropout=dropout, sign_bits_out=sign_bits_out)
 
 
-def linear_dgrad(dy2: Tensor, w: Tensor, *, relu_mask=None, residual=None, out=None, colsum=None, alpha: float = 1.0) -> Tensor:
-    """dx[M,K] = dy2[M,N] w[N,K]  (B operand N-contiguous: no transposed weight copy).
+def linear_dgrad(dy2: Tensor, w: Tensor, *, relu_mask=None, sign_bits=None, residual=None, out=None, colsum=None, alpha: float = 1.0) -> Tensor:
+    """dx[M,K] = dy2[M,N] w[N,K]  (B operand N-contiguous: no transposed weight copy), zeroed where `relu_mask` <= 0 / where its
+    one-bit form `sign_bits` is clear.
     `colsum` [K] fp32 += column sums of dx: the bias gradient of the Linear that produced this GEMM's input activation."""
     M, N = dy2.shape
-    return gemm(dy2, w, M=M, N=w.size(1), K=N, a_layout=0, b_layout=1, out=out, relu_mask=relu_mask, residual=residual, colsum=colsum,
-                alpha=alpha)
+    return gemm(dy2, w, M=M, N=w.size(1), K=N, a_layout=0, b_layout=1, out=out, relu_mask=relu_mask, sign_bits=sign_bits, residual=residual,
+                colsum=colsum, alpha=alpha)
 
 
 def linear_wgrad(dy2: Tensor, x2: Tensor, dw: Tensor) -> Tensor:

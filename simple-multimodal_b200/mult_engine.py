@@ -142,7 +142,11 @@ def _chunk_forward(xs, W: _Weights, H: int, heads: int, pooled_out: Tensor, keep
         ctx2 = ctx_.view(-1, H)
         s1 = K.linear_fwd(ctx2, W.w(f"{name}.attention.out_proj.weight"), W.f32(f"{name}.attention.out_proj.bias"), residual=x2[qm])
         x1, mean1, rstd1 = K.layernorm_fwd(s1, W.f32(f"{name}.norm1.weight"), W.f32(f"{name}.norm1.bias"), LN_EPS)
-        hid = K.linear_fwd(x1, W.w(f"{name}.ffn.0.weight"), W.f32(f"{name}.ffn.0.bias"), relu=True, dropout=_site(drop, 2 * bi + 1))
+        # the ReLU' (and dropout) mask of the hidden layer leaves the FFN1 epilogue as one bit per element: the FFN2 input-gradient
+        # GEMM reads 1/16 of the bytes it needed when it looked at the stored hidden layer itself
+        hbits = K.sign_bits_for(x1, 4 * H) if keep else None
+        hid = K.linear_fwd(x1, W.w(f"{name}.ffn.0.weight"), W.f32(f"{name}.ffn.0.bias"), relu=True, dropout=_site(drop, 2 * bi + 1),
+                           sign_bits_out=hbits)
         s2 = K.linear_fwd(hid, W.w(f"{name}.ffn.3.weight"), W.f32(f"{name}.ffn.3.bias"), residual=x1)
         if qm not in first_of:      # first block of this query modality: plain LN2
             first_of[qm] = name
@@ -153,7 +157,7 @@ def _chunk_forward(xs, W: _Weights, H: int, heads: int, pooled_out: Tensor, keep
                                               post1=blk_out[first_of[qm]], post2=x2[qm])
             enhanced[qm] = y
         if keep:
-            st[name] = dict(ctx=ctx_, lse=lse, s1=s1, x1=x1, mean1=mean1, rstd1=rstd1, hid=hid, s2=s2, mean2=mean2, rstd2=rstd2)
+            st[name] = dict(ctx=ctx_, lse=lse, s1=s1, x1=x1, mean1=mean1, rstd1=rstd1, hid=hid, hbits=hbits, s2=s2, mean2=mean2, rstd2=rstd2)
     if keep:
         st["proj"] = proj
     for m, mod in enumerate(MODS):
@@ -208,8 +212,9 @@ def _chunk_backward(st, W: _Weights, H: int, heads: int, dpooled: Tensor, G: Dic
         ds2 = K.layernorm_bwd(d_enh[qm], s["s2"], s["mean2"], s["rstd2"], W.f32(f"{name}.norm2.weight"),
                               G[f"{name}.norm2.weight"], G[f"{name}.norm2.bias"], dxsum=G[f"{name}.ffn.3.bias"])   # + bias grad of FFN2
         K.linear_wgrad(ds2, s["hid"], G[f"{name}.ffn.3.weight"])
-        dhid = K.linear_dgrad(ds2, W.w(f"{name}.ffn.3.weight"), relu_mask=s["hid"],       # ReLU' and the FFN1 bias gradient
-                              colsum=G[f"{name}.ffn.0.bias"], alpha=inv_keep)              # (column sums) fused in the epilogue;
+        dhid = K.linear_dgrad(ds2, W.w(f"{name}.ffn.3.weight"),                           # ReLU' and the FFN1 bias gradient
+                              relu_mask=s["hid"] if s["hbits"] is None else None, sign_bits=s["hbits"],   # (column sums) fused in the
+                              colsum=G[f"{name}.ffn.0.bias"], alpha=inv_keep)                             # epilogue;
         # with dropout the stored hidden is zero where dropped, so the same mask covers it and alpha carries 1/(1-p)
         K.linear_wgrad(dhid, s["x1"], G[f"{name}.ffn.0.weight"])
         dx1 = K.linear_dgrad(dhid, W.w(f"{name}.ffn.0.weight"), residual=ds2)             # + residual path x1 -> s2
@@ -241,7 +246,8 @@ def stash_bytes_per_sample(Ls, H: int, elem: int) -> int:
     tok = sum(Ls)
     per_tok = 6 * H + H + 3 * H + H                 # packed projection, enhanced, self qkv, self ctx
     per_qtok = 2 * (H + H + H + 4 * H + H)          # two query blocks per token: ctx, s1, x1, hid, s2
-    return (per_tok + per_qtok) * tok * elem
+    bits = 2 * (4 * H // 8) if elem == 2 else 0     # one-bit ReLU' masks of the two hidden layers (bf16 path)
+    return (per_tok + per_qtok) * tok * elem + bits * tok
 
 
 def _chunk_drop(drop, ci: int):

@@ -119,6 +119,57 @@ def test_gemm_fused_column_sums(dtype, shape):
     assert float((acc.double() - sums).abs().max()) <= 1e-5 * float(out.float().abs().sum(0).max()) + 1e-4
 
 
+@pytest.mark.parametrize("shape", [(1000, 512, 256), (4133, 2048, 512), (77, 128, 64), (300, 192, 64), (130, 64, 64), (8192, 2048, 512)])
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_gemm_sign_bits_replace_the_relu_mask(shape, p_drop):
+    """The one-bit ReLU' mask: the Linear+ReLU(+Dropout) forward writes bit (m, n) = [stored y > 0]; the input-gradient GEMM that reads
+    the bits gives exactly what it gives when it reads the stored activation as `relu_mask` (FFN1 -> FFN2-dgrad of a MulT block)."""
+    K = importlib.import_module("simple-multimodal_b200.kernels")
+    M, N, Kd = shape
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(M, Kd, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, Kd, device="cuda", generator=g) * Kd ** -0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    bits = K.sign_bits_for(x, N)
+    assert bits is not None and bits.shape == (M, N // 32)
+    bits.fill_(-1)
+    drop = (p_drop, 123, 456) if p_drop else None
+    y = K.linear_fwd(x, w, bias, relu=True, dropout=drop, sign_bits_out=bits)
+    y_plain = K.linear_fwd(x, w, bias, relu=True, dropout=drop)
+    assert torch.equal(y, y_plain)                                                    # writing the bits does not touch the output
+    # decode: element e of a 32-column word sits at bit 8 * (e % 4) + e / 4 (the library's own order, include/b200_fusion.h)
+    e = torch.arange(32, device="cuda")
+    pos = 8 * (e % 4) + e // 4
+    dec = ((bits.to(torch.int64).unsqueeze(-1) >> pos) & 1).reshape(M, N).bool()
+    assert torch.equal(dec, y > 0)
+    frac = float(dec.float().mean())
+    assert 0.3 < frac < 0.6                                                          # about half pass the ReLU, 10 % of those dropped
+    dy = torch.randn(M, 64, device="cuda", generator=g).bfloat16()                   # next Linear: [64, N] weight, dgrad K = 64 -> N
+    w2 = torch.randn(64, N, device="cuda", generator=g).bfloat16()
+    c1, c2 = torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
+    d_mask = K.linear_dgrad(dy, w2, relu_mask=y, colsum=c1, alpha=1.25)
+    d_bits = K.linear_dgrad(dy, w2, sign_bits=bits, colsum=c2, alpha=1.25)
+    assert torch.equal(d_mask, d_bits)
+    assert torch.allclose(c1, c2, rtol=1e-5, atol=1e-3)
+    assert float(d_bits[~dec].abs().max()) == 0.0 and float(d_bits[dec].abs().min()) >= 0.0
+
+
+def test_gemm_sign_bits_bad_args():
+    K = importlib.import_module("simple-multimodal_b200.kernels")
+    x = torch.randn(256, 64, device="cuda").bfloat16()
+    w = torch.randn(128, 64, device="cuda").bfloat16()
+    bits = K.sign_bits_for(x, 128)
+    with pytest.raises(L.B200FusionError, match="ReLU"):
+        K.linear_fwd(x, w, None, sign_bits_out=bits)                                  # no ReLU: the bit trick assumes non-negative outputs
+    assert K.sign_bits_for(x.float(), 128) is None and K.sign_bits_for(x, 120) is None
+    with pytest.raises(L.B200FusionError, match="tcgen05 path only"):
+        K.gemm(x.float(), w.float(), M=256, N=128, K=64, relu=True, sign_bits_out=bits)
+    with pytest.raises(L.B200FusionError, match="int32"):
+        K.linear_fwd(x, w, None, relu=True, sign_bits_out=bits.float())
+    with pytest.raises(L.B200FusionError, match="pass one"):
+        K.linear_dgrad(x, torch.randn(64, 128, device="cuda").bfloat16(), relu_mask=torch.ones(256, 128, device="cuda").bfloat16(), sign_bits=bits)
+
+
 def test_gemm_ragged_bf16_uses_cuda_cores():
     """Leading dimensions that are not 16-byte multiples (7-class logits, 3 gate logits) cannot go through TMA."""
     M, N, K = 130, 7, 512

@@ -89,6 +89,30 @@ if args.only in ("", "gemm"):
             cases.append((f"{name}_dgrad_colsumonly M{M} N{k_in} K{n_out}", 2.0 * M * n_out * k_in,
                           lambda dy=dy, w=w, dxout=dxout, cs=cs: K.linear_dgrad(dy, w, out=dxout, colsum=cs),
                           lambda dy=dy, w=w: torch.matmul(dy, w)))
+        if name == "ffn2":        # ... and with the mask as one bit per element (written by the FFN1 forward epilogue)
+            cs2 = torch.zeros(k_in, device=dev)
+            hb = K.sign_bits_for(x512, k_in)
+            hb.random_(-2**31, 2**31 - 1)
+            cases.append((f"{name}_dgrad_bits M{M} N{k_in} K{n_out}", 2.0 * M * n_out * k_in,
+                          lambda dy=dy, w=w, dxout=dxout, hb=hb: K.linear_dgrad(dy, w, out=dxout, sign_bits=hb),
+                          lambda dy=dy, w=w: torch.matmul(dy, w)))
+            cases.append((f"{name}_dgrad_bits_colsum M{M} N{k_in} K{n_out}", 2.0 * M * n_out * k_in,
+                          lambda dy=dy, w=w, dxout=dxout, hb=hb, cs2=cs2: K.linear_dgrad(dy, w, out=dxout, sign_bits=hb, colsum=cs2),
+                          lambda dy=dy, w=w: torch.matmul(dy, w)))
+            for mode in (1, 2):
+                def dbg(dy=dy, w=w, dxout=dxout, hb=hb, cs2=cs2, mode=mode):
+                    pkg._lib.lib().b200f_debug_set(13, mode)
+                    K.linear_dgrad(dy, w, out=dxout, sign_bits=hb, colsum=cs2)
+                    pkg._lib.lib().b200f_debug_set(13, 0)
+                cases.append((f"{name}_dgrad_bits_colsum_dbg{mode} M{M} N{k_in} K{n_out}", 2.0 * M * n_out * k_in, dbg, lambda dy=dy, w=w: torch.matmul(dy, w)))
+        if name == "ffn1":
+            hb1 = K.sign_bits_for(xin, n_out)
+            cases.append((f"{name}_fwd_bits M{M} N{n_out} K{k_in}", 2.0 * M * n_out * k_in,
+                          lambda xin=xin, w=w, bias=bias, yout=yout, hb1=hb1: K.linear_fwd(xin, w, bias, relu=True, out=yout, sign_bits_out=hb1),
+                          lambda xin=xin, w=w: torch.matmul(xin, w.t())))
+            cases.append((f"{name}_fwd_dropout_bits M{M} N{n_out} K{k_in}", 2.0 * M * n_out * k_in,
+                          lambda xin=xin, w=w, bias=bias, yout=yout, hb1=hb1: K.linear_fwd(xin, w, bias, relu=True, out=yout, dropout=(0.1, 11, 22), sign_bits_out=hb1),
+                          lambda xin=xin, w=w: torch.matmul(xin, w.t())))
         if name == "ffn1":        # FFN1 forward with the hidden-layer dropout generated in the epilogue (the training configuration)
             cases.append((f"{name}_fwd_dropout M{M} N{n_out} K{k_in}", 2.0 * M * n_out * k_in,
                           lambda xin=xin, w=w, bias=bias, yout=yout: K.linear_fwd(xin, w, bias, relu=True, out=yout, dropout=(0.1, 11, 22)),

@@ -17,7 +17,7 @@ pkg = importlib.import_module("simple-multimodal_b200")
 K = pkg.kernels
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--only", default="", help="attn | infonce")
+ap.add_argument("--only", default="", help="attn | infonce | gemm (gemm only on request)")
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--reps", type=int, default=1)
 args = ap.parse_args()
@@ -48,4 +48,26 @@ if args.only in ("", "infonce"):
             gs = torch.ones(1, device=dev)
             K.infonce_grad(x, y, lse_x, lse_y, 1.0 / (0.07 * 2 * Bg), gs, dx, True, 0, 1.0 / 0.07)
         torch.cuda.synchronize()
+if args.only == "gemm":
+    # the K = 512 -> N = 2048 GEMMs of one MulT block at chunk 256 (M = 131072), in launch order:
+    #   0 FFN1 forward (ReLU)            1 + dropout + one-bit mask out      2 FFN2 input gradient, plain
+    #   3 + column sums                  4 + stored-activation mask + sums   5 + one-bit mask + sums (the step's configuration)
+    M = args.batch * 512
+    x = torch.randn(M, 512, device=dev, generator=g).to(torch.bfloat16)
+    w1 = (torch.randn(2048, 512, device=dev, generator=g) * 0.04).to(torch.bfloat16)
+    b1 = torch.randn(2048, device=dev, generator=g) * 0.1
+    w2 = (torch.randn(512, 2048, device=dev, generator=g) * 0.02).to(torch.bfloat16)
+    dy = torch.randn(M, 512, device=dev, generator=g).to(torch.bfloat16)
+    hid = torch.empty(M, 2048, device=dev, dtype=torch.bfloat16)
+    dh = torch.empty_like(hid)
+    bits = K.sign_bits_for(x, 2048)
+    cs = torch.zeros(2048, device=dev)
+    for _ in range(args.reps):
+        K.linear_fwd(x, w1, b1, relu=True, out=hid)
+        K.linear_fwd(x, w1, b1, relu=True, out=hid, dropout=(0.1, 11, 22), sign_bits_out=bits)
+        K.linear_dgrad(dy, w2, out=dh)
+        K.linear_dgrad(dy, w2, out=dh, colsum=cs)
+        K.linear_dgrad(dy, w2, out=dh, relu_mask=hid, colsum=cs)
+        K.linear_dgrad(dy, w2, out=dh, sign_bits=bits, colsum=cs)
+    torch.cuda.synchronize()
 print("ncu_targets: done")

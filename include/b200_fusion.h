@@ -130,7 +130,14 @@ typedef struct {
    * exactly one warp, so the result is bit-reproducible; b200f_pool_finish sums the parts in order and scales -- the `.mean(dim=1)`
    * of the attended features (fusion_layers.py:166-168) straight out of the attention epilogue, no separate pass re-reads O. */
   float* pool_sum;
+  /* backward only, optional (nullable): scratch of b200f_attn_bwd_ws_bytes(args) bytes.  With it, the tcgen05 backward of blocks
+   * with >= 128 queries and keys computes the score gradient dS ONCE: the dK/dV kernel also stores its bf16 dS^T tiles here
+   * (bulk tensor stores straight from the shared-memory operand tiles) and dQ = dS K becomes a memory-bound batched GEMM over
+   * them, instead of a second kernel that recomputes S, P, dP and dS (exp, dropout hash and three of seven MMAs of the backward).
+   * The route is off by default (b200f_attn_bwd_ws_bytes returns 0): on the power-capped B200 it measured neutral, see csrc/attn_tc.cu. */
+  void* bwd_ws; int64_t bwd_ws_bytes;
 } b200f_attn_args;
+int64_t b200f_attn_bwd_ws_bytes(const b200f_attn_args* args); /* 0: this shape / dtype does not use the scratch */
 int32_t b200f_attn_pool_parts(const b200f_attn_args* args);   /* 0: the kernel family serving this shape / dtype has no pooled output */
 /* out[b, c] = scale * sum_p partial[b, p, c]  (p ascending; out bf16 or fp32 by `dtype`, leading dimension ldo) */
 int b200f_pool_finish(const float* partial, void* out, int64_t ldo, int64_t B, int32_t parts, int32_t W, float scale, int32_t dtype, void* stream);

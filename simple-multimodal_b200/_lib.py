@@ -50,7 +50,8 @@ class AttnArgs(C.Structure):
                 ("delta", C.c_void_p),
                 ("dbq", C.c_void_p), ("dbk", C.c_void_p), ("dbv", C.c_void_p),
                 ("dropout_p", C.c_float), ("drop_seed_lo", C.c_uint32), ("drop_seed_hi", C.c_uint32),
-                ("pool_sum", C.c_void_p)]
+                ("pool_sum", C.c_void_p),
+                ("bwd_ws", C.c_void_p), ("bwd_ws_bytes", C.c_int64)]
 
 
 _lib = None
@@ -92,6 +93,10 @@ def lib():
         _lib.b200f_launch_count.restype = C.c_ulonglong
         _lib.b200f_infonce_workspace_bytes.restype = C.c_size_t
         _lib.b200f_attn_pool_parts.restype = C.c_int32
+        _lib.b200f_attn_bwd_ws_bytes.restype = C.c_int64
+        for kv in filter(None, os.environ.get("B200F_DEBUG_SET", "").split(",")):      # A/B experiments only: "key=value,key=value"
+            key, val = kv.split("=")                                                      # (b200f_debug_set, csrc/api.cu)
+            _lib.b200f_debug_set(int(key), int(val))
     return _lib if CALL_PROFILE is None else _ProfiledLib()
 
 

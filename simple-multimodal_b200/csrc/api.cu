@@ -46,6 +46,7 @@ extern int g_dbg_colsum;
 extern bool g_dbg_no_spec_epi;
 extern bool g_dbg_no_ln_tma;
 extern int g_attn_fwd_variant;
+extern int g_attn_bwd_ds_route;
 extern int g_attn_bwd_variant;
 extern int g_infonce_variant;
 void attn_tc_epoch(uint32_t v, int add, cudaStream_t st);
@@ -129,6 +130,7 @@ int b200f_debug_set(int key, unsigned value) {
     case 12: b200f::g_dbg_late_aux = value != 0; break;
     case 13: b200f::g_dbg_colsum = int(value); break;
     case 14: b200f::g_dbg_no_spec_epi = value != 0; break;
+    case 15: b200f::g_attn_bwd_ds_route = int(value); break;
     default: return b200f::fail(B200F_ERR_UNSUPPORTED, "unknown debug key %d", key);
   }
   return B200F_OK;
@@ -141,6 +143,7 @@ int attn_fwd_simt_dispatch(const b200f_attn_args& a, cudaStream_t st);
 int attn_bwd_simt_dispatch(const b200f_attn_args& a, cudaStream_t st);
 int attn_fwd_tc(const b200f_attn_args& a, cudaStream_t st);
 int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st);
+int64_t attn_bwd_ws_bytes(const b200f_attn_args& a);
 int attn_narrow_kind(const b200f_attn_args& a);
 int attn_narrow_pool_parts(const b200f_attn_args& a);
 int attn_fwd_narrow(const b200f_attn_args& a, cudaStream_t st);
@@ -173,6 +176,11 @@ int b200f_attn_fwd(const b200f_attn_args* a, void* stream) {
     return b200f::attn_narrow_kind(*a) ? b200f::attn_fwd_narrow(*a, st) : b200f::attn_fwd_tc(*a, st);
   if (a->pool_sum) return b200f::fail(B200F_ERR_UNSUPPORTED, "attention: pool_sum needs the bf16 / head-dim-64 kernels");
   return b200f::attn_fwd_simt_dispatch(*a, st);
+}
+
+int64_t b200f_attn_bwd_ws_bytes(const b200f_attn_args* a) {
+  if (!a || b200f::attn_narrow_kind(*a)) return 0;
+  return b200f::attn_bwd_ws_bytes(*a);
 }
 
 int b200f_attn_bwd(const b200f_attn_args* a, void* stream) {

@@ -16,6 +16,7 @@
 //          S^T = K Q^T, dP^T = V dO^T, dV += P^T dO, dK += dS^T Q
 #include "common.cuh"
 #include "ptx.cuh"
+#include <string.h>
 
 namespace b200f {
 
@@ -619,26 +620,50 @@ int attn_fwd_tc(const b200f_attn_args& a, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 static constexpr int BT = 64;    // inner tile (keys for the dQ kernel, queries for the dKdV kernel)
 
-// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]; one thread per (b,h,i) row of 64
+// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d].  Thread block (8, H, Z): eight lanes share one 128-byte (row, head) segment (16 bytes
+// each -- a warp instruction reads 512 contiguous bytes of a token row), Z token rows per pass, U passes in flight per thread; no index
+// division on the load path (the first version spent more issue slots on 64-bit div / mod than the memory system needed time).
+static constexpr int DELTA_U = 4;
 __global__ void attn_delta_kernel(const bf16* __restrict__ dO, long long lddo, const bf16* __restrict__ O, long long ldo, float* __restrict__ delta,
                                   int B, int H, int Lq) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)B * H * Lq;
-  if (idx >= total) return;
-  const int h = int(idx % H);
-  const long long bl = idx / H;            // b*Lq + i
-  const bf16* g = dO + bl * lddo + h * HD;
-  const bf16* o = O + bl * ldo + h * HD;
-  float acc = 0.f;
+  const int part = threadIdx.x, h = threadIdx.y;
+  const long long n_rows = (long long)B * Lq;
+  const long long row0 = ((long long)blockIdx.x * DELTA_U) * blockDim.z + threadIdx.z;
+  Vec16<bf16> a[DELTA_U], b2[DELTA_U];
 #pragma unroll
-  for (int c = 0; c < HD; c += 8) {
-    Vec16<bf16> a, b2; a.load(g + c); b2.load(o + c);
-    float fa[8], fb[8]; a.unpack(fa); b2.unpack(fb);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc += fa[e] * fb[e];
+  for (int u = 0; u < DELTA_U; ++u) {
+    const long long bl = row0 + (long long)u * blockDim.z;
+    if (bl < n_rows) {
+      a[u].load(dO + bl * lddo + h * HD + part * 8);
+      b2[u].load(O + bl * ldo + h * HD + part * 8);
+    }
   }
-  const long long b = bl / Lq, i = bl % Lq;
-  delta[(b * H + h) * Lq + i] = acc;
+#pragma unroll
+  for (int u = 0; u < DELTA_U; ++u) {
+    const long long bl = row0 + (long long)u * blockDim.z;     // uniform over the 8 lanes of a segment; a warp holds whole segments
+    float acc = 0.f;
+    if (bl < n_rows) {
+      float fa[8], fb[8];
+      a[u].unpack(fa); b2[u].unpack(fb);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc += fa[e] * fb[e];
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (bl < n_rows && part == 0) {
+      const long long b = bl / Lq, i = bl - b * Lq;
+      delta[(b * H + h) * Lq + i] = acc;
+    }
+  }
+}
+static int launch_delta(const b200f_attn_args& a, cudaStream_t st) {
+  const int z = a.H * 8 >= 256 ? 1 : 256 / (a.H * 8);          // H = 8: 4 token rows per pass, 256 threads
+  B200F_REQUIRE(a.H * 8 <= 1024, B200F_ERR_UNSUPPORTED, "attention(tcgen05): more than 128 heads");
+  const long long n_rows = (long long)a.B * a.Lq, per_block = (long long)DELTA_U * z;
+  attn_delta_kernel<<<(unsigned)((n_rows + per_block - 1) / per_block), dim3(8, a.H, z), 0, st>>>(
+      static_cast<const bf16*>(a.dO), a.lddo, static_cast<const bf16*>(a.O), a.ldo, a.delta, a.B, a.H, a.Lq);
+  return check_launch("attn_delta_kernel");
 }
 
 struct DqSmem {
@@ -1199,10 +1224,13 @@ struct Dkv2Smem {
 };
 
 // work item = (batch, head, 256-key block); TMEM per tile t: S^T_t [256t, +64) dP^T_t [+64, +128) dV_t [+128, +192) dK_t [+192, +256)
-template <bool DROP>
+// DS_OUT: every warp also sends its 32-key slab of each dS^T tile to the scratch tensor [B, H, Lk, Lq] (tm_ds) with one bulk tensor
+// store from the shared-memory operand tile -- the dQ kernel below then needs no softmax work at all.
+template <bool DROP, bool DS_OUT>
 __global__ void __launch_bounds__(B2_THREADS, 1)
 attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
-                        const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p,
+                        const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                        const __grid_constant__ CUtensorMap tm_ds, const AttnTcParams p,
                         const int n_kblk, const int n_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Dkv2Smem::BAR_OFF);
@@ -1401,6 +1429,10 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           mbar_wait(&ds_free[t], dsf_cnt & 1);
           ++dsf_cnt;
         }
+        if (DS_OUT) {                                  // ... and the bulk store of this warp's previous dS^T slab must be done reading it
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+        }
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
@@ -1412,11 +1444,21 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ds_ready[t]);
+        if (lane == 0) {
+          mbar_arrive(&ds_ready[t]);
+          if (DS_OUT) {                                // [32 keys x 64 queries] of dS^T (scaled, dropout applied) -> scratch[b*H + h, query chunk i, k0 + 32 grp .., :]:
+            tma_store_4d(&tm_ds, ds_tile + grp * (32 * 128), 0, k0 + grp * 32, i, b * p.H + h);   // 4 KB contiguous; keys past Lk are clipped
+            tma_store_commit();
+          }
+        }
       }
       mbar_wait(&ds_free[t], dsf_cnt & 1);           // the item's last accumulation MMAs
       ++dsf_cnt;
       tc_fence_after();
+      if (DS_OUT) {                                  // the staging below reuses the dS^T slab
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
       // P^T / dS^T tiles are free once the last accumulation MMA retired: stage dV / dK through this warp's slices of them
       store_rows64(t_dv + lane_addr, p_tile + grp * (32 * 128), p.dV + ((long long)b * p.Lk + k0 + grp * 32) * p.lddv + h * HD, p.lddv,
                    p.Lk - (k0 + grp * 32), lane, DROP ? 1.f / p.scale : 1.f, p.dbv ? p.dbv + h * HD : nullptr);
@@ -1431,6 +1473,122 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   __syncthreads();
   if (warp == 9) tmem_dealloc<512>(tmem_base);
 }
+
+// ------------------------------------------------------------------------------------------------
+// dQ from the stored score gradient:  dQ[b, q, h, :] = sum_k dS[b, h, q, k] K[b, k, h, :]   (dS already carries scale and dropout).
+// A memory-bound batched GEMM: work item = (batch, head, 128-query tile); per 128-key step one TMA stage = the dS^T box
+// [128 keys x 128 queries] (two 64-query SW128 chunks: the A operand, MN-major -- queries contiguous) + the K tile [128 keys x 64]
+// (B operand, MN-major); 8 UMMAs (M = 128 queries, N = 64, K = 16 keys) accumulate into one of two TMEM accumulators; four epilogue
+// warps drain the other one (bf16 rows + the in-proj bias gradient column sums).  4-stage ring = 192 KB in flight per SM.
+// ------------------------------------------------------------------------------------------------
+static constexpr int DQS_THREADS = 192;    // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue (TMEM lane group = warp & 3)
+static constexpr int DQS_ST = 4;
+struct DqDsSmem {
+  static constexpr int DS_OFF = 0;                                   // DQS_ST x 2 x [128 keys x 64 queries]
+  static constexpr int K_OFF = DS_OFF + DQS_ST * 2 * TK * 64 * 2;    // DQS_ST x [128 keys x 64]
+  static constexpr int STG_OFF = K_OFF + DQS_ST * TK * HD * 2;       // 4 warps x [32 x 128 B]
+  static constexpr int BAR_OFF = STG_OFF + 4 * 32 * 128;
+  static constexpr int TOTAL = BAR_OFF + 256;
+};
+
+__global__ void __launch_bounds__(DQS_THREADS, 1)
+attn_bwd_dq_ds_kernel(const __grid_constant__ CUtensorMap tm_ds, const __grid_constant__ CUtensorMap tm_k, const AttnTcParams p,
+                      const int n_qt, const int n_items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DqDsSmem::BAR_OFF);
+  uint64_t* full = bars;                      // [DQS_ST]
+  uint64_t* empty = full + DQS_ST;            // [DQS_ST]
+  uint64_t* acc_full = empty + DQS_ST;        // [2]
+  uint64_t* acc_empty = acc_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_ks = (p.Lk + TK - 1) / TK;
+  if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    tma_prefetch_desc(&tm_ds); tma_prefetch_desc(&tm_k);
+    for (int i = 0; i < DQS_ST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int qt = item % n_qt, h = (item / n_qt) % p.H, b = item / (n_qt * p.H);
+        for (int ks = 0; ks < n_ks; ++ks, ++g) {
+          const int st = g % DQS_ST;
+          mbar_wait(&empty[st], ((g / DQS_ST) & 1) ^ 1);
+          mbar_expect_tx(&full[st], 2 * TK * 64 * 2 + TK * HD * 2);
+          uint8_t* ds = smem + DqDsSmem::DS_OFF + st * (2 * TK * 64 * 2);
+          tma_load_4d(ds, &tm_ds, &full[st], 0, ks * TK, 2 * qt, b * p.H + h);               // 16 KB contiguous each; out-of-range keys / chunks arrive as zeros
+          tma_load_4d(ds + TK * 64 * 2, &tm_ds, &full[st], 0, ks * TK, 2 * qt + 1, b * p.H + h);
+          tma_load_4d(smem + DqDsSmem::K_OFF + st * (TK * HD * 2), &tm_k, &full[st], 0, h, ks * TK, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_bf16(TQ, HD, 1, 1);             // A = dS^T tile read MN-major, B = K tile read MN-major
+    const uint32_t a_lo0 = umma_lo(smem_u32(smem + DqDsSmem::DS_OFF), TK * 128), b_lo0 = umma_lo(smem_u32(smem + DqDsSmem::K_OFF), TK * 128);
+    constexpr uint32_t A16 = 2 * TK * 64 * 2 / 16, B16 = TK * HD * 2 / 16;
+    uint32_t g = 0, it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int ks = 0; ks < n_ks; ++ks, ++g) {
+        const int st = g % DQS_ST;
+        mbar_wait(&full[st], (g / DQS_ST) & 1);
+        tc_fence_after();
+        if (leader) umma_chain<TK / 16>(tmem_base + acc * HD, a_lo0 + st * A16, 128, b_lo0 + st * B16, 128, idesc, ks > 0);   // 16 keys = 2048 B per step
+        if (leader) umma_commit(&empty[st]);
+      }
+      if (leader) umma_commit(&acc_full[acc]);
+    }
+    __syncwarp();
+  } else {
+    const int grp = warp & 3;
+    const uint32_t lane_addr = uint32_t(grp * 32) << 16;
+    uint8_t* stage = smem + DqDsSmem::STG_OFF + (warp - 2) * (32 * 128);
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int qt = item % n_qt, h = (item / n_qt) % p.H, b = item / (n_qt * p.H);
+      const int acc = it & 1;
+      const int q0 = qt * TQ + grp * 32;
+      mbar_wait(&acc_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      store_rows64(tmem_base + acc * HD + lane_addr, stage, p.dQ + ((long long)b * p.Lq + q0) * p.lddq + h * HD, p.lddq, p.Lq - q0, lane, 1.f,
+                   p.dbq ? p.dbq + h * HD : nullptr);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<128>(tmem_base);
+}
+
+// scratch of the dS route: bf16 [B * H, ceil(Lq / 64), Lk, 64] -- per 64-query chunk a [Lk x 64] matrix with 128-byte rows, so the 32-key
+// slabs the dK/dV kernel stores and the 128-key boxes the dQ kernel loads are contiguous (the first version, [B, H, Lk, Lq], made
+// every box 128 separate 128-byte pieces 1 KB apart and the dQ kernel ran at half the memory bandwidth)
+extern int g_attn_bwd_ds_route;
+int64_t attn_bwd_ws_bytes(const b200f_attn_args& a) {
+  if (!g_attn_bwd_ds_route || a.dtype != B200F_BF16 || a.D != HD || a.Lq < 128 || a.Lk < 128) return 0;
+  return (int64_t)a.B * a.H * a.Lk * ((a.Lq + 63) / 64 * 64) * 2;
+}
+// b200f_debug_set(15, 1) turns the dS route on.  OFF by default: measured on the B = 4096 step (same box, alternating runs, profiles/
+// r02_v_*): delta 0.17 + dQ-from-dS 0.95-1.1 ms replace the 1.83 ms recomputing dQ kernel per launch, but the 8.6 GB of extra HBM traffic
+// per launch costs what the saved exp / hash / MMA work gains on this power-capped part (SM clock 1.51 vs 1.54 GHz) -- 277.1 vs 277.7 ms
+// per step, i.e. nothing, for 4.3 GB more memory.  Kept, tested in both forms, for parts that are not power-bound.
+int g_attn_bwd_ds_route = 0;
 
 int g_attn_bwd_variant = 0;      // 0 = persistent two-tile kernels, 1 = one tile per CTA (debug / A-B; b200f_debug_set(5, v))
 
@@ -1452,19 +1610,58 @@ int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st) {
   B200F_REQUIRE(!drop || g_attn_bwd_variant == 0, B200F_ERR_UNSUPPORTED, "attention(tcgen05): dropout needs the persistent kernels");
   const long long rows = (long long)a.B * a.H * a.Lq;
   if (g_attn_bwd_variant != 0) {                     // the persistent dQ kernel computes delta from its own dO / O tiles
-    attn_delta_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(static_cast<const bf16*>(a.dO), a.lddo, static_cast<const bf16*>(a.O), a.ldo, a.delta, a.B, a.H, a.Lq);
-    if ((rc = check_launch("attn_delta_kernel"))) return rc;
+    if ((rc = launch_delta(a, st))) return rc;
   }
   static PerDeviceOnce configured;
   if (configured.first()) {
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::TOTAL));
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem::TOTAL));
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dq2Smem::TOTAL));
-    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dkv2Smem::TOTAL));
+    B200F_CHECK_CUDA(cudaFuncSetAttribute((attn_bwd_dkv_tc2_kernel<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, Dkv2Smem::TOTAL));
+    B200F_CHECK_CUDA(cudaFuncSetAttribute((attn_bwd_dkv_tc2_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, Dkv2Smem::TOTAL));
+    B200F_CHECK_CUDA(cudaFuncSetAttribute((attn_bwd_dkv_tc2_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, Dkv2Smem::TOTAL));
+    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_ds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqDsSmem::TOTAL));
     B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dq2Smem::TOTAL));
-    B200F_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dkv2Smem::TOTAL));
+    B200F_CHECK_CUDA(cudaFuncSetAttribute((attn_bwd_dkv_tc2_kernel<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, Dkv2Smem::TOTAL));
   }
-  CUtensorMap tq, tdo, tk, tv, to;
+  CUtensorMap tq, tdo, tk, tv, to, tds;
+  memset(&tds, 0, sizeof(tds));
+  const int64_t ws_need = attn_bwd_ws_bytes(a);
+  const bool ds_route = g_attn_bwd_variant == 0 && g_attn_bwd_ds_route && a.bwd_ws && ws_need > 0 && a.bwd_ws_bytes >= ws_need && aligned16(a.bwd_ws);
+  if (ds_route) {
+    // delta = rowsum(dO o O) first (the recomputing dQ kernel used to produce it), dK/dV + dS^T, then dQ = dS K
+    if ((rc = launch_delta(a, st))) return rc;
+    const uint64_t n_qc = uint64_t((a.Lq + 63) / 64);
+    const uint64_t dims[4] = {64, uint64_t(a.Lk), n_qc, uint64_t(a.B) * a.H};
+    const uint64_t strides[3] = {128, uint64_t(a.Lk) * 128, n_qc * a.Lk * 128};
+    {  // dKdV + dS^T slabs [32 keys x 64 queries]
+      const uint32_t box[4] = {64, 32, 1, 1};
+      if ((rc = make_tmap_bf16(&tds, a.bwd_ws, 4, dims, strides, box))) return rc;
+      if ((rc = make_head_tmap(&tq, a.Q, a.ldq, a.B, a.H, a.Lq, BT))) return rc;
+      if ((rc = make_head_tmap(&tdo, a.dO, a.lddo, a.B, a.H, a.Lq, BT))) return rc;
+      if ((rc = make_head_tmap(&tk, a.K, a.ldk, a.B, a.H, a.Lk, TK))) return rc;
+      if ((rc = make_head_tmap(&tv, a.V, a.ldv, a.B, a.H, a.Lk, TK))) return rc;
+      const int n_kblk = (a.Lk + 2 * TK - 1) / (2 * TK);
+      const long long n_items = (long long)n_kblk * a.H * a.B;
+      B200F_REQUIRE(n_items < (1ll << 31), B200F_ERR_SHAPE, "attention(tcgen05): too many work items");
+      const int grid = int(n_items < num_sms() ? n_items : num_sms());
+      if (drop) attn_bwd_dkv_tc2_kernel<true, true><<<grid, B2_THREADS, Dkv2Smem::TOTAL, st>>>(tq, tdo, tk, tv, tds, p, n_kblk, int(n_items));
+      else attn_bwd_dkv_tc2_kernel<false, true><<<grid, B2_THREADS, Dkv2Smem::TOTAL, st>>>(tq, tdo, tk, tv, tds, p, n_kblk, int(n_items));
+      if ((rc = check_launch("attn_bwd_dkv_tc2_kernel"))) return rc;
+    }
+    {  // dQ = dS K: dS^T boxes [128 keys x 64 queries], K boxes [128 keys x 64]
+      const uint32_t box[4] = {64, uint32_t(TK), 1, 1};
+      if ((rc = make_tmap_bf16(&tds, a.bwd_ws, 4, dims, strides, box))) return rc;
+      if ((rc = make_head_tmap(&tk, a.K, a.ldk, a.B, a.H, a.Lk, TK))) return rc;
+      const int n_qt = (a.Lq + TQ - 1) / TQ;
+      const long long n_items = (long long)n_qt * a.H * a.B;
+      B200F_REQUIRE(n_items < (1ll << 31), B200F_ERR_SHAPE, "attention(tcgen05): too many work items");
+      const int grid = int(n_items < num_sms() ? n_items : num_sms());
+      attn_bwd_dq_ds_kernel<<<grid, DQS_THREADS, DqDsSmem::TOTAL, st>>>(tds, tk, p, n_qt, int(n_items));
+      if ((rc = check_launch("attn_bwd_dq_ds_kernel"))) return rc;
+    }
+    return B200F_OK;
+  }
   if (g_attn_bwd_variant == 0) {
     B200F_REQUIRE(a.ldo % 8 == 0 && aligned16(a.O), B200F_ERR_ALIGN, "attention(tcgen05): O alignment");
     if ((rc = make_head_tmap(&to, a.O, a.ldo, a.B, a.H, a.Lq, TQ))) return rc;
@@ -1490,8 +1687,8 @@ int attn_bwd_tc(const b200f_attn_args& a, cudaStream_t st) {
       const long long n_items = (long long)n_kblk * a.H * a.B;
       B200F_REQUIRE(n_items < (1ll << 31), B200F_ERR_SHAPE, "attention(tcgen05): too many work items");
       const int grid = int(n_items < num_sms() ? n_items : num_sms());
-      if (drop) attn_bwd_dkv_tc2_kernel<true><<<grid, B2_THREADS, Dkv2Smem::TOTAL, st>>>(tq, tdo, tk, tv, p, n_kblk, int(n_items));
-      else attn_bwd_dkv_tc2_kernel<false><<<grid, B2_THREADS, Dkv2Smem::TOTAL, st>>>(tq, tdo, tk, tv, p, n_kblk, int(n_items));
+      if (drop) attn_bwd_dkv_tc2_kernel<true, false><<<grid, B2_THREADS, Dkv2Smem::TOTAL, st>>>(tq, tdo, tk, tv, tds, p, n_kblk, int(n_items));
+      else attn_bwd_dkv_tc2_kernel<false, false><<<grid, B2_THREADS, Dkv2Smem::TOTAL, st>>>(tq, tdo, tk, tv, tds, p, n_kblk, int(n_items));
       if ((rc = check_launch("attn_bwd_dkv_tc2_kernel"))) return rc;
     }
     return B200F_OK;

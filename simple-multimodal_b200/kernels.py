@@ -368,6 +368,9 @@ def attn_fwd(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float, out: Opt
     return out, lse
 
 
+ATTN_BWD_SCRATCH_MAX = 6 << 30      # bytes; one MulT chunk of 1024 samples at 512 x 512, 8 heads needs 4 GiB
+
+
 def attn_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor, heads: int, scale: float,
              dq: Tensor, dk: Tensor, dv: Tensor, dbq: Optional[Tensor] = None, dbk: Optional[Tensor] = None,
              dbv: Optional[Tensor] = None, dropout=None) -> None:
@@ -387,6 +390,12 @@ def attn_bwd(do: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor
                       dK=dkp, lddk=lddk, dV=dvp, lddv=lddv, delta=delta.data_ptr(),
                       dbq=None if dbq is None else dbq.data_ptr(), dbk=None if dbk is None else dbk.data_ptr(),
                       dbv=None if dbv is None else dbv.data_ptr(), **_drop_fields(dropout))
+    # scratch for the score gradient (bf16 [B, H, Lk, Lq]): with it the tcgen05 backward computes dS once and dQ = dS K is a
+    # memory-bound GEMM; without it (shape not served, or the scratch would exceed ATTN_BWD_SCRATCH_MAX) dQ recomputes S / P / dP
+    need = int(lib().b200f_attn_bwd_ws_bytes(C.byref(args)))
+    if 0 < need <= ATTN_BWD_SCRATCH_MAX:
+        ws = torch.empty(need, device=q.device, dtype=torch.uint8)
+        args.bwd_ws, args.bwd_ws_bytes = ws.data_ptr(), need
     check(lib().b200f_attn_bwd(C.byref(args), stream_ptr()), "b200f_attn_bwd")
 
 

@@ -39,16 +39,20 @@ def packed(B, L, width, dtype, seed):
     return torch.randn(B, L, width, device="cuda", generator=g).to(dtype)
 
 
-@pytest.fixture(params=[0, 1], ids=["persistent", "tile-per-cta"])
+@pytest.fixture(params=[0, 1, 2], ids=["persistent", "tile-per-cta", "persistent-recompute-dq"])
 def tc_variant(request):
-    """both generations of the tcgen05 kernels: b200f_debug_set(4 / 5, v) selects the forward / backward variant"""
+    """both generations of the tcgen05 kernels: b200f_debug_set(4 / 5, v) selects the forward / backward variant; the persistent
+    backward in its two forms: dS stored by the dK/dV kernel + dQ = dS K (default with >= 128 queries and keys), and the dQ kernel that
+    recomputes S / P / dP (b200f_debug_set(15, 0); also what runs when the caller gives no scratch)"""
     lib = pkg._lib.lib()
-    lib.b200f_debug_set(4, 2 if request.param == 0 else 1)
-    lib.b200f_debug_set(5, request.param)
+    lib.b200f_debug_set(4, 1 if request.param == 1 else 2)
+    lib.b200f_debug_set(5, 1 if request.param == 1 else 0)
+    lib.b200f_debug_set(15, 0 if request.param == 2 else 1)
     lib.b200f_debug_set(10, 0)          # shapes with a narrow side stay on the tcgen05 tiles here (test_narrow_attention covers attn_narrow.cu)
     yield request.param
     lib.b200f_debug_set(4, 0)
     lib.b200f_debug_set(5, 0)
+    lib.b200f_debug_set(15, 0)          # the library's default: dQ recomputes (see csrc/attn_tc.cu for the measurement)
     lib.b200f_debug_set(10, 1)
 
 
@@ -56,7 +60,7 @@ def tc_variant(request):
 @pytest.mark.parametrize("shape", SHAPES)
 def test_attention_forward_backward(shape, dtype, tc_variant):
     B, heads, Lq, Lk = shape
-    if dtype == torch.float32 and (tc_variant == 1 or B > 3):
+    if dtype == torch.float32 and (tc_variant >= 1 or B > 3):
         pytest.skip("the CUDA-core fp32 path has one variant; large batches are covered in bf16")
     W = heads * 64
     scale = 1 / math.sqrt(64)

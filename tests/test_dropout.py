@@ -111,7 +111,19 @@ def rel(x, r):
 @pytest.mark.parametrize("dtype,shape", [(torch.bfloat16, (3, 8, 300, 200)), (torch.bfloat16, (2, 8, 512, 512)), (torch.bfloat16, (5, 8, 30, 70)),
                                          (torch.bfloat16, (3, 8, 512, 30)), (torch.bfloat16, (3, 8, 30, 512)), (torch.bfloat16, (2, 8, 100, 17)),
                                          (torch.bfloat16, (2, 8, 17, 100)), (torch.float32, (2, 8, 65, 40))])
-def test_attention_dropout_matches_explicit_mask(dtype, shape):
+@pytest.mark.parametrize("ds_route", [1, 0], ids=["dq-from-stored-dS", "dq-recomputes"])
+def test_attention_dropout_matches_explicit_mask(dtype, shape, ds_route):
+    B, heads, Lq, Lk = shape
+    if ds_route == 0 and not (dtype == torch.bfloat16 and Lq >= 128 and Lk >= 128):
+        pytest.skip("only blocks with >= 128 queries and keys have the two dQ routes")
+    pkg._lib.lib().b200f_debug_set(15, ds_route)
+    try:
+        _attention_dropout_case(dtype, shape)
+    finally:
+        pkg._lib.lib().b200f_debug_set(15, 0)
+
+
+def _attention_dropout_case(dtype, shape):
     B, heads, Lq, Lk = shape
     W, p, lo, hi = heads * 64, 0.25, 0xDEADBEEF, 0x0BADF00D
     g = torch.Generator(device="cuda").manual_seed(1)

@@ -25,8 +25,8 @@ dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)
 heads, W = 8, 512
 
-if args.only in ("", "attn"):
-    for Lq, Lk in ((512, 512), (512, 30), (30, 512)):
+if args.only in ("", "attn", "attn512"):
+    for Lq, Lk in ((512, 512), (512, 30), (30, 512))[:1 if args.only == "attn512" else 3]:
         q, k, v, do = (torch.randn(args.batch, L, W, device=dev, generator=g).to(torch.bfloat16) for L in (Lq, Lk, Lk, Lq))
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         db = torch.zeros(3, W, device=dev)

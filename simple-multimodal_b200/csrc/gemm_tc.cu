@@ -1055,6 +1055,8 @@ int gemm_bf16_tc(const b200f_gemm_args& a, cudaStream_t st) {
       if (pkey == 0 && feat == (E_SPEC | E_BIAS | E_RELU | E_SBOUT)) return launch_pair<256, 5, 0, 0, 2, E_SPEC | E_BIAS | E_RELU | E_SBOUT>(ta, tb, tc, p, 2 * clusters, st);
       if (pkey == 1 && feat == (E_SPEC | E_SBIN | E_COLSUM)) return launch_pair<256, 5, 0, 1, 2, E_SPEC | E_SBIN | E_COLSUM>(ta, tb, tc, p, 2 * clusters, st);
       if (pkey == 1 && feat == (E_SPEC | E_RES)) return launch_pair<256, 5, 0, 1, 2, E_SPEC | E_RES>(ta, tb, tc, p, 2 * clusters, st);
+      if (pkey == 0 && feat == (E_SPEC | E_BIAS)) return launch_pair<256, 5, 0, 0, 2, E_SPEC | E_BIAS>(ta, tb, tc, p, 2 * clusters, st);   // packed projections
+      if (pkey == 1 && feat == E_SPEC) return launch_pair<256, 5, 0, 1, 2, E_SPEC>(ta, tb, tc, p, 2 * clusters, st);                        // plain input gradients
     }
     switch (pkey) {
       case 0: return launch_pair<256, 5, 0, 0, 2>(ta, tb, tc, p, 2 * clusters, st);

@@ -380,7 +380,9 @@ static int nce_setup(const void* x, const void* y, int64_t Bl, int64_t Bg, int32
   p->Bl = int(Bl); p->Bg = int(Bg); p->nk = D / 64; p->D = D;
   p->n_tiles = int((Bg + NT - 1) / NT);
   const int row_tiles = int((Bl + NT - 1) / NT);
-  int splits = (num_sms() + row_tiles - 1) / row_tiles;             // enough CTAs to fill the chip
+  // as many key splits as fit in ONE wave of CTAs (one CTA per SM: the kernels use > 113 KB of shared memory).  Rounding up instead
+  // (round 1: 32 row tiles x 5 splits = 160 CTAs on 148 SMs) put 12 CTAs into a second wave and doubled the kernel's time.
+  int splits = num_sms() / row_tiles;
   if (splits > p->n_tiles) splits = p->n_tiles;
   if (splits > 16) splits = 16;
   if (splits < 1) splits = 1;

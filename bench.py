@@ -65,7 +65,9 @@ class Cfg:
 
 def gemm_traffic():
     """DRAM bytes of one launch of the dominant kernel, from the committed `ncu --set full` capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
     return json.load(open(p)) if os.path.exists(p) else None
 
 

@@ -1,6 +1,7 @@
 """FusedAdamW + device-side gradient clipping against torch.optim.AdamW + torch.nn.utils.clip_grad_norm_ (the reference trainer's
 optimizer step, training/advanced_trainer.py:91-94,174-180) on the same parameters and gradients, two param groups with different
 learning rates, a OneCycleLR schedule, several steps; fp32, 1e-6."""
+import copy
 import importlib
 
 import pytest
@@ -66,7 +67,9 @@ def test_fused_adamw_resumes_a_torch_adamw_checkpoint_and_bumps_versions():
         for x, y in zip(pa, pb):
             y.copy_(x)
     ours = pkg.FusedAdamW(pb, lr=1e-3, weight_decay=0.01)
-    ours.load_state_dict(ref.state_dict())
+    # a checkpoint goes through torch.save / torch.load; load_state_dict alone would SHARE exp_avg / exp_avg_sq with `ref`
+    # (`.to()` of a tensor already on the right device and dtype returns the tensor itself) and both optimizers would update them
+    ours.load_state_dict(copy.deepcopy(ref.state_dict()))
     assert all(torch.is_tensor(st["step"]) for st in ours.state.values())        # what torch saved
     v0 = [y._version for y in pb]
     for _ in range(2):

@@ -16,6 +16,7 @@ is pure Python/torch and cannot travel to the GPU box) on the sam
 from __future__ import annotations
 
 import argparse
+import importlib
 import json
 import os
 import statistics
@@ -480,6 +481,10 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the b200 arm has no CPU fallback (use --impl reference for the CPU path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_cores = []
+    if os.environ.get("B200F_NO_NUMA_BIND", "") != "1":
+        # before any pinned allocation: the process (and its staging buffers) onto the GPU's own NUMA node
+        host_cores = importlib.import_module("simple-multimodal_b200").bind_host_to_gpu(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -535,7 +540,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": args.workload, "head": kind, "batch_per_gpu": batch, "global_batch": b_global, "seq_lens": lens,
                        "hidden": H, "heads": HEADS, "dropout": args.dropout, "modality_dropout": 0.1 if kind == "hierarchical" else None,
-                       "parallelism": f"dp{world}", "warmup_steps_run": warm_done, "host_issue_ms_per_step": host_issue_ms, "host_cpu_ms_per_step": host_cpu_ms, "issue": issue,
+                       "parallelism": f"dp{world}", "warmup_steps_run": warm_done, "host_issue_ms_per_step": host_issue_ms, "host_cpu_ms_per_step": host_cpu_ms, "host_cores_bound": len(host_cores), "issue": issue,
                        "collectives_per_step": (["all_gather(z)", "all_reduce(loss)", "all_gather(lse)", "all_reduce(grads, flat fp32 bucket)"]
                                                 if world > 1 and kind in ("contrastive", "hierarchical") else
                                                 (["all_reduce(grads, flat fp32 bucket)"] if world > 1 else [])),

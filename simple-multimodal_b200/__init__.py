@@ -10,7 +10,7 @@ from ._lib import B200FusionError, LIB_PATH                              # noqa:
 from .fusion_layers import (AdaptiveFusion, ContrastiveFusion, CrossModalTransformer, EarlyFusion, GraphFusion,   # noqa: F401
                             HierarchicalFusion, LateFusion, ModalityDropout, MultimodalTransformer)
 from .ops import GradBucket, allreduce_gradients, global_batch_scale, manual_seed   # noqa: F401
-from .staging import FeaturePrefetcher                                   # noqa: F401
+from .staging import FeaturePrefetcher, bind_host_to_gpu                 # noqa: F401
 from .graphs import GraphedTrainStep                                     # noqa: F401
 from .optim import FusedAdamW                                            # noqa: F401
 from .sequence_features import SequenceProjector, text_pooling_of        # noqa: F401
@@ -18,4 +18,4 @@ from . import prediction_heads                                           # noqa:
 from .prediction_heads import AuxiliaryHeads, EmotionClassifier, SmoothedCrossEntropy   # noqa: F401
 
 __all__ = ["EarlyFusion", "LateFusion", "MultimodalTransformer", "CrossModalTransformer", "GraphFusion", "ContrastiveFusion",
-           "AdaptiveFusion", "HierarchicalFusion", "ModalityDropout", "allreduce_gradients", "GradBucket", "global_batch_scale", "manual_seed", "FeaturePrefetcher", "GraphedTrainStep", "FusedAdamW", "SequenceProjector", "text_pooling_of", "EmotionClassifier", "AuxiliaryHeads", "SmoothedCrossEntropy", "B200FusionError"]
+           "AdaptiveFusion", "HierarchicalFusion", "ModalityDropout", "allreduce_gradients", "GradBucket", "global_batch_scale", "manual_seed", "FeaturePrefetcher", "bind_host_to_gpu", "GraphedTrainStep", "FusedAdamW", "SequenceProjector", "text_pooling_of", "EmotionClassifier", "AuxiliaryHeads", "SmoothedCrossEntropy", "B200FusionError"]

@@ -112,7 +112,16 @@ int b200f_dropout_epoch(uint32_t value, int32_t add, void* stream) {
   return b200f::check_launch("dropout_epoch");
 }
 
-// debug: override MN-major UMMA descriptor geometry (0 restores the default). Not part of the product API.
+// Debug / A-B switches (not part of the product API, not declared in include/b200_fusion.h; B200F_DEBUG_SET="key=value,..." sets
+// them from the environment when the Python binding loads the library).  Every value 0 restores the default unless noted.
+//   0-2  MN-major UMMA descriptor geometry (LBO / SBO / K advance in bytes)      3  no CTA-pair GEMM kernel
+//   4    attention forward: 1 = one tile per CTA, 2 = persistent two-tile        5  attention backward: 1 = one tile per CTA
+//   6    InfoNCE: GEMM + row-kernel route instead of the fused kernels           7  6-stage / one-staging-tile pair GEMM
+//   8    no bulk tensor stores in the GEMM epilogue                              9  LayerNorm without the TMA-staged kernels
+//   10   narrow-side attention: 0 = off (tcgen05 tiles), 1 = default, 2 = v1 backward kernels
+//   11   LDS + STG copy-out for GEMMs with a residual / mask block               12 aux block prefetched one column block ahead
+//   13   column sums: 1 = computed, REDs skipped; 2 = skipped (timing only)      14 generic (run-time flag) GEMM epilogue everywhere
+//   15   attention backward dS route: 1 = on (default 0, see csrc/attn_tc.cu)
 int b200f_debug_set(int key, unsigned value) {
   switch (key) {
     case 0: b200f::g_dbg_mn_lbo = value; break;

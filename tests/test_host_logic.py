@@ -57,3 +57,26 @@ def test_sequence_projector_refuses_cpu_tensors():
         sp(enc, enc, enc)
     with pytest.raises(ValueError):
         pkg.SequenceProjector(Cfg, nn.Linear(8, 16), nn.Linear(8, 16), nn.Linear(8, 16), text_pooling="max")
+
+
+def test_sign_bit_buffers_and_stash_accounting():
+    """One-bit ReLU' mask (b200f_gemm_args::sign_bits*): the buffer exists only where the bf16 tcgen05 epilogue can write it, and the
+    resident-stash estimate of the MulT engine counts it."""
+    K = pkg.kernels
+    x = torch.zeros(96, 512, dtype=torch.bfloat16)
+    bits = K.sign_bits_for(x, 2048)
+    assert bits.dtype == torch.int32 and tuple(bits.shape) == (96, 64) and bits.is_contiguous()
+    assert K.sign_bits_for(x.float(), 2048) is None                       # fp32 parity mode keeps relu_mask=
+    assert K.sign_bits_for(x, 2000) is None and K.sign_bits_for(x[:, :100], 2048) is None
+    me = importlib.import_module("simple-multimodal_b200.mult_engine")
+    Ls, H = (512, 512, 30), 512
+    bf16, fp32 = me.stash_bytes_per_sample(Ls, H, 2), me.stash_bytes_per_sample(Ls, H, 4)
+    assert bf16 - fp32 // 2 == 2 * (4 * H // 8) * sum(Ls)                  # two hidden layers per token, one bit per element
+
+
+def test_bind_host_to_gpu_is_a_hint_only():
+    """No NVML device behind a CPU 'device': the affinity helper must leave the process alone and not raise."""
+    import os
+    before = os.sched_getaffinity(0)
+    assert pkg.bind_host_to_gpu("cpu") == []
+    assert os.sched_getaffinity(0) == before

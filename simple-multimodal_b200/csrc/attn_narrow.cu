@@ -804,7 +804,9 @@ __global__ void __launch_bounds__(128, 2) attn_nq_fwd_kernel(const NarrowParams 
         if (DROP) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const uint32_t cm = drop_col_attn(uint32_t(key0 + nt * 8 + 2 * t + e));
+            // drop_col_attn(key0 + ...): key0 = 64 i + kw with kw + nt * 8 + 2 t + e < 64, so the 64-key group term is i * MulHi (hoisted per
+            // tile) and the in-group term needs no shift / mask per element
+            const uint32_t cm = (uint32_t(i) * kDropColMulHi) ^ (uint32_t(kw + nt * 8 + 2 * t + e) * kDropColMul);
             if (!drop_keep_c(rk[mt][0], cm, p.drop_thr)) pv[e] = 0.f;
             if (!drop_keep_c(rk[mt][1], cm, p.drop_thr)) pv[2 + e] = 0.f;
           }

@@ -95,3 +95,30 @@ def test_product_package_never_imports_the_oracle():
     src_dir = os.path.join(ROOT, "simple-multimodal_b200")
     for p in glob.glob(os.path.join(src_dir, "*.py")):
         assert not re.search(r"^\s*(from|import)\s+oracle\b", open(p).read(), re.M), p
+
+
+def test_ctypes_mirrors_have_the_size_and_field_offsets_of_the_c_structs(tmp_path):
+    """The Python binding restates b200f_gemm_args / b200f_attn_args field for field; a host compiler's view of the header (plain C, gcc)
+    must agree on the size and on the offset of every field -- a drifted mirror would hand the library garbage pointers."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no host C compiler")
+    L = importlib.import_module("simple-multimodal_b200._lib")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "b200_fusion.h"', "int main(void) {"]
+    for cname, cls in (("b200f_gemm_args", L.GemmArgs), ("b200f_attn_args", L.AttnArgs)):
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in (("b200f_gemm_args", L.GemmArgs), ("b200f_attn_args", L.AttnArgs)):
+        assert int(got[cname]) == C.sizeof(cls)
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
